@@ -1,0 +1,337 @@
+"""CPU oracle for the MPC planning hot path of iclavera/learning_to_adapt.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``learning_to_adapt_b200/`` may import this module;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs use it, and only as the checker / the timed CPU baseline, never as the product path.
+
+It is a numpy *restatement* (not a copy) of the reference's algorithm in the reference's exact
+dtype choreography: planner state and returns in float64, dense MLP in float32.
+All ``file:line`` citations are relative to the upstream tree (``/root/reference``).
+
+Pinning status (see DESIGN.md "Oracle"):
+  * planner loops (random shooting, CEM)  -- PINNED: ``tests/golden/make_golden.py`` runs the
+    verbatim reference ``MPCController`` (policies/mpc_controller.py) in the authoring container and the
+    golden fixtures hold its outputs; ``tests/test_oracle_golden.py`` checks this oracle against them.
+  * env ``reward`` closed forms            -- PINNED: fixtures come from the reference's own ``reward``
+    method bodies, executed from the upstream source text.
+  * ``predict`` / ``adapt`` host choreography (normalise, pad, task split, denormalise, delta add)
+                                           -- PINNED: fixtures come from the reference's own
+    ``MLPDynamicsModel.predict`` / ``MetaMLPDynamicsModel.{predict,_predict,_pad_inputs,adapt}`` bodies
+    run with a stub in place of the TF session.
+  * the TF1 graph itself (``tf.layers.dense`` forward, ``tf.gradients``)  -- PARITY UNPINNED:
+    TensorFlow 1.13.1 is not installable here (no wheels for py3.12, no network); the dense-layer math
+    ``act(x @ W + b)`` and the MSE gradient are restated from the published semantics and cross-checked
+    against torch autograd in ``tests/test_oracle_golden.py``.
+  * "ensemble = E" (BASELINE.json)         -- NO REFERENCE CODE exists; the aggregation
+    rule (mean of the E predicted deltas) is this build's definition.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+EPS = 1e-10  # mlp_dynamics.py:265-270
+
+REWARD_HALF_CHEETAH = 0
+REWARD_ANT = 1
+REWARD_ARM = 2
+REWARD_KINDS = {"half_cheetah": REWARD_HALF_CHEETAH, "ant": REWARD_ANT, "arm_7dof": REWARD_ARM}
+
+
+# --------------------------------------------------------------------------------------------------
+# parameters / normalisation
+# --------------------------------------------------------------------------------------------------
+def param_keys(n_hidden):
+    """Key order of the reference's param OrderedDict (core/utils.py:241-296, layers.py:142-171)."""
+    keys = []
+    for i in range(n_hidden):
+        keys += ["hidden_%d/kernel" % i, "hidden_%d/bias" % i]
+    keys += ["output/kernel", "output/bias"]
+    return keys
+
+
+def xavier_params(rng, in_dim, hidden_sizes, out_dim, out_scale=1.0):
+    """Xavier-uniform kernels [in, out] fp32, zero biases (core/utils.py:81-82 defaults)."""
+    sizes = [in_dim] + list(hidden_sizes) + [out_dim]
+    params = OrderedDict()
+    keys = param_keys(len(hidden_sizes))
+    for l in range(len(sizes) - 1):
+        lim = np.sqrt(6.0 / (sizes[l] + sizes[l + 1]))
+        w = rng.uniform(-lim, lim, size=(sizes[l], sizes[l + 1])).astype(np.float32)
+        if l == len(sizes) - 2:
+            w = (w * np.float32(out_scale)).astype(np.float32)
+        params[keys[2 * l]] = w
+        params[keys[2 * l + 1]] = np.zeros(sizes[l + 1], np.float32)
+    return params
+
+
+def make_normalization(rng, obs_dim, act_dim, act_low, act_high):
+    """Synthetic population stats in float64 (SURVEY.md 8(d) recipe)."""
+    norm = OrderedDict()
+    norm["obs"] = (rng.normal(0.0, 1.0, obs_dim), rng.uniform(0.5, 2.0, obs_dim))
+    norm["delta"] = (rng.normal(0.0, 0.01, obs_dim), rng.uniform(0.05, 0.2, obs_dim))
+    act_sigma = (np.asarray(act_high, np.float64) - np.asarray(act_low, np.float64)) / np.sqrt(12.0)
+    norm["act"] = (rng.normal(0.0, 0.1, act_dim), act_sigma * np.ones(act_dim))
+    return norm
+
+
+def normalize(x, mean, std):
+    return (x - mean) / (std + EPS)  # mlp_dynamics.py:265-266
+
+
+def denormalize(x, mean, std):
+    return x * (std + EPS) + mean  # mlp_dynamics.py:269-270
+
+
+# --------------------------------------------------------------------------------------------------
+# dense stack (tf.layers.dense semantics: act(x @ W + b), fp32)   core/utils.py:119-140, 241-296
+# --------------------------------------------------------------------------------------------------
+def mlp_forward(x32, params, keep_activations=False):
+    """x32: [n, in] float32.  Hidden ReLU, linear output."""
+    keys = list(params.keys())
+    n_layers = len(keys) // 2
+    h = np.ascontiguousarray(x32, dtype=np.float32)
+    acts = [h]
+    for l in range(n_layers):
+        w = params[keys[2 * l]]
+        b = params[keys[2 * l + 1]]
+        h = h @ w + b
+        if l < n_layers - 1:
+            h = np.maximum(h, np.float32(0.0))
+        if keep_activations:
+            acts.append(h)
+    return (h, acts) if keep_activations else h
+
+
+def f_delta_pred(obs_n, act_n, params):
+    """The TF placeholder feed casts float64 -> float32 (mlp_dynamics.py:63-68)."""
+    x = np.concatenate([obs_n, act_n], axis=1).astype(np.float32)
+    return mlp_forward(x, params)
+
+
+# --------------------------------------------------------------------------------------------------
+# one-step predict      mlp_dynamics.py:204-222 / meta_mlp_dynamics.py:276-306
+# --------------------------------------------------------------------------------------------------
+def predict(obs, act, params, norm):
+    obs = np.asarray(obs, np.float64)
+    act = np.asarray(act, np.float64)
+    obs_n = normalize(obs, *norm["obs"])
+    act_n = normalize(act, *norm["act"])
+    delta = np.array(f_delta_pred(obs_n, act_n, params))  # float32
+    delta = denormalize(delta, *norm["delta"])            # float32 * float64 -> float64
+    return obs + delta
+
+
+def predict_per_task(obs, act, param_sets, norm):
+    """GrBAL post-adapt predict: row chunk k (equal chunks) uses weight set k
+    (meta_mlp_dynamics.py:296-306 + inference graph 143-163).  Zero-padded tasks are not computed."""
+    obs = np.asarray(obs, np.float64)
+    act = np.asarray(act, np.float64)
+    k = len(param_sets)
+    assert obs.shape[0] % k == 0
+    obs_n = normalize(obs, *norm["obs"])
+    act_n = normalize(act, *norm["act"])
+    chunks_o = np.split(obs_n, k, axis=0)
+    chunks_a = np.split(act_n, k, axis=0)
+    delta = np.concatenate([f_delta_pred(o, a, p) for o, a, p in zip(chunks_o, chunks_a, param_sets)], axis=0)
+    delta = denormalize(delta, *norm["delta"])
+    return obs + delta
+
+
+def predict_ensemble_mean(obs, act, param_sets, norm):
+    """'ensemble=E' reading (ii): every row goes through all E sets; the E denormalised deltas are
+    averaged in float64, set order 0..E-1.  No reference code (see module docstring)."""
+    obs = np.asarray(obs, np.float64)
+    act = np.asarray(act, np.float64)
+    obs_n = normalize(obs, *norm["obs"])
+    act_n = normalize(act, *norm["act"])
+    acc = np.zeros_like(obs)
+    for p in param_sets:
+        acc = acc + denormalize(np.array(f_delta_pred(obs_n, act_n, p)), *norm["delta"])
+    return obs + acc / float(len(param_sets))
+
+
+# --------------------------------------------------------------------------------------------------
+# env reward closed forms
+# --------------------------------------------------------------------------------------------------
+def reward_fn(kind, dt):
+    if kind == REWARD_HALF_CHEETAH:   # envs/half_cheetah_env.py:58-65
+        def r(obs, action, next_obs):
+            ctrl_cost = 1e-1 * 0.5 * np.sum(np.square(action), axis=1)
+            return (next_obs[:, -3] - obs[:, -3]) / dt - ctrl_cost
+    elif kind == REWARD_ANT:          # envs/ant_env.py:56-66
+        def r(obs, action, next_obs):
+            return (next_obs[:, -3] - obs[:, -3]) / dt - 0 + 0.05
+    elif kind == REWARD_ARM:          # envs/arm_7dof_env.py:91-99
+        def r(obs, action, next_obs):
+            reward_dist = -np.linalg.norm(next_obs[:, -3:], axis=1)
+            reward_ctrl = -np.sum(np.square(action), axis=1)
+            return reward_dist + 0.01 * 0.5 * reward_ctrl
+    else:
+        raise ValueError(kind)
+    return r
+
+
+# --------------------------------------------------------------------------------------------------
+# planner: random shooting       policies/mpc_controller.py:108-129
+# --------------------------------------------------------------------------------------------------
+def _step_fn(param_sets, norm, mode):
+    if mode == "shared":
+        return lambda o, a: predict(o, a, param_sets[0], norm)
+    if mode == "per_env":
+        return lambda o, a: predict_per_task(o, a, param_sets, norm)
+    if mode == "ensemble":
+        return lambda o, a: predict_ensemble_mean(o, a, param_sets, norm)
+    raise ValueError(mode)
+
+
+def rollout_returns(observations, actions, param_sets, norm, reward_kind, dt, discount=1.0, mode="shared"):
+    """actions: [H, n*m, A] (row r belongs to env r // n).  Returns float64 [m, n]."""
+    observations = np.asarray(observations, np.float64)
+    actions = np.asarray(actions, np.float64)
+    h, rows, _ = actions.shape
+    m = observations.shape[0]
+    n = rows // m
+    assert n * m == rows
+    step = _step_fn(param_sets, norm, mode)
+    rew = reward_fn(reward_kind, dt)
+    returns = np.zeros((rows,))
+    observation = np.repeat(observations, n, axis=0)      # :119
+    for t in range(h):                                    # :116
+        next_observation = step(observation, actions[t])  # :120
+        rewards = rew(observation, actions[t], next_observation)  # :125
+        returns += discount ** t * rewards                # :126
+        observation = next_observation                    # :127
+    return returns.reshape(m, n)                          # :128
+
+
+def rs_plan(observations, actions, param_sets, norm, reward_kind, dt, discount=1.0, mode="shared"):
+    """Returns (chosen_actions [m, A] f64, best_idx [m], returns [m, n])."""
+    returns = rollout_returns(observations, actions, param_sets, norm, reward_kind, dt, discount, mode)
+    m, n = returns.shape
+    cand_a = np.asarray(actions, np.float64)[0].reshape(m, n, -1)   # :118
+    best = np.argmax(returns, axis=1)                                # :129 (first max wins ties)
+    return cand_a[range(m), best], best, returns
+
+
+# --------------------------------------------------------------------------------------------------
+# planner: CEM, bug-compatible       policies/mpc_controller.py:71-106   
+# --------------------------------------------------------------------------------------------------
+def cem_plan(observations, z_per_iter, act_low, act_high, param_sets, norm, reward_kind, dt, horizon,
+             percent_elites=0.1, alpha=0.1, discount=1.0, mode="shared", corrected=False):
+    """z_per_iter: list of standard-normal draws, each [n, m, H*A] (mpc_controller.py:85).
+    ``corrected=False`` reproduces the reference including the rank-mask defect (:101) and the use of
+    unclipped samples in the rollout (:88-89); ``corrected=True`` selects the true top-k as elites.
+    Returns (chosen_actions [m,A], best_idx [m], returns [m,n] of the last iteration, mean, std)."""
+    observations = np.asarray(observations, np.float64)
+    m = observations.shape[0]
+    n = z_per_iter[0].shape[0]
+    h = horizon
+    act_dim = len(act_low)
+    num_elites = max(int(n * percent_elites), 1)                 # :78
+    mean = np.zeros((m, h * act_dim))                            # :79
+    std = np.ones((m, h * act_dim))                              # :80
+    clip_low = np.concatenate([np.asarray(act_low, np.float64)] * h)   # :81
+    clip_high = np.concatenate([np.asarray(act_high, np.float64)] * h)  # :82
+    returns = None
+    cand_a = None
+    for z in z_per_iter:                                         # :84
+        a = mean + z * std                                       # :86
+        a_stacked = np.clip(a, clip_low, clip_high)              # :87
+        a = a.reshape((n * m, h, act_dim))                       # :88
+        a = np.transpose(a, (1, 0, 2))                           # :89  -> [H, n*m, A], UNclipped
+        cand_a = a[0].reshape((m, n, -1))                        # :94
+        returns = rollout_returns(observations, a, param_sets, norm, reward_kind, dt, discount, mode)
+        if corrected:
+            ranks = (-returns).argsort(axis=-1).argsort(axis=-1)
+            elites_idx = (ranks < num_elites).T
+        else:
+            elites_idx = ((-returns).argsort(axis=-1) < num_elites).T   # :101
+        elites = a_stacked[elites_idx]                           # :102
+        mean = mean * alpha + (1 - alpha) * np.mean(elites, axis=0)     # :103
+        std = np.std(elites, axis=0)                             # :104
+    best = np.argmax(returns, axis=1)
+    return cand_a[range(m), best], best, returns, mean, std      # :106
+
+
+# --------------------------------------------------------------------------------------------------
+# GrBAL adapt: one SGD step on the M-row context, from the prior, per task
+#   meta_mlp_dynamics.py:321-345 (host), 96-120 (graph), 409-421 (_adapt_sym)
+# --------------------------------------------------------------------------------------------------
+def adapt_one_task(x32, target32, params, inner_lr):
+    """x32 [M, D+A] normalised input, target32 [M, D] normalised delta, both float32.
+    loss = mean over M*D of (target - f(x))^2 (:118); theta' = theta - lr * dloss/dtheta (:409-421).
+    Manual fp32 backprop (what tf.gradients computes for a dense/ReLU stack)."""
+    keys = list(params.keys())
+    n_layers = len(keys) // 2
+    y, acts = mlp_forward(x32, params, keep_activations=True)
+    mrows, dout = y.shape
+    g = (np.float32(2.0) / np.float32(mrows * dout)) * (y - target32)      # dL/dy
+    new_params = OrderedDict()
+    for l in reversed(range(n_layers)):
+        w = params[keys[2 * l]]
+        h_in = acts[l]
+        gw = h_in.T @ g
+        gb = g.sum(axis=0)
+        new_params[keys[2 * l]] = (w - np.float32(inner_lr) * gw).astype(np.float32)
+        new_params[keys[2 * l + 1]] = (params[keys[2 * l + 1]] - np.float32(inner_lr) * gb).astype(np.float32)
+        if l > 0:
+            g = (g @ w.T) * (acts[l] > 0).astype(np.float32)
+    return OrderedDict((k, new_params[k]) for k in keys)
+
+
+def adapt(obs_list, act_list, obs_next_list, params, norm, inner_lr):
+    """obs_list: K arrays [M, D] etc. (sampler.py:83-90).  Returns K adapted OrderedDicts."""
+    out = []
+    for ob, ac, ob_next in zip(obs_list, act_list, obs_next_list):
+        ob = np.asarray(ob, np.float64)
+        ac = np.asarray(ac, np.float64)
+        ob_next = np.asarray(ob_next, np.float64)
+        obs_n = normalize(ob, *norm["obs"])                                  # :334-339
+        act_n = normalize(ac, *norm["act"])
+        delta_n = normalize(ob_next - ob, *norm["delta"])
+        x32 = np.concatenate([obs_n, act_n], axis=1).astype(np.float32)
+        out.append(adapt_one_task(x32, delta_n.astype(np.float32), params, inner_lr))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# seeded synthetic problem generator shared by tests / bench / golden generation
+# --------------------------------------------------------------------------------------------------
+ENV_SPECS = {
+    # name: (obs_dim, act_dim, ctrl_limit, dt, reward kind)
+    "half_cheetah": (20, 6, 1.0, 0.01, REWARD_HALF_CHEETAH),
+    "ant": (41, 8, 150.0, 0.02, REWARD_ANT),
+    "arm_7dof": (17, 7, 1.0, 0.02, REWARD_ARM),   # qpos 7 + qvel 7 + 3; ctrl range illustrative
+}
+
+
+def make_problem(env="half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=1, out_scale=0.1, seed=0):
+    obs_dim, act_dim, lim, dt, kind = ENV_SPECS[env]
+    low = -lim * np.ones(act_dim)
+    high = lim * np.ones(act_dim)
+    sets = [xavier_params(np.random.RandomState(1000 * seed + e), obs_dim + act_dim, hidden_sizes, obs_dim,
+                          out_scale=out_scale) for e in range(n_sets)]
+    norm = make_normalization(np.random.RandomState(seed + 1), obs_dim, act_dim, low, high)
+    rng = np.random.RandomState(seed + 2)
+    obs0 = norm["obs"][0] + norm["obs"][1] * rng.normal(size=(m, obs_dim))
+    return dict(env=env, obs_dim=obs_dim, act_dim=act_dim, low=low, high=high, dt=dt, reward_kind=kind,
+                param_sets=sets, norm=norm, obs0=obs0, hidden_sizes=tuple(hidden_sizes))
+
+
+def sample_rs_actions(seed, low, high, horizon, rows):
+    """The reference's own draw: uniform(low, high, (H*rows, A)).reshape(H, rows, A) (mpc_controller.py:67-69,114)."""
+    rng = np.random.RandomState(seed)
+    return rng.uniform(low=low, high=high, size=(horizon * rows,) + low.shape).reshape((horizon, rows, -1))
+
+
+def make_adapt_context(seed, prob, k, m_rows):
+    rng = np.random.RandomState(seed)
+    obs, act, nxt = [], [], []
+    for _ in range(k):
+        o = prob["norm"]["obs"][0] + prob["norm"]["obs"][1] * rng.normal(size=(m_rows, prob["obs_dim"]))
+        a = rng.uniform(prob["low"], prob["high"], size=(m_rows, prob["act_dim"]))
+        d = prob["norm"]["delta"][0] + prob["norm"]["delta"][1] * rng.normal(size=(m_rows, prob["obs_dim"]))
+        obs.append(o)
+        act.append(a)
+        nxt.append(o + d)
+    return obs, act, nxt
