@@ -1,0 +1,164 @@
+/*
+ * l2a_b200.h -- C ABI of the B200-native MPC planning engine (libl2a_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of iclavera/learning_to_adapt:
+ *   MPCController.get_actions  ->  {random shooting | CEM}  ->  H x dynamics_model.predict  ->
+ *   env.reward  ->  argmax,   plus GrBAL's one-gradient-step MetaMLPDynamicsModel.adapt.
+ *
+ * The reference has no FFI layer (pure Python over TF1); each entry point below names the reference
+ * Python call site (file:line, relative to the upstream tree) it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types in any signature.
+ *   - every function returns 0 on success or a negative l2a_status; the message of the last failure
+ *     on the calling thread is returned by l2a_last_error().  No exceptions cross the boundary.
+ *   - unless stated otherwise every data pointer is a DEVICE pointer to float32 (or int32) memory owned by
+ *     the caller (e.g. torch tensor .data_ptr()); the library only borrows it for the duration of the
+ *     stream-ordered call.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - calls on one l2a_ctx are not re-entrant; use one ctx per (process, device).
+ */
+#ifndef L2A_B200_H
+#define L2A_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L2A_MAX_LAYERS 8          /* dense layers incl. the output layer */
+
+typedef enum {
+  L2A_OK = 0,
+  L2A_ERR_INVALID = -1,           /* bad argument / unsupported shape */
+  L2A_ERR_CUDA = -2,              /* a CUDA runtime call failed */
+  L2A_ERR_UNSUPPORTED = -3,       /* no kernel for this configuration (there is NO CPU fallback) */
+  L2A_ERR_NO_DEVICE = -4
+} l2a_status;
+
+/* reward families = the closed forms of the reference env classes */
+typedef enum {
+  L2A_REWARD_HALF_CHEETAH = 0,    /* envs/half_cheetah_env.py:58-65 (+ _blocks_env.py:56-63, _hfield_env.py:59-66) */
+  L2A_REWARD_ANT = 1,             /* envs/ant_env.py:56-66 */
+  L2A_REWARD_ARM = 2              /* envs/arm_7dof_env.py:91-99 */
+} l2a_reward_kind;
+
+/* which weight set a candidate row is stepped through */
+typedef enum {
+  L2A_SETS_SHARED = 0,            /* every row uses set `first_set`            (mlp_dynamics.py:204-222) */
+  L2A_SETS_PER_ENV = 1,           /* rows of env k use set first_set + k       (meta_mlp_dynamics.py:296-306) */
+  L2A_SETS_ENSEMBLE_MEAN = 2      /* every row goes through n_sets sets, deltas averaged (BASELINE "ensemble") */
+} l2a_set_mode;
+
+typedef enum {
+  L2A_KERNEL_AUTO = 0,            /* tcgen05 when every hidden width is a multiple of 128, else SIMT */
+  L2A_KERNEL_SIMT = 1,            /* fp32 FFMA kernel, any shape */
+  L2A_KERNEL_TCGEN05 = 2          /* split-bf16 (3-pass) tcgen05.mma kernel, fp32 accumulate in TMEM */
+} l2a_kernel_choice;
+
+typedef struct l2a_ctx l2a_ctx;
+typedef struct l2a_model l2a_model;
+
+/* Shape of the dynamics MLP: [obs_dim + act_dim] -> hidden[0] -> ... -> hidden[n_hidden-1] -> obs_dim,
+ * ReLU hidden layers, linear output (dynamics/core/utils.py:75-142).  n_sets = weight sets resident at once
+ * (set 0 = prior theta; GrBAL adapted sets / ensemble members use the others). */
+typedef struct {
+  int32_t obs_dim;
+  int32_t act_dim;
+  int32_t n_hidden;
+  int32_t hidden[L2A_MAX_LAYERS - 1];
+  int32_t n_sets;
+} l2a_mlp_desc;
+
+typedef struct {
+  int32_t n_candidates;           /* N: candidates per env                        (mpc_controller.py:109) */
+  int32_t n_envs;                 /* m: observations planned in this call         (mpc_controller.py:110) */
+  int32_t horizon;                /* H                                            (mpc_controller.py:111) */
+  int32_t set_mode;               /* l2a_set_mode */
+  int32_t first_set;
+  int32_t n_sets;                 /* used by L2A_SETS_ENSEMBLE_MEAN */
+  int32_t reward_kind;            /* l2a_reward_kind */
+  float   dt;                     /* env.dt */
+  int64_t act_stride_t;           /* element strides of the candidate-action tensor: action j of row r at */
+  int64_t act_stride_row;         /*   step t is actions[t*act_stride_t + r*act_stride_row + j]           */
+  int32_t kernel;                 /* l2a_kernel_choice */
+  int32_t reserved;
+} l2a_rollout_params;
+
+const char* l2a_last_error(void);
+int l2a_version(void);
+
+/* ---- context (replaces tf.Session creation, trainers/mb_trainer.py:46-48) ------------------------------ */
+int l2a_ctx_create(int device, l2a_ctx** out);
+int l2a_ctx_destroy(l2a_ctx* ctx);
+/* number of this library's kernels launched on the ctx since creation (bench.py's gpu_launches) */
+int64_t l2a_ctx_launch_count(const l2a_ctx* ctx);
+
+/* ---- model storage (replaces the TF variables of dynamics/core/layers.py:142-171) --------------------- */
+int l2a_model_create(l2a_ctx* ctx, const l2a_mlp_desc* desc, l2a_model** out);
+int l2a_model_destroy(l2a_ctx* ctx, l2a_model* model);
+/* W[l]: device fp32 [in_l, out_l] row-major ("hidden_l/kernel"), b[l]: device fp32 [out_l]; W and b are HOST arrays
+ * of n_hidden+1 device pointers.  Values are copied (and re-tiled for the tensor-core path) before return of the
+ * stream-ordered work.  Replaces MLP.set_params (layers.py:81-101). */
+int l2a_model_set_params(l2a_ctx* ctx, l2a_model* model, int set, const float* const* W, const float* const* b,
+                         void* stream);
+/* copies set `set` out into caller-provided device buffers (MLP.get_param_values, layers.py:71-79) */
+int l2a_model_get_params(l2a_ctx* ctx, l2a_model* model, int set, float* const* W, float* const* b, void* stream);
+/* mean / denominators of the reference's normalize()/denormalize() (mlp_dynamics.py:265-270):
+ * x_n = (x - mean) / den with den = std + 1e-10 already folded in by the caller (in float64), and
+ * delta = y * delta_scale + delta_mean with delta_scale = std_delta + 1e-10.  Six device fp32 arrays. */
+int l2a_model_set_normalization(l2a_ctx* ctx, l2a_model* model, const float* obs_mean, const float* obs_den,
+                                const float* act_mean, const float* act_den, const float* delta_mean,
+                                const float* delta_scale, void* stream);
+
+/* ---- K1: fused H-step rollout + reward + per-env argmax ------------------------------------------------
+ * Replaces the body of MPCController.get_rs_action (policies/mpc_controller.py:116-129): H x predict
+ * (mlp_dynamics.py:204-222 / meta_mlp_dynamics.py:276-306), env.reward, discounted accumulate, np.argmax.
+ *   obs0          [m, D]       observation per env
+ *   actions       strided      candidate actions (see l2a_rollout_params); row r belongs to env r / N
+ *   discount_pow  [H]          discount**t, computed by the caller in float64 and rounded
+ *   returns       [m, N] or NULL
+ *   best_ret [m], best_idx [m] (int32, first max wins like np.argmax), best_act [m, A] = actions at t=0 of the winner */
+int l2a_rollout(l2a_ctx* ctx, l2a_model* model, const l2a_rollout_params* p, const float* obs0,
+                const float* actions, const float* discount_pow, float* returns, float* best_ret,
+                int32_t* best_idx, float* best_act, void* stream);
+
+/* ---- K4: one dynamics step (API compatibility) --------------------------------------------------------
+ * Replaces (Meta)MLPDynamicsModel.predict (mlp_dynamics.py:204-222, meta_mlp_dynamics.py:276-306).
+ * obs [n, D], act [n, A] raw (un-normalised).  set_mode SHARED: all rows use first_set; PER_ENV: n must be
+ * divisible by n_sets and row chunk k uses set first_set + k; ENSEMBLE_MEAN: mean over n_sets.
+ * Writes the denormalised delta [n, D] and/or next_obs = obs + delta [n, D] (either may be NULL). */
+int l2a_predict(l2a_ctx* ctx, l2a_model* model, int set_mode, int first_set, int n_sets, const float* obs,
+                const float* act, int n, float* delta_out, float* next_out, int kernel, void* stream);
+
+/* ---- K2: GrBAL one-step inner adaptation ---------------------------------------------------------------
+ * Replaces MetaMLPDynamicsModel.adapt (meta_mlp_dynamics.py:321-345) + _adapt_sym (409-421): for task k < K,
+ *   theta'_k = theta_src - inner_lr * d/dtheta mean_{M x D}( (target_k - f_theta(x_k))^2 ).
+ * x [K, M, D+A], target [K, M, D]: already normalised by the caller exactly as the reference does on the
+ * host (:334-339).  Result goes to weight sets dst_first_set .. dst_first_set+K-1. */
+int l2a_adapt(l2a_ctx* ctx, l2a_model* model, const float* x, const float* target, int K, int M, float inner_lr,
+              int src_set, int dst_first_set, void* stream);
+
+/* ---- K1c: CEM sampling / refit (policies/mpc_controller.py:84-104) -------------------------------------
+ * l2a_cem_sample: a = mean + z*std (:86) -> samples [n, m, H*A] fp32 (rolled out UNclipped, :88-89) and
+ *   clipped copy (:87).  mean/std are float64 [m, H*A]; z fp32 [n, m, H*A]; clip_low/high fp32 [H*A].
+ * l2a_cem_refit: elite selection + mean/std update (:101-104) from returns [m, n].
+ *   compat != 0 reproduces the reference's rank-mask defect (:101); compat == 0 takes the true top-k.
+ *   rank_scratch: int32 [m, n]. */
+int l2a_cem_sample(l2a_ctx* ctx, const float* z, const double* mean, const double* std, const float* clip_low,
+                   const float* clip_high, int n, int m, int ha, float* samples, float* clipped, void* stream);
+int l2a_cem_refit(l2a_ctx* ctx, const float* returns, const float* clipped, int n, int m, int ha, int num_elites,
+                  double alpha, int compat, int32_t* rank_scratch, double* mean, double* std, void* stream);
+
+/* ---- diagnostics -----------------------------------------------------------------------------------------
+ * Single tcgen05 GEMM tile through the same descriptor / TMEM code as the rollout kernel:
+ * C[128, n] = A[128, k] * B[n, k]^T with A, B fp32 split into bf16 hi/lo on the device. */
+int l2a_debug_umma_tile(l2a_ctx* ctx, const float* A, const float* B, float* C, int n, int k, int variant,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L2A_B200_H */

@@ -1,0 +1,77 @@
+"""ctypes binding of libl2a_b200.so (include/l2a_b200.h).  There is no CPU fallback: if the shared library is
+missing or no B200 is present the product path raises."""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+L2A_MAX_LAYERS = 8
+
+REWARD_HALF_CHEETAH, REWARD_ANT, REWARD_ARM = 0, 1, 2
+SETS_SHARED, SETS_PER_ENV, SETS_ENSEMBLE_MEAN = 0, 1, 2
+KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05 = 0, 1, 2
+
+EXPORTS = [
+    "l2a_last_error", "l2a_version", "l2a_ctx_create", "l2a_ctx_destroy", "l2a_ctx_launch_count",
+    "l2a_model_create", "l2a_model_destroy", "l2a_model_set_params", "l2a_model_get_params",
+    "l2a_model_set_normalization", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
+    "l2a_debug_umma_tile",
+]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("n_hidden", C.c_int32),
+                ("hidden", C.c_int32 * (L2A_MAX_LAYERS - 1)), ("n_sets", C.c_int32)]
+
+
+class RolloutParams(C.Structure):
+    _fields_ = [("n_candidates", C.c_int32), ("n_envs", C.c_int32), ("horizon", C.c_int32), ("set_mode", C.c_int32),
+                ("first_set", C.c_int32), ("n_sets", C.c_int32), ("reward_kind", C.c_int32), ("dt", C.c_float),
+                ("act_stride_t", C.c_int64), ("act_stride_row", C.c_int64), ("kernel", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes.  Raises ImportError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "learning_to_adapt_b200: %s is missing. Build it with `python -m learning_to_adapt_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback for the planning path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    pp = C.POINTER(vp)
+    lib.l2a_last_error.restype = C.c_char_p
+    lib.l2a_last_error.argtypes = []
+    lib.l2a_version.restype = i32
+    lib.l2a_ctx_create.argtypes = [i32, pp]
+    lib.l2a_ctx_destroy.argtypes = [vp]
+    lib.l2a_ctx_launch_count.argtypes = [vp]
+    lib.l2a_ctx_launch_count.restype = i64
+    lib.l2a_model_create.argtypes = [vp, C.POINTER(MlpDesc), pp]
+    lib.l2a_model_destroy.argtypes = [vp, vp]
+    lib.l2a_model_set_params.argtypes = [vp, vp, i32, pp, pp, vp]
+    lib.l2a_model_get_params.argtypes = [vp, vp, i32, pp, pp, vp]
+    lib.l2a_model_set_normalization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
+    lib.l2a_adapt.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]
+    lib.l2a_cem_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.l2a_cem_refit.argtypes = [vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp]
+    lib.l2a_debug_umma_tile.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("l2a_last_error", "l2a_ctx_launch_count"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("libl2a_b200: %s (status %d)" % (load().l2a_last_error().decode(), status))

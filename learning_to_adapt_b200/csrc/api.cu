@@ -1,0 +1,564 @@
+// libl2a_b200.so -- C ABI of the B200-native MPC planning engine (see include/l2a_b200.h).
+// Host side: argument validation, workspace management, kernel selection and launches.  sm_100a only.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "adapt.cuh"
+#include "cem.cuh"
+#include "common.cuh"
+#include "debug_tile.cuh"
+#include "rollout_simt.cuh"
+#include "rollout_tc.cuh"
+
+using namespace l2a;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(L2A_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                              \
+  } while (0)
+
+struct l2a_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  long long launches = 0;
+  // per-env reduction workspace
+  float* part_ret = nullptr;
+  int* part_idx = nullptr;
+  unsigned int* counters = nullptr;
+  size_t part_cap = 0, counter_cap = 0;
+  // adapt workspace
+  float* adapt_acts = nullptr;
+  float* adapt_grads = nullptr;
+  size_t adapt_acts_cap = 0, adapt_grads_cap = 0;
+};
+
+struct l2a_model {
+  l2a_mlp_desc desc;
+  MlpDims dims;
+  TcPlan plan;
+  bool tc_ok = false;
+  float* params = nullptr;     // [n_sets][set_stride]
+  uint8_t* blobs = nullptr;    // [n_sets][plan.set_bytes]
+  float* norm = nullptr;       // obs_mean[D] obs_den[D] act_mean[A] act_den[A] delta_mean[D] delta_scale[D]
+  bool norm_set = false;
+  NormDev norm_dev() const {
+    const int D = dims.obs_dim, A = dims.act_dim;
+    NormDev n;
+    n.obs_mean = norm;
+    n.obs_den = norm + D;
+    n.act_mean = norm + 2 * D;
+    n.act_den = norm + 2 * D + A;
+    n.delta_mean = norm + 2 * D + 2 * A;
+    n.delta_scale = norm + 3 * D + 2 * A;
+    return n;
+  }
+};
+
+extern "C" const char* l2a_last_error(void) { return g_err; }
+extern "C" int l2a_version(void) { return 100; }
+
+extern "C" int l2a_ctx_create(int device, l2a_ctx** out) {
+  if (!out) return fail(L2A_ERR_INVALID, "out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(L2A_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(L2A_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(L2A_ERR_UNSUPPORTED, "device %d is sm_%d%d; libl2a_b200 is built for sm_100a (B200) only", device, prop.major,
+                prop.minor);
+  l2a_ctx* c = new (std::nothrow) l2a_ctx();
+  if (!c) return fail(L2A_ERR_INVALID, "out of host memory");
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = c;
+  return L2A_OK;
+}
+
+extern "C" int l2a_ctx_destroy(l2a_ctx* c) {
+  if (!c) return L2A_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->part_ret);
+  cudaFree(c->part_idx);
+  cudaFree(c->counters);
+  cudaFree(c->adapt_acts);
+  cudaFree(c->adapt_grads);
+  delete c;
+  return L2A_OK;
+}
+
+extern "C" int64_t l2a_ctx_launch_count(const l2a_ctx* c) { return c ? c->launches : 0; }
+
+// --------------------------------------------------------------------------------------------- model
+extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** out) {
+  if (!c || !d || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (d->n_hidden < 1 || d->n_hidden > kMaxLayers - 1) return fail(L2A_ERR_INVALID, "n_hidden %d not in [1,%d]", d->n_hidden, kMaxLayers - 1);
+  if (d->obs_dim < 3 || d->act_dim < 1 || d->n_sets < 1) return fail(L2A_ERR_INVALID, "bad obs_dim/act_dim/n_sets");
+  CUDA_TRY(cudaSetDevice(c->device));
+  l2a_model* m = new (std::nothrow) l2a_model();
+  if (!m) return fail(L2A_ERR_INVALID, "out of host memory");
+  m->desc = *d;
+  MlpDims& md = m->dims;
+  memset(&md, 0, sizeof(md));
+  md.n_layers = d->n_hidden + 1;
+  md.obs_dim = d->obs_dim;
+  md.act_dim = d->act_dim;
+  md.dims[0] = d->obs_dim + d->act_dim;
+  for (int i = 0; i < d->n_hidden; ++i) {
+    if (d->hidden[i] < 1) { delete m; return fail(L2A_ERR_INVALID, "hidden[%d] = %d", i, d->hidden[i]); }
+    md.dims[i + 1] = d->hidden[i];
+  }
+  md.dims[md.n_layers] = d->obs_dim;
+  int off = 0, maxw = 0;
+  for (int l = 0; l < md.n_layers; ++l) {
+    md.w_off[l] = off;
+    off += md.dims[l] * md.dims[l + 1];
+    md.b_off[l] = off;
+    off += md.dims[l + 1];
+    off = (off + 3) & ~3;                        // keep every kernel 16-byte aligned
+  }
+  for (int l = 0; l <= md.n_layers; ++l) maxw = std::max(maxw, md.dims[l]);
+  md.set_stride = off;
+  md.max_width = maxw;
+  m->tc_ok = tc_make_plan(md, &m->plan);
+  const size_t pbytes = (size_t)d->n_sets * md.set_stride * sizeof(float);
+  if (cudaMalloc(&m->params, pbytes) != cudaSuccess) { delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(params, %zu)", pbytes); }
+  cudaMemset(m->params, 0, pbytes);
+  if (m->tc_ok) {
+    const size_t bbytes = (size_t)d->n_sets * (size_t)m->plan.set_bytes;
+    if (cudaMalloc(&m->blobs, bbytes) != cudaSuccess) { cudaFree(m->params); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(blobs, %zu)", bbytes); }
+    cudaMemset(m->blobs, 0, bbytes);
+  }
+  const size_t nbytes = sizeof(float) * (size_t)(4 * d->obs_dim + 2 * d->act_dim);
+  if (cudaMalloc(&m->norm, nbytes) != cudaSuccess) { cudaFree(m->params); cudaFree(m->blobs); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(norm)"); }
+  *out = m;
+  return L2A_OK;
+}
+
+extern "C" int l2a_model_destroy(l2a_ctx* c, l2a_model* m) {
+  if (!m) return L2A_OK;
+  if (c) cudaSetDevice(c->device);
+  cudaFree(m->params);
+  cudaFree(m->blobs);
+  cudaFree(m->norm);
+  delete m;
+  return L2A_OK;
+}
+
+static int launch_prep(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, cudaStream_t st) {
+  if (!m->tc_ok) return L2A_OK;
+  PrepArgs pa;
+  pa.dims = m->dims;
+  pa.plan = m->plan;
+  pa.params = m->params;
+  pa.blobs = m->blobs;
+  pa.first_set = first_set;
+  dim3 grid(m->plan.tiles_per_set / 2, n_sets);
+  tc_prep_kernel<<<grid, 256, 0, st>>>(pa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+extern "C" int l2a_model_set_params(l2a_ctx* c, l2a_model* m, int set, const float* const* W, const float* const* b, void* stream) {
+  if (!c || !m || !W || !b) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (set < 0 || set >= m->desc.n_sets) return fail(L2A_ERR_INVALID, "set %d out of range [0,%d)", set, m->desc.n_sets);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const MlpDims& md = m->dims;
+  float* base = m->params + (size_t)set * md.set_stride;
+  for (int l = 0; l < md.n_layers; ++l) {
+    if (!W[l] || !b[l]) return fail(L2A_ERR_INVALID, "W[%d] or b[%d] is NULL", l, l);
+    CUDA_TRY(cudaMemcpyAsync(base + md.w_off[l], W[l], sizeof(float) * (size_t)md.dims[l] * md.dims[l + 1], cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + md.b_off[l], b[l], sizeof(float) * (size_t)md.dims[l + 1], cudaMemcpyDeviceToDevice, st));
+  }
+  return launch_prep(c, m, set, 1, st);
+}
+
+extern "C" int l2a_model_get_params(l2a_ctx* c, l2a_model* m, int set, float* const* W, float* const* b, void* stream) {
+  if (!c || !m || !W || !b) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (set < 0 || set >= m->desc.n_sets) return fail(L2A_ERR_INVALID, "set %d out of range [0,%d)", set, m->desc.n_sets);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const MlpDims& md = m->dims;
+  const float* base = m->params + (size_t)set * md.set_stride;
+  for (int l = 0; l < md.n_layers; ++l) {
+    CUDA_TRY(cudaMemcpyAsync(W[l], base + md.w_off[l], sizeof(float) * (size_t)md.dims[l] * md.dims[l + 1], cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b[l], base + md.b_off[l], sizeof(float) * (size_t)md.dims[l + 1], cudaMemcpyDeviceToDevice, st));
+  }
+  return L2A_OK;
+}
+
+extern "C" int l2a_model_set_normalization(l2a_ctx* c, l2a_model* m, const float* obs_mean, const float* obs_den,
+                                           const float* act_mean, const float* act_den, const float* delta_mean,
+                                           const float* delta_scale, void* stream) {
+  if (!c || !m || !obs_mean || !obs_den || !act_mean || !act_den || !delta_mean || !delta_scale)
+    return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dims.obs_dim, A = m->dims.act_dim;
+  NormDev n = m->norm_dev();
+  CUDA_TRY(cudaMemcpyAsync((void*)n.obs_mean, obs_mean, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.obs_den, obs_den, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.act_mean, act_mean, sizeof(float) * A, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.act_den, act_den, sizeof(float) * A, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.delta_mean, delta_mean, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.delta_scale, delta_scale, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  m->norm_set = true;
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- workspace
+static int ensure_reduce_ws(l2a_ctx* c, size_t n_part, size_t n_env, cudaStream_t st) {
+  if (n_part > c->part_cap) {
+    cudaFree(c->part_ret);
+    cudaFree(c->part_idx);
+    c->part_ret = nullptr;
+    c->part_idx = nullptr;
+    c->part_cap = 0;
+    const size_t cap = std::max<size_t>(n_part * 2, 4096);
+    CUDA_TRY(cudaMalloc(&c->part_ret, cap * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->part_idx, cap * sizeof(int)));
+    c->part_cap = cap;
+  }
+  if (n_env > c->counter_cap) {
+    cudaFree(c->counters);
+    c->counters = nullptr;
+    c->counter_cap = 0;
+    const size_t cap = std::max<size_t>(n_env * 2, 1024);
+    CUDA_TRY(cudaMalloc(&c->counters, cap * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(c->counters, 0, cap * sizeof(unsigned int), st));
+    c->counter_cap = cap;
+  }
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- rollout
+template <int NC>
+static int launch_tc(l2a_ctx* c, const TcArgs& ta, int csize, cudaStream_t st) {
+  const size_t smem = TcSmem<NC>::total(ta.dims.obs_dim, ta.dims.act_dim);
+  if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "tcgen05 rollout needs %zu B shared memory (> %d)", smem, c->max_smem_optin);
+  CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(ta.n_envs * ta.groups_per_env * csize));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, rollout_tc_kernel<NC>, ta));
+  c->launches++;
+  return L2A_OK;
+}
+
+static int pick_nc(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
+  static const int opts[4] = {80, 64, 48, 32};
+  int best = 80;
+  double best_cost = 1e300;
+  const int slots = std::max(1, c->num_sms / csize);           // clusters resident at once (1 CTA / SM)
+  for (int i = 0; i < 4; ++i) {
+    const int nc = opts[i];
+    const long long clusters = (long long)n_envs * ((n_cand + nc - 1) / nc);
+    const long long waves = (clusters + slots - 1) / slots;
+    const double cost = (double)waves * (48.0 + nc);           // fixed per-step weight-stream cost + N-proportional MMA time
+    if (cost < best_cost) { best_cost = cost; best = nc; }
+  }
+  return best;
+}
+
+extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p, const float* obs0, const float* actions,
+                           const float* discount_pow, float* returns, float* best_ret, int32_t* best_idx, float* best_act,
+                           void* stream) {
+  if (!c || !m || !p || !obs0 || !actions || !discount_pow || !best_ret || !best_idx || !best_act)
+    return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!m->norm_set) return fail(L2A_ERR_INVALID, "normalization not set (l2a_model_set_normalization)");
+  if (p->n_candidates < 1 || p->n_envs < 1 || p->horizon < 1) return fail(L2A_ERR_INVALID, "n_candidates/n_envs/horizon must be >= 1");
+  if (p->reward_kind < 0 || p->reward_kind > 2) return fail(L2A_ERR_INVALID, "reward_kind %d", p->reward_kind);
+  if (!(p->dt > 0.f)) return fail(L2A_ERR_INVALID, "dt must be > 0");
+  int last_set = p->first_set;
+  if (p->set_mode == L2A_SETS_PER_ENV) last_set = p->first_set + p->n_envs - 1;
+  else if (p->set_mode == L2A_SETS_ENSEMBLE_MEAN) {
+    if (p->n_sets < 1) return fail(L2A_ERR_INVALID, "n_sets must be >= 1");
+    last_set = p->first_set + p->n_sets - 1;
+  } else if (p->set_mode != L2A_SETS_SHARED) return fail(L2A_ERR_INVALID, "set_mode %d", p->set_mode);
+  if (p->first_set < 0 || last_set >= m->desc.n_sets)
+    return fail(L2A_ERR_INVALID, "weight sets [%d,%d] out of range [0,%d)", p->first_set, last_set, m->desc.n_sets);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+
+  int kernel = p->kernel;
+  const int csize = (p->set_mode == L2A_SETS_ENSEMBLE_MEAN) ? p->n_sets : 1;
+  const bool tc_possible = m->tc_ok && csize <= 8;
+  if (kernel == L2A_KERNEL_AUTO) kernel = tc_possible ? L2A_KERNEL_TCGEN05 : L2A_KERNEL_SIMT;
+  if (kernel == L2A_KERNEL_TCGEN05 && !tc_possible)
+    return fail(L2A_ERR_UNSUPPORTED, "tcgen05 rollout needs hidden widths that are multiples of 128 (<= 512), obs_dim <= 128, "
+                                     "act_dim <= 16 and <= 8 ensemble members");
+
+  ReduceArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.best_ret = best_ret;
+  ra.best_idx = best_idx;
+  ra.best_act = best_act;
+  ra.actions = actions;
+  ra.act_stride_row = p->act_stride_row;
+  ra.act_dim = m->dims.act_dim;
+  ra.n_candidates = p->n_candidates;
+
+  if (kernel == L2A_KERNEL_SIMT) {
+    const int tiles = (p->n_candidates + kSimtRT - 1) / kSimtRT;
+    int rc = ensure_reduce_ws(c, (size_t)tiles * p->n_envs, p->n_envs, st);
+    if (rc) return rc;
+    ra.part_ret = c->part_ret;
+    ra.part_idx = c->part_idx;
+    ra.counters = c->counters;
+    ra.tiles_per_env = tiles;
+    SimtArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.dims = m->dims;
+    sa.norm = m->norm_dev();
+    sa.params = m->params;
+    sa.obs = obs0;
+    sa.actions = actions;
+    sa.act_stride_t = p->act_stride_t;
+    sa.act_stride_row = p->act_stride_row;
+    sa.discount_pow = discount_pow;
+    sa.rows_per_group = p->n_candidates;
+    sa.n_groups = p->n_envs;
+    sa.horizon = p->horizon;
+    sa.set_mode = p->set_mode;
+    sa.first_set = p->first_set;
+    sa.n_sets = p->n_sets;
+    sa.reward_kind = p->reward_kind;
+    sa.dt = p->dt;
+    sa.returns = returns;
+    sa.red = ra;
+    const size_t smem = simt_smem_bytes(m->dims);
+    if ((int)smem > c->max_smem_optin)
+      return fail(L2A_ERR_UNSUPPORTED, "SIMT rollout needs %zu B shared memory (> %d): layer width %d too large", smem, c->max_smem_optin, m->dims.max_width);
+    CUDA_TRY(cudaFuncSetAttribute(rollout_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_simt_kernel<false><<<(unsigned)(tiles * p->n_envs), kSimtThreads, smem, st>>>(sa);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return L2A_OK;
+  }
+
+  const int nc = pick_nc(c, p->n_candidates, p->n_envs, csize);
+  const int groups = (p->n_candidates + nc - 1) / nc;
+  int rc = ensure_reduce_ws(c, (size_t)groups * p->n_envs, p->n_envs, st);
+  if (rc) return rc;
+  ra.part_ret = c->part_ret;
+  ra.part_idx = c->part_idx;
+  ra.counters = c->counters;
+  ra.tiles_per_env = groups;
+  TcArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.dims = m->dims;
+  ta.plan = m->plan;
+  ta.norm = m->norm_dev();
+  ta.params = m->params;
+  ta.blobs = m->blobs;
+  ta.obs0 = obs0;
+  ta.actions = actions;
+  ta.act_stride_t = p->act_stride_t;
+  ta.act_stride_row = p->act_stride_row;
+  ta.discount_pow = discount_pow;
+  ta.n_candidates = p->n_candidates;
+  ta.n_envs = p->n_envs;
+  ta.horizon = p->horizon;
+  ta.set_mode = p->set_mode;
+  ta.first_set = p->first_set;
+  ta.n_sets = p->n_sets;
+  ta.reward_kind = p->reward_kind;
+  ta.dt = p->dt;
+  ta.groups_per_env = groups;
+  ta.returns = returns;
+  ta.red = ra;
+  switch (nc) {
+    case 80: return launch_tc<80>(c, ta, csize, st);
+    case 64: return launch_tc<64>(c, ta, csize, st);
+    case 48: return launch_tc<48>(c, ta, csize, st);
+    default: return launch_tc<32>(c, ta, csize, st);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- predict
+extern "C" int l2a_predict(l2a_ctx* c, l2a_model* m, int set_mode, int first_set, int n_sets, const float* obs,
+                           const float* act, int n, float* delta_out, float* next_out, int kernel, void* stream) {
+  if (!c || !m || !obs || !act) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!delta_out && !next_out) return fail(L2A_ERR_INVALID, "both outputs are NULL");
+  if (!m->norm_set) return fail(L2A_ERR_INVALID, "normalization not set");
+  if (n < 1) return fail(L2A_ERR_INVALID, "n must be >= 1");
+  if (kernel == L2A_KERNEL_TCGEN05) return fail(L2A_ERR_UNSUPPORTED, "one-step predict runs on the SIMT kernel");
+  int groups = 1, rows = n, last_set = first_set;
+  if (set_mode == L2A_SETS_PER_ENV) {
+    if (n_sets < 1 || n % n_sets != 0) return fail(L2A_ERR_INVALID, "n=%d is not divisible by n_sets=%d", n, n_sets);
+    groups = n_sets;
+    rows = n / n_sets;
+    last_set = first_set + n_sets - 1;
+  } else if (set_mode == L2A_SETS_ENSEMBLE_MEAN) {
+    if (n_sets < 1) return fail(L2A_ERR_INVALID, "n_sets must be >= 1");
+    last_set = first_set + n_sets - 1;
+  } else if (set_mode != L2A_SETS_SHARED) return fail(L2A_ERR_INVALID, "set_mode %d", set_mode);
+  if (first_set < 0 || last_set >= m->desc.n_sets) return fail(L2A_ERR_INVALID, "weight sets [%d,%d] out of range", first_set, last_set);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  SimtArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.dims = m->dims;
+  sa.norm = m->norm_dev();
+  sa.params = m->params;
+  sa.obs = obs;
+  sa.actions = act;
+  sa.act_stride_t = 0;
+  sa.act_stride_row = m->dims.act_dim;
+  sa.rows_per_group = rows;
+  sa.n_groups = groups;
+  sa.horizon = 1;
+  sa.set_mode = set_mode;
+  sa.first_set = first_set;
+  sa.n_sets = n_sets;
+  sa.delta_out = delta_out;
+  sa.next_out = next_out;
+  const size_t smem = simt_smem_bytes(m->dims);
+  if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "predict needs %zu B shared memory (> %d)", smem, c->max_smem_optin);
+  CUDA_TRY(cudaFuncSetAttribute(rollout_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (rows + kSimtRT - 1) / kSimtRT;
+  rollout_simt_kernel<true><<<(unsigned)(tiles * groups), kSimtThreads, smem, st>>>(sa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- adapt
+extern "C" int l2a_adapt(l2a_ctx* c, l2a_model* m, const float* x, const float* target, int K, int M, float inner_lr,
+                         int src_set, int dst_first_set, void* stream) {
+  if (!c || !m || !x || !target) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (K < 1 || M < 1 || M > kAdaptMaxM) return fail(L2A_ERR_INVALID, "K=%d, M=%d: need K >= 1 and 1 <= M <= %d", K, M, kAdaptMaxM);
+  if (src_set < 0 || src_set >= m->desc.n_sets || dst_first_set < 0 || dst_first_set + K > m->desc.n_sets)
+    return fail(L2A_ERR_INVALID, "src_set %d / dst sets [%d,%d) out of range [0,%d)", src_set, dst_first_set, dst_first_set + K, m->desc.n_sets);
+  if (src_set >= dst_first_set && src_set < dst_first_set + K) return fail(L2A_ERR_INVALID, "src_set inside the destination range");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const MlpDims& md = m->dims;
+  AdaptArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.dims = md;
+  int ao = 0, go = 0;
+  for (int l = 0; l < md.n_layers; ++l) {
+    aa.act_off[l] = ao;
+    ao += md.dims[l] * M;
+    aa.grad_off[l] = go;
+    go += md.dims[l + 1] * M;
+  }
+  aa.act_off[md.n_layers] = ao;
+  aa.grad_off[md.n_layers] = go;
+  const size_t need_a = (size_t)K * ao, need_g = (size_t)K * go;
+  if (need_a > c->adapt_acts_cap) {
+    cudaFree(c->adapt_acts);
+    c->adapt_acts = nullptr;
+    c->adapt_acts_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->adapt_acts, need_a * 2 * sizeof(float)));
+    c->adapt_acts_cap = need_a * 2;
+  }
+  if (need_g > c->adapt_grads_cap) {
+    cudaFree(c->adapt_grads);
+    c->adapt_grads = nullptr;
+    c->adapt_grads_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->adapt_grads, need_g * 2 * sizeof(float)));
+    c->adapt_grads_cap = need_g * 2;
+  }
+  aa.params = m->params;
+  aa.params_out = m->params;
+  aa.src_set = src_set;
+  aa.dst_first_set = dst_first_set;
+  aa.x = x;
+  aa.target = target;
+  aa.K = K;
+  aa.M = M;
+  aa.lr = inner_lr;
+  aa.acts = c->adapt_acts;
+  aa.grads = c->adapt_grads;
+  adapt_fwd_bwd_kernel<<<K, kAdaptThreads, 0, st>>>(aa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  int max_elems = 0;
+  for (int l = 0; l < md.n_layers; ++l) max_elems = std::max(max_elems, md.dims[l] * md.dims[l + 1] + md.dims[l + 1]);
+  dim3 grid((max_elems + 256 * 4 - 1) / (256 * 4), md.n_layers, K);
+  adapt_update_kernel<<<grid, 256, 0, st>>>(aa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return launch_prep(c, m, dst_first_set, K, st);
+}
+
+// --------------------------------------------------------------------------------------------- CEM
+extern "C" int l2a_cem_sample(l2a_ctx* c, const float* z, const double* mean, const double* std_, const float* clip_low,
+                              const float* clip_high, int n, int m, int ha, float* samples, float* clipped, void* stream) {
+  if (!c || !z || !mean || !std_ || !clip_low || !clip_high || !samples || !clipped) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (n < 1 || m < 1 || ha < 1) return fail(L2A_ERR_INVALID, "n/m/ha must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const long long total = (long long)n * m * ha;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->num_sms * 8);
+  cem_sample_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, mean, std_, clip_low, clip_high, n, m, ha, samples, clipped);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+extern "C" int l2a_cem_refit(l2a_ctx* c, const float* returns, const float* clipped, int n, int m, int ha, int num_elites,
+                             double alpha, int compat, int32_t* rank_scratch, double* mean, double* std_, void* stream) {
+  if (!c || !returns || !clipped || !rank_scratch || !mean || !std_) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (n < 1 || m < 1 || ha < 1 || num_elites < 1 || num_elites > n) return fail(L2A_ERR_INVALID, "bad n/m/ha/num_elites");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g1((n + 255) / 256, m);
+  cem_rank_kernel<<<g1, 256, 0, st>>>(returns, n, rank_scratch);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  cem_refit_kernel<<<ha, 256, 0, st>>>(rank_scratch, clipped, n, m, ha, num_elites, alpha, compat, mean, std_);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- diagnostics
+extern "C" int l2a_debug_umma_tile(l2a_ctx* c, const float* A, const float* B, float* C, int n, int k, int variant, void* stream) {
+  if (!c || !A || !B || !C) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (n < 16 || n > 128 || n % 16 != 0 || k < 64 || k > 256 || k % 64 != 0) return fail(L2A_ERR_INVALID, "need n in {16..128} %% 16, k in {64..256} %% 64");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int nkc = k / 64;
+  const size_t smem = (size_t)2 * nkc * 16384 + (size_t)2 * nkc * n * 128 + 64 + 1024;
+  CUDA_TRY(cudaFuncSetAttribute(debug_umma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  debug_umma_tile_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, n, k, variant);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}

@@ -1,0 +1,77 @@
+// Diagnostics: one split-bf16 tcgen05 GEMM tile through the exact descriptor / swizzle / TMEM-load code of the rollout
+// kernel.  C[128, n] = A[128, k] * B[n, k]^T, fp32 in / out, k % 64 == 0 (k <= 256), n % 16 == 0 (n <= 128).
+#pragma once
+#include "umma.cuh"
+
+namespace l2a {
+
+__global__ void __launch_bounds__(128, 1) debug_umma_tile_kernel(const float* A, const float* B, float* C, int n, int k,
+                                                                 int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nkc = k / 64;
+  const int b_chunk = n * 128;
+  uint8_t* a_hi = smem;                                  // nkc tiles of 16 KB
+  uint8_t* a_lo = a_hi + (size_t)nkc * 16384;
+  uint8_t* b_hi = a_lo + (size_t)nkc * 16384;            // nkc chunks of n*128 B (1024-aligned when n % 8 == 0)
+  uint8_t* b_lo = b_hi + (size_t)nkc * b_chunk;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + (size_t)nkc * b_chunk);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  for (int idx = tid; idx < 128 * k; idx += 128) {
+    const int r = idx / k, c = idx % k;
+    uint16_t hi, lo;
+    umma::split_bf16(A[idx], hi, lo);
+    const uint32_t off = (uint32_t)(c >> 6) * 16384u + umma::sw128_offset(r, c & 63);
+    *reinterpret_cast<uint16_t*>(a_hi + off) = hi;
+    *reinterpret_cast<uint16_t*>(a_lo + off) = lo;
+  }
+  for (int idx = tid; idx < n * k; idx += 128) {
+    const int r = idx / k, c = idx % k;
+    uint16_t hi, lo;
+    umma::split_bf16(B[idx], hi, lo);
+    const uint32_t off = (uint32_t)(c >> 6) * b_chunk + umma::sw128_offset(r, c & 63);
+    *reinterpret_cast<uint16_t*>(b_hi + off) = hi;
+    *reinterpret_cast<uint16_t*>(b_lo + off) = lo;
+  }
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
+  if (warp == 0) umma::tmem_alloc<128>(tmem_slot);
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int passes = (variant & 4) ? 1 : 3;              // variant bit 2: single bf16 pass (hi*hi only)
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_bf16(128, (uint32_t)n);
+    uint32_t acc = 0;
+    for (int kc = 0; kc < nkc; ++kc)
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ah = umma::make_desc_sw128(umma::smem_u32(a_hi) + kc * 16384 + ks * 32, variant & 3);
+        const uint64_t al = umma::make_desc_sw128(umma::smem_u32(a_lo) + kc * 16384 + ks * 32, variant & 3);
+        const uint64_t bh = umma::make_desc_sw128(umma::smem_u32(b_hi) + kc * b_chunk + ks * 32, variant & 3);
+        const uint64_t bl = umma::make_desc_sw128(umma::smem_u32(b_lo) + kc * b_chunk + ks * 32, variant & 3);
+        umma::mma_bf16_ss(tmem_base, ah, bh, idesc, acc);
+        acc = 1;
+        if (passes == 3) {
+          umma::mma_bf16_ss(tmem_base, ah, bl, idesc, 1u);
+          umma::mma_bf16_ss(tmem_base, al, bh, idesc, 1u);
+        }
+      }
+    umma::mma_commit(bar);
+  }
+  umma::mbar_wait(bar, 0);
+  umma::tc_fence_after();
+  for (int c16 = 0; c16 < n / 16; ++c16) {
+    uint32_t r[16];
+    umma::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c16 * 16), r);
+    umma::tmem_ld_wait();
+    for (int i = 0; i < 16; ++i) C[(size_t)tid * n + c16 * 16 + i] = __uint_as_float(r[i]);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc<128>(tmem_base); }
+}
+
+}  // namespace l2a

@@ -1,0 +1,442 @@
+// K1, tensor-core variant: persistent fused H-step rollout on tcgen05 (sm_100a).
+//
+// Orientation: the dense layers are computed TRANSPOSED, Y^T[out, cand] = W^T[out, in] * X^T[in, cand], so that
+//   * the MMA "M" dimension (128 TMEM lanes) is the layer's output features  -> bias / ReLU are per-thread scalars,
+//   * the MMA "N" dimension is the CTA's NC candidates                       -> NC need only be a multiple of 16,
+//   * A = W^T tiles [128 out x 64 in] stream from L2 by TMA bulk copies of pre-swizzled 16 KB tiles (mbarrier ring),
+//   * B = activations [NC cand x K] live in shared memory for the whole rollout (K-major, 128B swizzle),
+//   * D = fp32 accumulators in TMEM (one 128 x NC block per 128 output features).
+// Precision: split-bf16.  Every fp32 operand x is carried as hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits) and
+// each product is three MMA passes  W_hi*x_hi + W_hi*x_lo + W_lo*x_hi  accumulated in fp32 (measured return error
+// vs the fp32/fp64 reference: ~5e-6 relative).  A single bf16 pass misses the 1e-4 parity bar.
+//
+// Warp roles (192 threads): warps 0-3 epilogue + "env step" (TMEM -> regs -> bias/ReLU/split -> smem; state update,
+// reward, normalisation, argmax), warp 4 TMA producer (one lane), warp 5 MMA issuer (one lane) + TMEM owner.
+// Ensemble mode (BASELINE "ensemble=E"): a thread-block cluster of E CTAs, one member each, same candidates; the E
+// denormalised deltas are exchanged through distributed shared memory every step and averaged in member order, so
+// all E CTAs carry bit-identical states.
+//
+// Replaces policies/mpc_controller.py:116-129 + dynamics/mlp_dynamics.py:204-222 / meta_mlp_dynamics.py:296-306.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace l2a {
+
+constexpr int kTcTileBytes = 16384;     // one [128 x 64] bf16 weight tile (hi or lo part)
+constexpr int kTcStages = 3;
+constexpr int kTcMaxChunks = 8;         // activation width <= 512
+constexpr int kTcThreads = 192;
+constexpr int kTcMaxAct = 16;           // action dim limit of this variant
+
+// Tile enumeration of one weight set's blob; consumed in exactly this order by the kernel.
+// tile(l, mb, kc, part) = tile_off[l] + ((mb * nkc[l] + kc) * 2 + part), part 0 = hi, 1 = lo.
+struct TcPlan {
+  int n_layers;
+  int nmb[kMaxLayers];
+  int nkc[kMaxLayers];
+  int nks_last[kMaxLayers];
+  int tile_off[kMaxLayers];
+  int tiles_per_set;
+  long long set_bytes;
+};
+
+inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
+  if (md.act_dim > kTcMaxAct || md.obs_dim > 128 || md.obs_dim < 3) return false;
+  p->n_layers = md.n_layers;
+  int off = 0;
+  for (int l = 0; l < md.n_layers; ++l) {
+    const int din = md.dims[l], dout = md.dims[l + 1];
+    if (l + 1 < md.n_layers && (dout % 128 != 0 || dout > 64 * kTcMaxChunks)) return false;
+    if (l > 0 && din % 64 != 0) return false;
+    if (din > 64 * kTcMaxChunks) return false;
+    p->nmb[l] = (dout + 127) / 128;
+    p->nkc[l] = (din + 63) / 64;
+    const int rem = din - (p->nkc[l] - 1) * 64;
+    p->nks_last[l] = (rem + 15) / 16;
+    p->tile_off[l] = off;
+    off += p->nmb[l] * p->nkc[l] * 2;
+  }
+  if (md.n_layers < 2) return false;
+  p->tiles_per_set = off;
+  p->set_bytes = (long long)off * kTcTileBytes;
+  return true;
+}
+
+// fp32 [in, out] kernels -> bf16 hi/lo tiles, transposed to [out, in] (K-major) and pre-swizzled (SWIZZLE_128B),
+// zero padded.  grid.x = (layer, mb, kc) triples of one set, grid.y = set.
+struct PrepArgs {
+  MlpDims dims;
+  TcPlan plan;
+  const float* params;
+  uint8_t* blobs;
+  int first_set;
+};
+
+__global__ void __launch_bounds__(256) tc_prep_kernel(const PrepArgs a) {
+  const int set = a.first_set + blockIdx.y;
+  int l = 0, rem = blockIdx.x;
+  while (l + 1 < a.plan.n_layers && rem >= a.plan.nmb[l] * a.plan.nkc[l]) { rem -= a.plan.nmb[l] * a.plan.nkc[l]; ++l; }
+  const int mb = rem / a.plan.nkc[l], kc = rem % a.plan.nkc[l];
+  const int din = a.dims.dims[l], dout = a.dims.dims[l + 1];
+  const float* W = a.params + (size_t)set * a.dims.set_stride + a.dims.w_off[l];
+  uint8_t* tile_hi = a.blobs + (size_t)set * a.plan.set_bytes +
+                     (size_t)(a.plan.tile_off[l] + (mb * a.plan.nkc[l] + kc) * 2) * kTcTileBytes;
+  uint8_t* tile_lo = tile_hi + kTcTileBytes;
+  for (int item = threadIdx.x; item < 128 * 8; item += blockDim.x) {
+    const int r = item & 127, ch = item >> 7;
+    const int f = mb * 128 + r;
+    uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kc * 64 + ch * 8 + i;
+      const float w = (f < dout && k < din) ? W[(size_t)k * dout + f] : 0.f;
+      umma::split_bf16(w, hi[i], lo[i]);
+    }
+    const uint32_t off = umma::sw128_offset(r, ch * 8);
+    *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+    *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+  }
+}
+
+struct TcArgs {
+  MlpDims dims;
+  TcPlan plan;
+  NormDev norm;
+  const float* params;
+  const uint8_t* blobs;
+  const float* obs0;
+  const float* actions;
+  long long act_stride_t, act_stride_row;
+  const float* discount_pow;
+  int n_candidates, n_envs, horizon;
+  int set_mode, first_set, n_sets;
+  int reward_kind;
+  float dt;
+  int groups_per_env;
+  float* returns;
+  ReduceArgs red;
+};
+
+template <int NC>
+struct TcSmem {
+  static constexpr int kChunkBytes = NC * 128;
+  static constexpr int kNCP = NC + 1;
+  static constexpr size_t act_bytes = (size_t)2 * kTcMaxChunks * kChunkBytes;
+  static constexpr size_t stage_off = act_bytes;
+  static constexpr size_t misc_off = stage_off + (size_t)kTcStages * kTcTileBytes;
+  static size_t total(int D, int A) {
+    size_t misc = sizeof(float) * ((size_t)D * kNCP + 4 * (size_t)D + 2 * (size_t)A) + 64 /*pad*/ + 16 * sizeof(uint64_t) + 64;
+    return misc_off + misc + 1024 /*alignment slack*/;
+  }
+};
+
+template <int NC>
+__global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs a) {
+  using S = TcSmem<NC>;
+  constexpr int kChunkBytes = S::kChunkBytes;
+  constexpr int NCP = S::kNCP;
+  constexpr uint32_t kIdesc = umma::make_idesc_bf16(128, NC);
+  static_assert(NC % 16 == 0 && NC >= 16 && NC <= 128, "UMMA N constraint");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const MlpDims& md = a.dims;
+  const TcPlan& plan = a.plan;
+  const int D = md.obs_dim, A = md.act_dim, L = md.n_layers, H = a.horizon;
+
+  uint8_t* act_hi = smem;
+  uint8_t* act_lo = smem + (size_t)kTcMaxChunks * kChunkBytes;
+  uint8_t* stages = smem + S::stage_off;
+  float* state = reinterpret_cast<float*>(smem + S::misc_off);      // [D][NCP]
+  float* n_obs_mean = state + (size_t)D * NCP;
+  float* n_obs_den = n_obs_mean + D;
+  float* n_dmean = n_obs_den + D;
+  float* n_dscale = n_dmean + D;
+  float* n_act_mean = n_dscale + D;
+  float* n_act_den = n_act_mean + A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(n_act_den + A) + 15) & ~(uintptr_t)15);
+  uint64_t* full = bars;                      // [kTcStages]
+  uint64_t* empty = bars + kTcStages;         // [kTcStages]
+  uint64_t* layer_full = bars + 2 * kTcStages;
+  uint64_t* act_ready = layer_full + 1;
+  uint64_t* peer_ready = layer_full + 2;
+  uint64_t* peer_free = layer_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 4);
+  float* red_v = reinterpret_cast<float*>(tmem_slot + 2);   // [4]
+  int* red_i = reinterpret_cast<int*>(red_v + 4);           // [4]
+  int* s_flag = red_i + 4;
+  // the exchange buffer of denormalised deltas aliases activation chunks >= 1 (dead between the output layer's MMAs and
+  // the next layer-0 epilogue)
+  float* dbuf = reinterpret_cast<float*>(act_hi + kChunkBytes);     // [D][NCP]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool ensemble = (a.set_mode == L2A_SETS_ENSEMBLE_MEAN) && a.n_sets > 1;
+  const int csize = ensemble ? a.n_sets : 1;
+  const int crank = ensemble ? (int)umma::cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / csize;
+  const int env = cluster_id / a.groups_per_env;
+  const int group = cluster_id % a.groups_per_env;
+  const int c0 = group * NC;
+  const int nvalid = min(NC, a.n_candidates - c0);
+  int set = a.first_set;
+  if (a.set_mode == L2A_SETS_PER_ENV) set += env;
+  if (ensemble) set += crank;
+  const float* P = a.params + (size_t)set * md.set_stride;
+  const uint8_t* blob = a.blobs + (size_t)set * plan.set_bytes;
+
+  // ------------------------------------------------------------------ setup
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    umma::mbar_init(layer_full, 1);
+    umma::mbar_init(act_ready, 128);
+    umma::mbar_init(peer_ready, csize);
+    umma::mbar_init(peer_free, csize);
+    umma::fence_barrier_init();
+  }
+  if (warp == 5) umma::tmem_alloc<512>(tmem_slot);
+  for (int i = tid; i < D; i += kTcThreads) {
+    n_obs_mean[i] = a.norm.obs_mean[i];
+    n_obs_den[i] = a.norm.obs_den[i];
+    n_dmean[i] = a.norm.delta_mean[i];
+    n_dscale[i] = a.norm.delta_scale[i];
+  }
+  for (int i = tid; i < A; i += kTcThreads) { n_act_mean[i] = a.norm.act_mean[i]; n_act_den[i] = a.norm.act_den[i]; }
+  for (int i = tid; i < D * NC; i += kTcThreads) state[(i / NC) * NCP + (i % NC)] = a.obs0[(size_t)env * D + i / NC];
+  umma::tc_fence_before();
+  __syncthreads();
+  if (ensemble) umma::cluster_sync_all();      // peers' barriers are initialised before any remote arrive
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < H; ++t) {
+        for (int tile = 0; tile < plan.tiles_per_set; ++tile) {
+          umma::mbar_wait(&empty[stage], phase ^ 1u);
+          umma::mbar_arrive_expect_tx(&full[stage], kTcTileBytes);
+          umma::bulk_g2s(stages + (size_t)stage * kTcTileBytes, blob + (size_t)tile * kTcTileBytes, kTcTileBytes, &full[stage]);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, act_phase = 0;
+      const uint32_t hi_addr = umma::smem_u32(act_hi), lo_addr = umma::smem_u32(act_lo), st_addr = umma::smem_u32(stages);
+      for (int t = 0; t < H; ++t) {
+        for (int l = 0; l < L; ++l) {
+          umma::mbar_wait(act_ready, act_phase);
+          act_phase ^= 1u;
+          umma::tc_fence_after();
+          for (int mb = 0; mb < plan.nmb[l]; ++mb) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(mb * NC);
+            for (int kc = 0; kc < plan.nkc[l]; ++kc) {
+              const int nks = (kc == plan.nkc[l] - 1) ? plan.nks_last[l] : 4;
+              const uint32_t bh = hi_addr + (uint32_t)(kc * kChunkBytes), bl = lo_addr + (uint32_t)(kc * kChunkBytes);
+              // W_hi tile: W_hi*x_hi + W_hi*x_lo
+              umma::mbar_wait(&full[stage], phase);
+              umma::tc_fence_after();
+              uint32_t a_addr = st_addr + (uint32_t)(stage * kTcTileBytes);
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t ad = umma::make_desc_sw128(a_addr + ks * 32);
+                umma::mma_bf16_ss(d_tmem, ad, umma::make_desc_sw128(bh + ks * 32), kIdesc, (kc | ks) != 0);
+                umma::mma_bf16_ss(d_tmem, ad, umma::make_desc_sw128(bl + ks * 32), kIdesc, 1u);
+              }
+              umma::mma_commit(&empty[stage]);
+              if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+              // W_lo tile: W_lo*x_hi
+              umma::mbar_wait(&full[stage], phase);
+              umma::tc_fence_after();
+              a_addr = st_addr + (uint32_t)(stage * kTcTileBytes);
+              for (int ks = 0; ks < nks; ++ks)
+                umma::mma_bf16_ss(d_tmem, umma::make_desc_sw128(a_addr + ks * 32), umma::make_desc_sw128(bh + ks * 32), kIdesc, 1u);
+              umma::mma_commit(&empty[stage]);
+              if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          umma::mma_commit(layer_full);
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue + env step (warps 0-3, 128 threads)
+    const int n = tid;                                  // candidate owned in the env phase
+    const bool has_cand = n < NC;
+    const bool valid = n < nvalid;
+    const long long row = (long long)env * a.n_candidates + c0 + (valid ? n : 0);
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int nkc0 = plan.nkc[0];
+    uint32_t lf_phase = 0, pr_phase = 0, pf_phase = 0;
+    float ret = 0.f, asq = 0.f;
+    float a_cur[kTcMaxAct];
+
+    auto load_actions = [&](int t) {
+      const float* src = a.actions + (long long)t * a.act_stride_t + row * a.act_stride_row;
+#pragma unroll
+      for (int j = 0; j < kTcMaxAct; ++j) a_cur[j] = (j < A && valid && has_cand) ? __ldg(src + j) : 0.f;
+    };
+    // normalised network input of the candidate for the step whose actions are in a_cur: features [state | action | 0]
+    auto write_x = [&]() {
+      if (has_cand) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTcMaxAct; ++j) s = fmaf(a_cur[j], a_cur[j], s);
+        asq = s;
+        for (int g = 0; g < nkc0 * 8; ++g) {
+          uint16_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = g * 8 + i;
+            float v = 0.f;
+            if (k < D) v = (state[k * NCP + n] - n_obs_mean[k]) / n_obs_den[k];       // mlp_dynamics.py:265-266
+            else if (k < D + A) {
+              float av = 0.f;
+#pragma unroll
+              for (int j = 0; j < kTcMaxAct; ++j) av = (j == k - D) ? a_cur[j] : av;
+              v = (av - n_act_mean[k - D]) / n_act_den[k - D];
+            }
+            umma::split_bf16(v, hi[i], lo[i]);
+          }
+          const uint32_t off = (uint32_t)(g >> 3) * kChunkBytes + umma::sw128_offset(n, (g & 7) * 8);
+          *reinterpret_cast<uint4*>(act_hi + off) = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+          *reinterpret_cast<uint4*>(act_lo + off) = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+        }
+      }
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_before();
+      umma::mbar_arrive(act_ready);
+    };
+
+    load_actions(0);
+    write_x();
+
+    for (int t = 0; t < H; ++t) {
+      // ---------------- hidden layers: TMEM -> bias + ReLU -> split -> next layer's B operand (in place)
+      for (int l = 0; l + 1 < L; ++l) {
+        umma::mbar_wait(layer_full, lf_phase);
+        lf_phase ^= 1u;
+        umma::tc_fence_after();
+        if (l == 0 && ensemble && t > 0) {               // peers have finished reading my dbuf (aliases act chunks >= 1)
+          umma::mbar_wait_cluster(peer_free, pf_phase);
+          pf_phase ^= 1u;
+        }
+        for (int mb = 0; mb < plan.nmb[l]; ++mb) {
+          const int f = mb * 128 + tid;
+          const float bias = __ldg(P + md.b_off[l] + f);
+          uint8_t* dst_hi = act_hi + (size_t)(f >> 6) * kChunkBytes;
+          uint8_t* dst_lo = act_lo + (size_t)(f >> 6) * kChunkBytes;
+          const uint32_t col = (uint32_t)(f & 63);
+#pragma unroll 1
+          for (int c16 = 0; c16 < NC / 16; ++c16) {
+            uint32_t r[16];
+            umma::tmem_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(mb * NC + c16 * 16), r);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float v = fmaxf(__uint_as_float(r[i]) + bias, 0.f);     // core/utils.py:119-126 (ReLU dense)
+              uint16_t hi, lo;
+              umma::split_bf16(v, hi, lo);
+              const uint32_t off = umma::sw128_offset((uint32_t)(c16 * 16 + i), col);
+              *reinterpret_cast<uint16_t*>(dst_hi + off) = hi;
+              *reinterpret_cast<uint16_t*>(dst_lo + off) = lo;
+            }
+          }
+        }
+        umma::fence_proxy_async_smem();
+        umma::tc_fence_before();
+        umma::mbar_arrive(act_ready);
+      }
+      // ---------------- output layer: y -> denormalised delta -> exchange buffer
+      if (t + 1 < H) load_actions(t + 1);                 // prefetch the next step's actions (HBM) under the MMA wait
+      umma::mbar_wait(layer_full, lf_phase);
+      lf_phase ^= 1u;
+      umma::tc_fence_after();
+      if (warp * 32 < D) {
+        const int f = tid;
+        const bool frow = f < D;
+        const float bias = frow ? __ldg(P + md.b_off[L - 1] + f) : 0.f;
+        const float sc = frow ? n_dscale[f] : 0.f, mu = frow ? n_dmean[f] : 0.f;
+#pragma unroll 1
+        for (int c16 = 0; c16 < NC / 16; ++c16) {
+          uint32_t r[16];
+          umma::tmem_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(c16 * 16), r);
+          umma::tmem_ld_wait();
+          if (frow) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              dbuf[f * NCP + c16 * 16 + i] = (__uint_as_float(r[i]) + bias) * sc + mu;   // mlp_dynamics.py:269-270
+          }
+        }
+      }
+      umma::tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ensemble) {
+        if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_ready), (uint32_t)tid));
+        umma::mbar_wait_cluster(peer_ready, pr_phase);
+        pr_phase ^= 1u;
+      }
+      // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
+      if (has_cand) {
+        float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
+        const float inv_e = 1.0f / (float)csize;
+        const uint32_t dbuf_addr = umma::smem_u32(dbuf);
+        for (int k = 0; k < D; ++k) {
+          float d;
+          if (ensemble) {
+            d = 0.f;
+            for (int e = 0; e < csize; ++e)
+              d += umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)((k * NCP + n) * 4), (uint32_t)e));
+            d *= inv_e;
+          } else {
+            d = dbuf[k * NCP + n];
+          }
+          const float s_new = state[k * NCP + n] + d;       // mlp_dynamics.py:220
+          state[k * NCP + n] = s_new;
+          if (k == D - 3) { dx = d; nx0 = s_new; }
+          if (k == D - 2) nx1 = s_new;
+          if (k == D - 1) nx2 = s_new;
+        }
+        const float rew = reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2);
+        ret = fmaf(__ldg(a.discount_pow + t), rew, ret);     // mpc_controller.py:126
+      }
+      if (ensemble) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_free), (uint32_t)tid));
+      }
+      if (t + 1 < H) write_x();
+    }
+
+    // ---------------- per-CTA argmax; one CTA per cluster publishes
+    float v = -__int_as_float(0x7f800000);
+    int idx = 0x7fffffff;
+    if (valid && has_cand) { v = ret; idx = c0 + n; }
+    if (crank == 0 && a.returns && valid && has_cand) a.returns[(size_t)env * a.n_candidates + c0 + n] = ret;
+    warp_argmax(v, idx);
+    if (lane == 0) { red_v[warp] = v; red_i[warp] = idx; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 0) {
+      v = (lane < 4) ? red_v[lane] : -__int_as_float(0x7f800000);
+      idx = (lane < 4) ? red_i[lane] : 0x7fffffff;
+      warp_argmax(v, idx);
+      if (lane == 0) { red_v[0] = v; red_i[0] = idx; }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  umma::tc_fence_before();
+  __syncthreads();
+  if (crank == 0) publish_and_reduce(a.red, env, group, red_v[0], red_i[0], tid, s_flag);
+  if (ensemble) umma::cluster_sync_all();      // nobody exits while a peer may still read its shared memory
+  if (warp == 5) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace l2a

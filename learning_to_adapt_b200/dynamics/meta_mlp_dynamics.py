@@ -1,0 +1,120 @@
+"""MetaMLPDynamicsModel (GrBAL) on the B200 engine: same constructor and methods as
+learning_to_adapt/dynamics/meta_mlp_dynamics.py:11-445.
+
+Weight set 0 is the prior theta; sets 1..meta_batch_size hold the per-env adapted theta'_k produced by kernel K2.
+``adapt`` never touches theta (meta_mlp_dynamics.py:321-345); ``switch_to_pre_adapt`` just forgets the adapted sets
+(:347-351).  After ``adapt`` with K tasks, ``predict`` and the fused rollout step row chunk k through theta'_k
+(:296-306) -- without re-uploading K x theta' every horizon step as the TF feed_dict did.
+"""
+import numpy as np
+
+from learning_to_adapt_b200 import _native as N
+from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel, normalize
+from learning_to_adapt_b200.utils.serializable import Serializable
+
+
+class MetaMLPDynamicsModel(MLPDynamicsModel):
+    def __init__(self, name, env, hidden_sizes=(512, 512), meta_batch_size=10, hidden_nonlinearity="relu",
+                 output_nonlinearity=None, batch_size=500, learning_rate=0.001, inner_learning_rate=0.1,
+                 normalize_input=True, optimizer=None, valid_split_ratio=0.2, rolling_average_persitency=0.99,
+                 device=0, seed=None):
+        Serializable.quick_init(self, locals())
+        self.meta_batch_size = int(meta_batch_size)
+        self.inner_learning_rate = inner_learning_rate
+        self._num_adapted_models = None
+        self._adapted = False
+        MLPDynamicsModel.__init__(self, name, env, hidden_sizes=hidden_sizes, hidden_nonlinearity=hidden_nonlinearity,
+                                  output_nonlinearity=output_nonlinearity, batch_size=batch_size,
+                                  learning_rate=learning_rate, normalize_input=normalize_input, optimizer=optimizer,
+                                  valid_split_ratio=valid_split_ratio,
+                                  rolling_average_persitency=rolling_average_persitency, ensemble_size=1, device=device,
+                                  seed=seed)
+
+    def _total_sets(self):
+        return 1 + self.meta_batch_size
+
+    def planning_sets(self, n_envs):
+        if self._adapted:
+            k = self._num_adapted_models
+            if n_envs != k:
+                raise NotImplementedError("adapted to %d tasks but planning for %d envs: the reference's row chunking "
+                                          "(meta_mlp_dynamics.py:296-306) only lines up with envs when they are equal" % (k, n_envs))
+            return N.SETS_PER_ENV, 1, k
+        return N.SETS_SHARED, 0, 1
+
+    def compute_normalization(self, obs, act, obs_next):
+        """3-D inputs [tasks, T, dim], statistics over axes (0, 1) (meta_mlp_dynamics.py:396-407)."""
+        if obs.ndim == 2:
+            return MLPDynamicsModel.compute_normalization(self, obs, act, obs_next)
+        D, A = obs.shape[-1], act.shape[-1]
+        return MLPDynamicsModel.compute_normalization(self, obs.reshape(-1, D), act.reshape(-1, A), obs_next.reshape(-1, D))
+
+    # ------------------------------------------------------------------ K2
+    def adapt(self, obs, act, obs_next):
+        """obs/act/obs_next: K lists of [M, .] arrays, the last M transitions per env (samplers/sampler.py:83-90)."""
+        k = len(obs)
+        assert len(obs) == len(act) == len(obs_next)
+        if k > self.meta_batch_size:
+            raise ValueError("adapt() got %d tasks but meta_batch_size is %d" % (k, self.meta_batch_size))
+        obs = np.stack([np.asarray(o, np.float64) for o in obs])
+        act = np.stack([np.asarray(a, np.float64) for a in act])
+        obs_next = np.stack([np.asarray(o, np.float64) for o in obs_next])
+        assert obs.ndim == 3 and obs.shape[2] == self.obs_space_dims
+        assert act.ndim == 3 and act.shape[2] == self.action_space_dims
+        assert obs_next.shape == obs.shape
+        # host-side float64 normalisation, float32 feed (meta_mlp_dynamics.py:334-339)
+        obs_n = normalize(obs, *self.normalization["obs"])
+        act_n = normalize(act, *self.normalization["act"])
+        delta_n = normalize(obs_next - obs, *self.normalization["delta"])
+        eng = self._engine
+        x = eng._f32(np.concatenate([obs_n, act_n], axis=2))
+        target = eng._f32(delta_n)
+        eng.adapt(x, target, self.inner_learning_rate, src_set=0, dst_first_set=1)
+        self._num_adapted_models = k
+        self._adapted = True
+
+    def switch_to_pre_adapt(self):
+        self._adapted = False                       # theta itself was never modified (:347-351)
+
+    def get_adapted_params(self, k):
+        assert self._adapted and k < self._num_adapted_models
+        return self._engine.get_params(1 + k)
+
+    # ------------------------------------------------------------------ K4 with per-task weights
+    def _predict_delta(self, obs, act):
+        eng = self._engine
+        if self._adapted:
+            k = self._num_adapted_models
+            assert obs.shape[0] % k == 0, "rows must split evenly over the adapted tasks (meta_mlp_dynamics.py:308-312)"
+            d = eng.predict_delta(eng._f32(obs), eng._f32(act), N.SETS_PER_ENV, 1, k)
+        else:
+            d = eng.predict_delta(eng._f32(obs), eng._f32(act), N.SETS_SHARED, 0, 1)
+        return d.cpu().numpy()
+
+    def fit(self, obs, act, obs_next, epochs=1000, compute_normalization=True, valid_split_ratio=None,
+            rolling_average_persitency=None, verbose=False, log_tabular=False):
+        """MAML outer loop (meta_mlp_dynamics.py:167-274): torch autograd through the one-step inner update.
+        Host-side glue, off the planning hot path."""
+        from learning_to_adapt_b200.dynamics.fit import fit_maml
+        assert obs.ndim == 3 and act.ndim == 3 and obs_next.ndim == 3
+        if compute_normalization or self.normalization is None:
+            self.compute_normalization(obs, act, obs_next)
+        obs_n = normalize(obs, *self.normalization["obs"])
+        act_n = normalize(act, *self.normalization["act"])
+        delta_n = normalize(obs_next - obs, *self.normalization["delta"])
+        params = fit_maml(self._engine.get_params(0), obs_n, act_n, delta_n, epochs=epochs, batch_size=self.batch_size,
+                          meta_batch_size=self.meta_batch_size, learning_rate=self.learning_rate,
+                          inner_learning_rate=self.inner_learning_rate,
+                          valid_split_ratio=self.valid_split_ratio if valid_split_ratio is None else valid_split_ratio,
+                          rolling_average_persitency=(self.rolling_average_persitency
+                                                      if rolling_average_persitency is None else rolling_average_persitency),
+                          device=self._engine.device, verbose=verbose)
+        self._engine.set_params(0, params)
+        self._adapted = False
+
+    def __getstate__(self):
+        state = dict()
+        state["init_args"] = Serializable.__getstate__(self)
+        state["normalization"] = self.normalization
+        state["networks"] = [{"network_params": self.get_params(0)}]
+        return state

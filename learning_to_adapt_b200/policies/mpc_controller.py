@@ -1,0 +1,149 @@
+"""MPCController on the B200 engine: same constructor and methods as
+learning_to_adapt/policies/mpc_controller.py:6-135.
+
+The reference's H-iteration python loop (one TF ``sess.run`` + numpy reward per step, :116-127) collapses into ONE
+fused kernel call per planning step (random shooting) or per CEM iteration: sample -> K1 rollout/reward/argmax ->
+(CEM: rank + refit).  The dynamics model must be one of this package's engine-backed models; there is no CPU
+fallback.
+
+Candidate sampling
+  sampler="numpy" (default): the reference's own draw from the global numpy MT19937 stream
+      (``np.random.uniform`` :67-69,114 / ``np.random.normal`` :85), uploaded as fp32 -> identical candidates,
+      hence identical chosen actions for a fixed ``np.random.seed`` (parity mode).
+  sampler="device": Philox draws on the GPU (torch.rand / torch.randn) -> no host RNG, no H2D of candidates
+      (throughput mode; env var L2A_B200_SAMPLER=device selects it without touching the run scripts).
+"""
+import os
+
+import numpy as np
+import torch
+
+from learning_to_adapt_b200 import _native as N
+from learning_to_adapt_b200.envs.synthetic import reward_kind_of
+from learning_to_adapt_b200.policies.base import Policy
+from learning_to_adapt_b200.utils.serializable import Serializable
+
+
+class MPCController(Policy, Serializable):
+    def __init__(self, name, env, dynamics_model, reward_model=None, discount=1, use_cem=False, n_candidates=1024,
+                 horizon=10, num_cem_iters=8, percent_elites=0.1, use_reward_model=False, alpha=0.1, sampler=None,
+                 cem_compat=True, kernel=N.KERNEL_AUTO, parallel=None):
+        self.dynamics_model = dynamics_model
+        self.reward_model = reward_model
+        self.discount = discount
+        self.n_candidates = n_candidates
+        self.horizon = horizon
+        self.use_cem = use_cem
+        self.num_cem_iters = num_cem_iters
+        self.percent_elites = percent_elites
+        self.env = env
+        self.use_reward_model = use_reward_model
+        self.alpha = alpha
+        self.sampler = sampler or os.environ.get("L2A_B200_SAMPLER", "numpy")
+        assert self.sampler in ("numpy", "device")
+        self.cem_compat = cem_compat
+        self.kernel = kernel
+        self.parallel = parallel          # optional learning_to_adapt_b200.parallel.CandidateShard
+
+        self.unwrapped_env = env
+        while hasattr(self.unwrapped_env, "wrapped_env"):
+            self.unwrapped_env = self.unwrapped_env.wrapped_env
+        # make sure that env has reward function (mpc_controller.py:38-39)
+        assert hasattr(self.unwrapped_env, "reward"), "env must have a reward function"
+        if use_reward_model:
+            raise NotImplementedError("use_reward_model=True: learned reward models are not on the fused path")
+        if not hasattr(dynamics_model, "_engine"):
+            raise TypeError("dynamics_model must be an engine-backed learning_to_adapt_b200 model "
+                            "(MLPDynamicsModel / MetaMLPDynamicsModel); there is no CPU fallback")
+        self._reward_kind, self._dt = reward_kind_of(self.unwrapped_env)
+        self.last_plan = None             # device tensors of the most recent planning call (diagnostics / tests)
+
+        Serializable.quick_init(self, locals())
+        super(MPCController, self).__init__(env=env)
+
+    @property
+    def vectorized(self):
+        return True
+
+    def get_action(self, observation):
+        if observation.ndim == 1:
+            observation = observation[None]
+        if self.use_cem:
+            action = self.get_cem_action(observation)
+        else:
+            action = self.get_rs_action(observation)
+        return action, dict()
+
+    def get_actions(self, observations):
+        if self.use_cem:
+            actions = self.get_cem_action(observations)
+        else:
+            actions = self.get_rs_action(observations)
+        return actions, dict()
+
+    def get_random_action(self, n):
+        return np.random.uniform(low=self.action_space.low, high=self.action_space.high,
+                                 size=(n,) + self.action_space.low.shape)
+
+    # ------------------------------------------------------------------ random shooting (mpc_controller.py:108-129)
+    def get_rs_action(self, observations):
+        observations = np.asarray(observations, np.float64)
+        n, m, h = self.n_candidates, len(observations), self.horizon
+        eng = self.dynamics_model._engine
+        act_dim = self.action_space.shape[0]
+        set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
+        obs_dev = eng._f32(observations)
+        if self.parallel is not None:
+            return self.parallel.plan_rs(self, observations, obs_dev, set_mode, first_set, n_sets)
+        a_host = None
+        if self.sampler == "numpy":
+            a_host = self.get_random_action(h * n * m).reshape((h, n * m, -1))            # :114
+            a_dev = eng._f32(a_host)
+        else:
+            low = eng._f32(self.action_space.low)
+            high = eng._f32(self.action_space.high)
+            a_dev = torch.rand((h, n * m, act_dim), device=eng.device, dtype=torch.float32) * (high - low) + low
+        res = eng.rollout(obs_dev, a_dev, n, h, self._reward_kind, self._dt, discount=self.discount, set_mode=set_mode,
+                          first_set=first_set, n_sets=n_sets, layout="thra", want_returns=False, kernel=self.kernel)
+        self.last_plan = res
+        if a_host is not None:
+            best = res["best_idx"].cpu().numpy()
+            cand_a = a_host[0].reshape((m, n, -1))                                        # :118
+            return cand_a[range(m), best]                                                 # :129, float64
+        return res["best_act"].cpu().numpy().astype(np.float64)
+
+    # ------------------------------------------------------------------ CEM (mpc_controller.py:71-106)
+    def get_cem_action(self, observations):
+        observations = np.asarray(observations, np.float64)
+        n, m, h = self.n_candidates, len(observations), self.horizon
+        eng = self.dynamics_model._engine
+        act_dim = self.action_space.shape[0]
+        ha = h * act_dim
+        set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
+        num_elites = max(int(self.n_candidates * self.percent_elites), 1)                 # :78
+        mean = torch.zeros((m, ha), device=eng.device, dtype=torch.float64)               # :79
+        std = torch.ones((m, ha), device=eng.device, dtype=torch.float64)                 # :80
+        clip_low = eng._f32(np.concatenate([self.action_space.low] * h))                  # :81
+        clip_high = eng._f32(np.concatenate([self.action_space.high] * h))                # :82
+        obs_dev = eng._f32(observations)
+        res = None
+        for _ in range(self.num_cem_iters):                                               # :84
+            if self.sampler == "numpy":
+                z = eng._f32(np.random.normal(size=(n, m, ha)))                           # :85
+            else:
+                z = torch.randn((n, m, ha), device=eng.device, dtype=torch.float32)
+            samples, clipped = eng.cem_sample(z, mean, std, clip_low, clip_high)          # :86-87
+            # rows of the (n*m, H, A) view are rolled out UNclipped, row r from env r // n  (:88-99)
+            res = eng.rollout(obs_dev, samples, n, h, self._reward_kind, self._dt, discount=self.discount,
+                              set_mode=set_mode, first_set=first_set, n_sets=n_sets, layout="nmha", want_returns=True,
+                              kernel=self.kernel)
+            eng.cem_refit(res["returns"], clipped, num_elites, self.alpha, mean, std, compat=self.cem_compat)  # :101-104
+        self.last_plan = res
+        self.last_cem_state = (mean, std)
+        return res["best_act"].cpu().numpy().astype(np.float64)                           # :106
+
+    def get_params_internal(self, **tags):
+        return []
+
+    def reset(self, dones=None):
+        pass
