@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         }
       }
     }
+    __syncwarp();
   } else if (warp == 5) {
     // ================================================================ MMA issuer
     if (lane == 0) {
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         }
       }
     }
+    __syncwarp();
   } else {
     // ================================================================ epilogue + env step (warps 0-3, 128 threads)
     const int n = tid;                                  // candidate owned in the env phase

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace l2a {
 namespace umma {
@@ -34,8 +35,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Watchdog: a barrier that does not complete within ~4e9 SM cycles (>2 s) is a protocol bug; trap instead of
+// hanging the GPU.
+#ifndef L2A_WATCHDOG_CYCLES
+#define L2A_WATCHDOG_CYCLES 4000000000ll
+#endif
+__device__ __noinline__ void watchdog_fail(uint32_t bar_addr, uint32_t parity) {
+  printf("l2a_b200 watchdog: mbarrier 0x%x parity %u never completed (block %d thread %d)\n", bar_addr, parity,
+         (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > L2A_WATCHDOG_CYCLES) watchdog_fail(smem_u32(bar), parity);
+  }
 }
 // cluster-scope variants (peer CTA barriers addressed through mapa)
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_rank) {
@@ -58,7 +73,11 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait_cluster(bar, parity)) {}
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > L2A_WATCHDOG_CYCLES) watchdog_fail(smem_u32(bar), parity);
+  }
 }
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   float v;

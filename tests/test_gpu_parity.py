@@ -22,7 +22,7 @@ def _native():
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 tile
-@pytest.mark.parametrize("n,k", [(16, 64), (32, 128), (80, 64), (80, 256), (128, 256)])
+@pytest.mark.parametrize("n,k", [(16, 64), (32, 128), (80, 64), (80, 256), (128, 128)])
 def test_umma_tile_matches_fp32_matmul(n, k):
     from learning_to_adapt_b200.engine import PlanningEngine
     eng = PlanningEngine(20, 6, (128,), n_sets=1)
