@@ -63,11 +63,29 @@ __global__ void __launch_bounds__(128, 1) debug_umma_tile_kernel(const float* A,
   }
   umma::mbar_wait(bar, 0);
   umma::tc_fence_after();
-  for (int c16 = 0; c16 < n / 16; ++c16) {
-    uint32_t r[16];
-    umma::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c16 * 16), r);
-    umma::tmem_ld_wait();
-    for (int i = 0; i < 16; ++i) C[(size_t)tid * n + c16 * 16 + i] = __uint_as_float(r[i]);
+  if (variant & 8) {
+    // accumulator-fragment loads (the rollout epilogue's path): thread T holds lanes T/4, T/4+8 x column pairs
+    const int lane = tid & 31;
+    for (int half = 0; half < 2; ++half)
+      for (int cb = 0; cb < n / 16; ++cb) {
+        uint32_t r[8];
+        umma::tmem_ld_16x256b_x2(tmem_base + ((uint32_t)(warp * 32 + half * 16) << 16) + (uint32_t)(cb * 16), r);
+        umma::tmem_ld_wait();
+        for (int j = 0; j < 2; ++j)
+          for (int q = 0; q < 2; ++q) {
+            const int row = warp * 32 + half * 16 + (lane >> 2) + q * 8;
+            const int col = cb * 16 + j * 8 + 2 * (lane & 3);
+            C[(size_t)row * n + col] = __uint_as_float(r[4 * j + 2 * q]);
+            C[(size_t)row * n + col + 1] = __uint_as_float(r[4 * j + 2 * q + 1]);
+          }
+      }
+  } else {
+    for (int c16 = 0; c16 < n / 16; ++c16) {
+      uint32_t r[16];
+      umma::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c16 * 16), r);
+      umma::tmem_ld_wait();
+      for (int i = 0; i < 16; ++i) C[(size_t)tid * n + c16 * 16 + i] = __uint_as_float(r[i]);
+    }
   }
   umma::tc_fence_before();
   __syncthreads();

@@ -226,46 +226,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     __syncwarp();
   } else if (warp == 5) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp walks the loops (so every descriptor is computed warp-uniformly and lands in uniform registers);
+    // only the elected lane issues tcgen05.mma / tcgen05.commit.
+    {
       int stage = 0;
       uint32_t phase = 0, act_phase = 0;
-      const uint32_t hi_addr = umma::smem_u32(act_hi), lo_addr = umma::smem_u32(act_lo), st_addr = umma::smem_u32(stages);
+      const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
+      const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
+      constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)kTcTileBytes >> 4;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l < L; ++l) {
+          const int nmb = plan.nmb[l], nkc = plan.nkc[l], nks_last = plan.nks_last[l];
           umma::mbar_wait(act_ready, act_phase);
           act_phase ^= 1u;
           umma::tc_fence_after();
-          for (int mb = 0; mb < plan.nmb[l]; ++mb) {
+          for (int mb = 0; mb < nmb; ++mb) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(mb * NC);
-            for (int kc = 0; kc < plan.nkc[l]; ++kc) {
-              const int nks = (kc == plan.nkc[l] - 1) ? plan.nks_last[l] : 4;
-              const uint32_t bh = hi_addr + (uint32_t)(kc * kChunkBytes), bl = lo_addr + (uint32_t)(kc * kChunkBytes);
+            for (int kc = 0; kc < nkc; ++kc) {
+              const bool full_k = (kc != nkc - 1) || (nks_last == 4);
+              const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
               // W_hi tile: W_hi*x_hi + W_hi*x_lo
               umma::mbar_wait(&full[stage], phase);
               umma::tc_fence_after();
-              uint32_t a_addr = st_addr + (uint32_t)(stage * kTcTileBytes);
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t ad = umma::make_desc_sw128(a_addr + ks * 32);
-                umma::mma_bf16_ss(d_tmem, ad, umma::make_desc_sw128(bh + ks * 32), kIdesc, (kc | ks) != 0);
-                umma::mma_bf16_ss(d_tmem, ad, umma::make_desc_sw128(bl + ks * 32), kIdesc, 1u);
+              uint32_t a_lo = st_lo32 + (uint32_t)stage * kStageStep;
+              if (umma::elect_one()) {
+                if (full_k) {
+                  umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, (uint32_t)(kc != 0));
+                  umma::mma_bf16_ss_lo(d_tmem, a_lo, bl, kIdesc, 1u);
+#pragma unroll
+                  for (int ks = 1; ks < 4; ++ks) {
+                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+                  }
+                } else {
+                  for (int ks = 0; ks < nks_last; ++ks) {
+                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, (uint32_t)((kc | ks) != 0));
+                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+                  }
+                }
+                umma::mma_commit(&empty[stage]);
               }
-              umma::mma_commit(&empty[stage]);
+              __syncwarp();
               if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
               // W_lo tile: W_lo*x_hi
               umma::mbar_wait(&full[stage], phase);
               umma::tc_fence_after();
-              a_addr = st_addr + (uint32_t)(stage * kTcTileBytes);
-              for (int ks = 0; ks < nks; ++ks)
-                umma::mma_bf16_ss(d_tmem, umma::make_desc_sw128(a_addr + ks * 32), umma::make_desc_sw128(bh + ks * 32), kIdesc, 1u);
-              umma::mma_commit(&empty[stage]);
+              a_lo = st_lo32 + (uint32_t)stage * kStageStep;
+              if (umma::elect_one()) {
+                if (full_k) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+                } else {
+                  for (int ks = 0; ks < nks_last; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+                }
+                umma::mma_commit(&empty[stage]);
+              }
+              __syncwarp();
               if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
             }
           }
-          umma::mma_commit(layer_full);
+          if (umma::elect_one()) umma::mma_commit(layer_full);
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     // ================================================================ epilogue + env step (warps 0-3, 128 threads)
     const int n = tid;                                  // candidate owned in the env phase
@@ -328,25 +352,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           umma::mbar_wait_cluster(peer_free, pf_phase);
           pf_phase ^= 1u;
         }
-        for (int mb = 0; mb < plan.nmb[l]; ++mb) {
-          const int f = mb * 128 + tid;
-          const float bias = __ldg(P + md.b_off[l] + f);
-          uint8_t* dst_hi = act_hi + (size_t)(f >> 6) * kChunkBytes;
-          uint8_t* dst_lo = act_lo + (size_t)(f >> 6) * kChunkBytes;
-          const uint32_t col = (uint32_t)(f & 63);
-#pragma unroll 1
-          for (int c16 = 0; c16 < NC / 16; ++c16) {
-            uint32_t r[16];
-            umma::tmem_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(mb * NC + c16 * 16), r);
-            umma::tmem_ld_wait();
+        // Accumulator fragments (16x256b TMEM loads: thread T holds features T/4, T/4+8 x candidate pairs) are turned into
+        // the next layer's K-major B operand with transposed 8x8 stmatrix stores: 16-byte rows of 8 features per candidate.
+        {
+          const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
+          const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;          // stmatrix row owned by this lane (within 16 candidates)
+          const int fsel = ((lane >> 3) & 1) * 8;                         // ... of the feature-group matrix 0 / +8
+          for (int mb = 0; mb < plan.nmb[l]; ++mb) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float v = fmaxf(__uint_as_float(r[i]) + bias, 0.f);     // core/utils.py:119-126 (ReLU dense)
-              uint16_t hi, lo;
-              umma::split_bf16(v, hi, lo);
-              const uint32_t off = umma::sw128_offset((uint32_t)(c16 * 16 + i), col);
-              *reinterpret_cast<uint16_t*>(dst_hi + off) = hi;
-              *reinterpret_cast<uint16_t*>(dst_lo + off) = lo;
+            for (int half = 0; half < 2; ++half) {
+              const int fbase = mb * 128 + warp * 32 + half * 16;         // 16 features handled by this (warp, half)
+              const float bias_a = __ldg(P + md.b_off[l] + fbase + (lane >> 2));
+              const float bias_b = __ldg(P + md.b_off[l] + fbase + (lane >> 2) + 8);
+              const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32 + half * 16) << 16) + (uint32_t)(mb * NC);
+              const uint32_t chunk_off = (uint32_t)(fbase >> 6) * kChunkBytes;
+              const uint32_t fcol = (uint32_t)((fbase & 63) + fsel) >> 3;  // 16-byte column of this lane's matrix rows
+#pragma unroll 2
+              for (int cb = 0; cb < NC / 16; ++cb) {
+                uint32_t r[8];
+                umma::tmem_ld_16x256b_x2(t_addr + (uint32_t)(cb * 16), r);
+                umma::tmem_ld_wait();
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float b = (q & 1) ? bias_b : bias_a;
+                  const float v0 = fmaxf(__uint_as_float(r[2 * q]) + b, 0.f);          // core/utils.py:119-126 (ReLU dense)
+                  const float v1 = fmaxf(__uint_as_float(r[2 * q + 1]) + b, 0.f);
+                  umma::split_bf16x2(v0, v1, hi[q], lo[q]);
+                }
+                const uint32_t cand = (uint32_t)(cb * 16 + cand_l);
+                const uint32_t off = chunk_off + cand * 128u + (((fcol ^ cand) & 7u) << 4);
+                umma::stmatrix_x4_trans(act_hi_addr + off, hi[0], hi[1], hi[2], hi[3]);
+                umma::stmatrix_x4_trans(act_lo_addr + off, lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
         }
@@ -391,9 +429,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         for (int k = 0; k < D; ++k) {
           float d;
           if (ensemble) {
+            float pe[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              pe[e] = (e < csize) ? umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)((k * NCP + n) * 4), (uint32_t)e)) : 0.f;
             d = 0.f;
-            for (int e = 0; e < csize; ++e)
-              d += umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)((k * NCP + n) * 4), (uint32_t)e));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d += pe[e];            // member order 0..E-1 (unused slots add +0)
             d *= inv_e;
           } else {
             d = dbuf[k * NCP + n];

@@ -33,6 +33,8 @@ def test_umma_tile_matches_fp32_matmul(n, k):
     got = eng.debug_umma_tile(dev(A), dev(B), variant=0).cpu().numpy()
     err = np.abs(got - want).max() / np.abs(want).max()
     assert err < 2e-5, "split-bf16 tile error %.3e" % err
+    got8 = eng.debug_umma_tile(dev(A), dev(B), variant=8).cpu().numpy()     # accumulator-fragment TMEM loads (16x256b)
+    np.testing.assert_array_equal(got8, got)
     got1 = eng.debug_umma_tile(dev(A), dev(B), variant=4).cpu().numpy()     # single bf16 pass: must be visibly worse
     err1 = np.abs(got1 - want).max() / np.abs(want).max()
     assert 1e-4 < err1 < 3e-2, "single-pass bf16 error %.3e" % err1
