@@ -29,8 +29,11 @@ constexpr int kTcMaxChunks = 8;         // activation width <= 512
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxAct = 16;           // action dim limit of this variant
 
-// Tile enumeration of one weight set's blob; consumed in exactly this order by the kernel.
-// tile(l, mb, kc, part) = tile_off[l] + ((mb * nkc[l] + kc) * 2 + part), part 0 = hi, 1 = lo.
+// Tile enumeration of one weight set's blob; consumed in exactly this order by the kernel.  Within a layer the M-blocks
+// are split into phase A (the first min(2, nmb) blocks) and phase B (the rest); each phase is K-OUTER:
+//   A: for kc: for mb in A: (hi, lo)      B: for kc: for mb in B: (hi, lo)
+// so that phase A of layer l+1 can start on the first activation chunks while layer l's epilogue is still writing the
+// later ones (see the schedule notes in rollout_tc_kernel).
 struct TcPlan {
   int n_layers;
   int nmb[kMaxLayers];
@@ -41,6 +44,13 @@ struct TcPlan {
   long long set_bytes;
 };
 
+__host__ __device__ inline int tc_tile_index(const TcPlan& p, int l, int mb, int kc, int part) {
+  const int nmb = p.nmb[l], nkc = p.nkc[l];
+  const int nA = nmb < 2 ? nmb : 2, nB = nmb - nA;
+  if (mb < nA) return p.tile_off[l] + ((kc * nA + mb) * 2 + part);
+  return p.tile_off[l] + nkc * nA * 2 + ((kc * nB + (mb - nA)) * 2 + part);
+}
+
 inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
   if (md.act_dim > kTcMaxAct || md.obs_dim > 128 || md.obs_dim < 3) return false;
   p->n_layers = md.n_layers;
@@ -48,6 +58,7 @@ inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
   for (int l = 0; l < md.n_layers; ++l) {
     const int din = md.dims[l], dout = md.dims[l + 1];
     if (l + 1 < md.n_layers && (dout % 128 != 0 || dout > 64 * kTcMaxChunks)) return false;
+    if ((dout + 127) / 128 > 4) return false;
     if (l > 0 && din % 64 != 0) return false;
     if (din > 64 * kTcMaxChunks) return false;
     p->nmb[l] = (dout + 127) / 128;
@@ -80,8 +91,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const PrepArgs a) {
   const int mb = rem / a.plan.nkc[l], kc = rem % a.plan.nkc[l];
   const int din = a.dims.dims[l], dout = a.dims.dims[l + 1];
   const float* W = a.params + (size_t)set * a.dims.set_stride + a.dims.w_off[l];
-  uint8_t* tile_hi = a.blobs + (size_t)set * a.plan.set_bytes +
-                     (size_t)(a.plan.tile_off[l] + (mb * a.plan.nkc[l] + kc) * 2) * kTcTileBytes;
+  uint8_t* tile_hi = a.blobs + (size_t)set * a.plan.set_bytes + (size_t)tc_tile_index(a.plan, l, mb, kc, 0) * kTcTileBytes;
   uint8_t* tile_lo = tile_hi + kTcTileBytes;
   for (int item = threadIdx.x; item < 128 * 8; item += blockDim.x) {
     const int r = item & 127, ch = item >> 7;
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   constexpr int kChunkBytes = S::kChunkBytes;
   constexpr int NCP = S::kNCP;
   constexpr uint32_t kIdesc = umma::make_idesc_bf16(128, NC);
-  static_assert(NC % 16 == 0 && NC >= 16 && NC <= 128, "UMMA N constraint");
+  static_assert(NC % 16 == 0 && NC >= 16 && 6 * NC <= 512, "UMMA N constraint / six accumulator slots must fit the 512 TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -234,59 +244,80 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)kTcTileBytes >> 4;
+      // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block
+      auto tile_pair = [&](uint32_t d_tmem, int kc, bool first, bool full_k, int nks_last) {
+        const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
+        // W_hi tile: W_hi*x_hi + W_hi*x_lo
+        umma::mbar_wait(&full[stage], phase);
+        umma::tc_fence_after();
+        uint32_t a_lo = st_lo32 + (uint32_t)stage * kStageStep;
+        if (umma::elect_one()) {
+          if (full_k) {
+            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, first ? 0u : 1u);
+            umma::mma_bf16_ss_lo(d_tmem, a_lo, bl, kIdesc, 1u);
+#pragma unroll
+            for (int ks = 1; ks < 4; ++ks) {
+              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+            }
+          } else {
+            for (int ks = 0; ks < nks_last; ++ks) {
+              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
+              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+            }
+          }
+          umma::mma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        // W_lo tile: W_lo*x_hi
+        umma::mbar_wait(&full[stage], phase);
+        umma::tc_fence_after();
+        a_lo = st_lo32 + (uint32_t)stage * kStageStep;
+        if (umma::elect_one()) {
+          if (full_k) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+          } else {
+            for (int ks = 0; ks < nks_last; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+          }
+          umma::mma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+      };
+      // Accumulator slots: 3 pairs x 2 slots x NC TMEM columns.  Layer i accumulates its M-blocks {0,1} in pair a_i and
+      // {2,3} in pair b_i = a_i + 1; a_{i+1} = a_i + 2 (mod 3) is the pair layer i does not touch, so phase A of layer i+1
+      // can run while layer i's epilogue is still draining a_i / b_i, and b_{i+1} = a_i is drained by the time phase B starts.
+      int pair_a = 0;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l < L; ++l) {
           const int nmb = plan.nmb[l], nkc = plan.nkc[l], nks_last = plan.nks_last[l];
-          umma::mbar_wait(act_ready, act_phase);
-          act_phase ^= 1u;
-          umma::tc_fence_after();
-          for (int mb = 0; mb < nmb; ++mb) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(mb * NC);
-            for (int kc = 0; kc < nkc; ++kc) {
+          const int nA = nmb < 2 ? nmb : 2;
+          const int pair_b = (pair_a + 1) % 3;
+          const int nsrc = (l == 0) ? 1 : plan.nmb[l - 1];          // readiness events of this layer's input
+          const int cpe = (l == 0) ? nkc : 2;                       // activation chunks published per event
+          // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
+          for (int ev = 0; ev < nsrc; ++ev) {
+            umma::mbar_wait(act_ready, act_phase);
+            act_phase ^= 1u;
+            umma::tc_fence_after();
+            const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * cpe);
+            for (int kc = ev * cpe; kc < kc_end; ++kc) {
               const bool full_k = (kc != nkc - 1) || (nks_last == 4);
-              const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
-              // W_hi tile: W_hi*x_hi + W_hi*x_lo
-              umma::mbar_wait(&full[stage], phase);
-              umma::tc_fence_after();
-              uint32_t a_lo = st_lo32 + (uint32_t)stage * kStageStep;
-              if (umma::elect_one()) {
-                if (full_k) {
-                  umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, (uint32_t)(kc != 0));
-                  umma::mma_bf16_ss_lo(d_tmem, a_lo, bl, kIdesc, 1u);
-#pragma unroll
-                  for (int ks = 1; ks < 4; ++ks) {
-                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
-                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
-                  }
-                } else {
-                  for (int ks = 0; ks < nks_last; ++ks) {
-                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, (uint32_t)((kc | ks) != 0));
-                    umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
-                  }
-                }
-                umma::mma_commit(&empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
-              // W_lo tile: W_lo*x_hi
-              umma::mbar_wait(&full[stage], phase);
-              umma::tc_fence_after();
-              a_lo = st_lo32 + (uint32_t)stage * kStageStep;
-              if (umma::elect_one()) {
-                if (full_k) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
-                } else {
-                  for (int ks = 0; ks < nks_last; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
-                }
-                umma::mma_commit(&empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+              for (int mb = 0; mb < nA; ++mb)
+                tile_pair(tmem_base + (uint32_t)((2 * pair_a + mb) * NC), kc, kc == 0, full_k, nks_last);
             }
+          }
+          // phase B: every chunk is there and the previous layer's accumulators (pair_b) are drained
+          for (int kc = 0; kc < nkc; ++kc) {
+            const bool full_k = (kc != nkc - 1) || (nks_last == 4);
+            for (int mb = nA; mb < nmb; ++mb)
+              tile_pair(tmem_base + (uint32_t)((2 * pair_b + (mb - nA)) * NC), kc, kc == 0, full_k, nks_last);
           }
           if (umma::elect_one()) umma::mma_commit(layer_full);
           __syncwarp();
+          pair_a = (pair_a + 2) % 3;
         }
       }
     }
@@ -299,6 +330,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const int nkc0 = plan.nkc[0];
     uint32_t lf_phase = 0, pr_phase = 0, pf_phase = 0;
+    int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
     float a_cur[kTcMaxAct];
 
@@ -359,25 +391,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;          // stmatrix row owned by this lane (within 16 candidates)
           const int fsel = ((lane >> 3) & 1) * 8;                         // ... of the feature-group matrix 0 / +8
           for (int mb = 0; mb < plan.nmb[l]; ++mb) {
+            const int slot = (mb < 2) ? (2 * pair_a + mb) : (2 * ((pair_a + 1) % 3) + (mb - 2));
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int fbase = mb * 128 + warp * 32 + half * 16;         // 16 features handled by this (warp, half)
               const float bias_a = __ldg(P + md.b_off[l] + fbase + (lane >> 2));
               const float bias_b = __ldg(P + md.b_off[l] + fbase + (lane >> 2) + 8);
-              const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32 + half * 16) << 16) + (uint32_t)(mb * NC);
+              const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32 + half * 16) << 16) + (uint32_t)(slot * NC);
               const uint32_t chunk_off = (uint32_t)(fbase >> 6) * kChunkBytes;
               const uint32_t fcol = (uint32_t)((fbase & 63) + fsel) >> 3;  // 16-byte column of this lane's matrix rows
-#pragma unroll 2
+              uint32_t r[NC / 16][8];
+#pragma unroll
+              for (int cb = 0; cb < NC / 16; ++cb) umma::tmem_ld_16x256b_x2(t_addr + (uint32_t)(cb * 16), r[cb]);
+              umma::tmem_ld_wait();                                        // one wait for the whole 16 x NC block
+#pragma unroll
               for (int cb = 0; cb < NC / 16; ++cb) {
-                uint32_t r[8];
-                umma::tmem_ld_16x256b_x2(t_addr + (uint32_t)(cb * 16), r);
-                umma::tmem_ld_wait();
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float b = (q & 1) ? bias_b : bias_a;
-                  const float v0 = fmaxf(__uint_as_float(r[2 * q]) + b, 0.f);          // core/utils.py:119-126 (ReLU dense)
-                  const float v1 = fmaxf(__uint_as_float(r[2 * q + 1]) + b, 0.f);
+                  const float v0 = fmaxf(__uint_as_float(r[cb][2 * q]) + b, 0.f);      // core/utils.py:119-126 (ReLU dense)
+                  const float v1 = fmaxf(__uint_as_float(r[cb][2 * q + 1]) + b, 0.f);
                   umma::split_bf16x2(v0, v1, hi[q], lo[q]);
                 }
                 const uint32_t cand = (uint32_t)(cb * 16 + cand_l);
@@ -386,11 +420,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
                 umma::stmatrix_x4_trans(act_lo_addr + off, lo[0], lo[1], lo[2], lo[3]);
               }
             }
+            // chunks 2mb, 2mb+1 of the next layer's input are complete: publish them (one readiness event per M-block)
+            umma::fence_proxy_async_smem();
+            umma::tc_fence_before();
+            umma::mbar_arrive(act_ready);
           }
         }
-        umma::fence_proxy_async_smem();
-        umma::tc_fence_before();
-        umma::mbar_arrive(act_ready);
+        pair_a = (pair_a + 2) % 3;
       }
       // ---------------- output layer: y -> denormalised delta -> exchange buffer
       if (t + 1 < H) load_actions(t + 1);                 // prefetch the next step's actions (HBM) under the MMA wait
@@ -402,18 +438,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         const bool frow = f < D;
         const float bias = frow ? __ldg(P + md.b_off[L - 1] + f) : 0.f;
         const float sc = frow ? n_dscale[f] : 0.f, mu = frow ? n_dmean[f] : 0.f;
-#pragma unroll 1
-        for (int c16 = 0; c16 < NC / 16; ++c16) {
-          uint32_t r[16];
-          umma::tmem_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(c16 * 16), r);
-          umma::tmem_ld_wait();
-          if (frow) {
+        uint32_t r[NC / 16][16];
+#pragma unroll
+        for (int c16 = 0; c16 < NC / 16; ++c16)
+          umma::tmem_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(2 * pair_a * NC + c16 * 16), r[c16]);
+        umma::tmem_ld_wait();
+        if (frow) {
+#pragma unroll
+          for (int c16 = 0; c16 < NC / 16; ++c16)
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              dbuf[f * NCP + c16 * 16 + i] = (__uint_as_float(r[i]) + bias) * sc + mu;   // mlp_dynamics.py:269-270
-          }
+              dbuf[f * NCP + c16 * 16 + i] = (__uint_as_float(r[c16][i]) + bias) * sc + mu;   // mlp_dynamics.py:269-270
         }
       }
+      pair_a = (pair_a + 2) % 3;
       umma::tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (ensemble) {
@@ -426,25 +464,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
         const float inv_e = 1.0f / (float)csize;
         const uint32_t dbuf_addr = umma::smem_u32(dbuf);
-        for (int k = 0; k < D; ++k) {
-          float d;
+        for (int k0 = 0; k0 < D; k0 += 4) {
+          float dv[4];
           if (ensemble) {
-            float pe[8];
+            float pe[4][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              pe[e] = (e < csize) ? umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)((k * NCP + n) * 4), (uint32_t)e)) : 0.f;
-            d = 0.f;
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) d += pe[e];            // member order 0..E-1 (unused slots add +0)
-            d *= inv_e;
+              for (int e = 0; e < 8; ++e)
+                pe[u][e] = (e < csize && k0 + u < D)
+                               ? umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)(((k0 + u) * NCP + n) * 4), (uint32_t)e))
+                               : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float d = 0.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) d += pe[u][e];        // member order 0..E-1 (unused slots add +0)
+              dv[u] = d * inv_e;
+            }
           } else {
-            d = dbuf[k * NCP + n];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dv[u] = (k0 + u < D) ? dbuf[(k0 + u) * NCP + n] : 0.f;
           }
-          const float s_new = state[k * NCP + n] + d;       // mlp_dynamics.py:220
-          state[k * NCP + n] = s_new;
-          if (k == D - 3) { dx = d; nx0 = s_new; }
-          if (k == D - 2) nx1 = s_new;
-          if (k == D - 1) nx2 = s_new;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u;
+            if (k < D) {
+              const float d = dv[u];
+              const float s_new = state[k * NCP + n] + d;       // mlp_dynamics.py:220
+              state[k * NCP + n] = s_new;
+              if (k == D - 3) { dx = d; nx0 = s_new; }
+              if (k == D - 2) nx1 = s_new;
+              if (k == D - 1) nx2 = s_new;
+            }
+          }
         }
         const float rew = reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2);
         ret = fmaf(__ldg(a.discount_pow + t), rew, ret);     // mpc_controller.py:126
