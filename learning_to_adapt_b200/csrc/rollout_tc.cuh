@@ -169,10 +169,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   uint64_t* full = bars;                      // [kTcStages]
   uint64_t* empty = bars + kTcStages;         // [kTcStages]
   uint64_t* layer_full = bars + 2 * kTcStages;
-  uint64_t* act_ready = layer_full + 1;
-  uint64_t* peer_ready = layer_full + 2;
-  uint64_t* peer_free = layer_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 4);
+  uint64_t* act_ready = layer_full + 1;       // [4]: one barrier per readiness event (source M-block) of a layer's input, so the
+                                              // MMA issuer can lag several events behind without mbarrier parity aliasing
+  uint64_t* peer_ready = layer_full + 5;
+  uint64_t* peer_free = layer_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 7);
   float* red_v = reinterpret_cast<float*>(tmem_slot + 2);   // [4]
   int* red_i = reinterpret_cast<int*>(red_v + 4);           // [4]
   int* s_flag = red_i + 4;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
     umma::mbar_init(layer_full, 1);
-    umma::mbar_init(act_ready, 128);
+    for (int j = 0; j < 4; ++j) umma::mbar_init(&act_ready[j], 128);
     umma::mbar_init(peer_ready, csize);
     umma::mbar_init(peer_free, csize);
     umma::fence_barrier_init();
@@ -299,8 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           const int cpe = (l == 0) ? nkc : 2;                       // activation chunks published per event
           // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
           for (int ev = 0; ev < nsrc; ++ev) {
-            umma::mbar_wait(act_ready, act_phase);
-            act_phase ^= 1u;
+            umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
+            act_phase ^= (1u << ev);
             umma::tc_fence_after();
             const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * cpe);
             for (int kc = ev * cpe; kc < kc_end; ++kc) {
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       }
       umma::fence_proxy_async_smem();
       umma::tc_fence_before();
-      umma::mbar_arrive(act_ready);
+      umma::mbar_arrive(&act_ready[0]);
     };
 
     load_actions(0);
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             // chunks 2mb, 2mb+1 of the next layer's input are complete: publish them (one readiness event per M-block)
             umma::fence_proxy_async_smem();
             umma::tc_fence_before();
-            umma::mbar_arrive(act_ready);
+            umma::mbar_arrive(&act_ready[mb]);
           }
         }
         pair_a = (pair_a + 2) % 3;
