@@ -158,6 +158,16 @@ int l2a_cem_refit(l2a_ctx* ctx, const float* returns, const float* clipped, int 
 int l2a_debug_umma_tile(l2a_ctx* ctx, const float* A, const float* B, float* C, int n, int k, int variant,
                         void* stream);
 
+/* Weight-stream pipeline microbenchmark: every CTA of `grid` streams n_tiles_per_pass tiles of tile_bytes from `blob`
+ * `passes` times through a `stages`-deep TMA/mbarrier ring (consumer holds each tile hold_cycles); cycles_out[grid] (device
+ * int64) receives the SM cycles each CTA took. */
+int l2a_debug_stream(l2a_ctx* ctx, const void* blob, int n_tiles_per_pass, int passes, int stages, int tile_bytes,
+                     int hold_cycles, int grid, long long* cycles_out, void* stream);
+
+/* When set (device int64[128]), CTA 0 of the tcgen05 rollout records clock64() stamps of its pipeline events during
+ * horizon step 1 (see L2A_STAMP slots in csrc/rollout_tc.cuh).  NULL switches it off. */
+int l2a_debug_set_timeline(l2a_ctx* ctx, long long* buf128);
+
 #ifdef __cplusplus
 }
 #endif

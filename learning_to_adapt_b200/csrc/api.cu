@@ -36,6 +36,7 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 struct l2a_ctx {
+  long long* timeline = nullptr;   // optional diagnostics buffer (l2a_debug_set_timeline)
   int device = 0;
   int num_sms = 0;
   int max_smem_optin = 0;
@@ -402,6 +403,7 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   ta.groups_per_env = groups;
   ta.returns = returns;
   ta.red = ra;
+  ta.timeline = c->timeline;
   switch (nc) {
     case 80: return launch_tc<80>(c, ta, csize, st);
     case 64: return launch_tc<64>(c, ta, csize, st);
@@ -560,5 +562,26 @@ extern "C" int l2a_debug_umma_tile(l2a_ctx* c, const float* A, const float* B, f
   debug_umma_tile_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, n, k, variant);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+extern "C" int l2a_debug_stream(l2a_ctx* c, const void* blob, int n_tiles_per_pass, int passes, int stages, int tile_bytes,
+                                int hold_cycles, int grid, long long* cycles_out, void* stream) {
+  if (!c || !blob || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (stages < 1 || stages > 13 || tile_bytes % 1024 != 0 || grid < 1) return fail(L2A_ERR_INVALID, "bad stages/tile_bytes/grid");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t smem = (size_t)stages * tile_bytes + 2 * stages * sizeof(uint64_t) + 1024 + 64;
+  if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "needs %zu B shared memory", smem);
+  CUDA_TRY(cudaFuncSetAttribute(debug_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  debug_stream_kernel<<<grid, 64, smem, (cudaStream_t)stream>>>((const uint8_t*)blob, n_tiles_per_pass, passes, stages, tile_bytes,
+                                                               hold_cycles, cycles_out);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+extern "C" int l2a_debug_set_timeline(l2a_ctx* c, long long* buf128) {
+  if (!c) return fail(L2A_ERR_INVALID, "NULL ctx");
+  c->timeline = buf128;
   return L2A_OK;
 }

@@ -93,3 +93,44 @@ __global__ void __launch_bounds__(128, 1) debug_umma_tile_kernel(const float* A,
 }
 
 }  // namespace l2a
+
+namespace l2a {
+// Diagnostics: pure weight-stream pipeline (TMA bulk copies of `tile_bytes` through an `stages`-deep mbarrier ring, the
+// consumer only waits and releases, optionally holding each tile for `hold_cycles`).  Reports SM cycles per CTA.
+__global__ void __launch_bounds__(64, 1) debug_stream_kernel(const uint8_t* blob, int n_tiles_per_pass, int passes, int stages,
+                                                             int tile_bytes, int hold_cycles, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * tile_bytes);
+  uint64_t* empty = full + stages;
+  const int tid = threadIdx.x;
+  blob += (size_t)(blockIdx.x % 5) * (size_t)n_tiles_per_pass * tile_bytes;     // five "members", like the ensemble rollout
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    umma::fence_barrier_init();
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  if (tid == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int p = 0; p < passes; ++p)
+      for (int t = 0; t < n_tiles_per_pass; ++t) {
+        umma::mbar_wait(&empty[stage], phase ^ 1u);
+        umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)tile_bytes);
+        umma::bulk_g2s(smem + (size_t)stage * tile_bytes, blob + (size_t)t * tile_bytes, (uint32_t)tile_bytes, &full[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+  } else if (tid == 32) {
+    int stage = 0; uint32_t phase = 0;
+    for (int p = 0; p < passes; ++p)
+      for (int t = 0; t < n_tiles_per_pass; ++t) {
+        umma::mbar_wait(&full[stage], phase);
+        if (hold_cycles > 0) { const long long h0 = clock64(); while (clock64() - h0 < hold_cycles) {} }
+        umma::mbar_arrive(&empty[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+  }
+  __syncthreads();
+  if (tid == 0) cycles_out[blockIdx.x] = clock64() - t0;
+}
+}  // namespace l2a

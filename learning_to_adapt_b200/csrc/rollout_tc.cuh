@@ -24,10 +24,11 @@
 namespace l2a {
 
 constexpr int kTcTileBytes = 16384;     // one [128 x 64] bf16 weight tile (hi or lo part)
-constexpr int kTcStages = 3;
+constexpr int kTcMaxStages = 8;         // weight-tile ring depth is per NC: as many 16 KB stages as shared memory allows (even, <= 8)
 constexpr int kTcMaxChunks = 8;         // activation width <= 512
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxAct = 16;           // action dim limit of this variant
+constexpr int kTcMaxObs = 48;           // obs dim limit of this variant (candidate state lives in registers)
 
 // Tile enumeration of one weight set's blob; consumed in exactly this order by the kernel.  Within a layer the M-blocks
 // are split into phase A (the first min(2, nmb) blocks) and phase B (the rest); each phase is K-OUTER:
@@ -51,8 +52,19 @@ __host__ __device__ inline int tc_tile_index(const TcPlan& p, int l, int mb, int
   return p.tile_off[l] + nkc * nA * 2 + ((kc * nB + (mb - nA)) * 2 + part);
 }
 
+// Layer-0 input feature order of the tensor-core path: [obs (D) | zero pad to a multiple of 8 | act (A) | zero pad]; the
+// padding lets the env step write whole 16-byte groups of state features and of action features with static register
+// indices.  in0_of_col maps a layer-0 K column to the reference's input feature (or -1 for padding).
+__host__ __device__ inline int tc_obs_pad(int D) { return (D + 7) & ~7; }
+__host__ __device__ inline int tc_in0_of_col(int D, int A, int c) {
+  const int d8 = tc_obs_pad(D);
+  if (c < d8) return c < D ? c : -1;
+  return (c - d8 < A) ? D + (c - d8) : -1;
+}
+
 inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
-  if (md.act_dim > kTcMaxAct || md.obs_dim > 128 || md.obs_dim < 3) return false;
+  if (md.act_dim > kTcMaxAct || md.obs_dim > kTcMaxObs || md.obs_dim < 3) return false;
+  if (tc_obs_pad(md.obs_dim) + md.act_dim > 64) return false;
   p->n_layers = md.n_layers;
   int off = 0;
   for (int l = 0; l < md.n_layers; ++l) {
@@ -62,8 +74,9 @@ inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
     if (l > 0 && din % 64 != 0) return false;
     if (din > 64 * kTcMaxChunks) return false;
     p->nmb[l] = (dout + 127) / 128;
-    p->nkc[l] = (din + 63) / 64;
-    const int rem = din - (p->nkc[l] - 1) * 64;
+    const int din_eff = (l == 0) ? tc_obs_pad(md.obs_dim) + md.act_dim : din;   // padded layer-0 layout
+    p->nkc[l] = (din_eff + 63) / 64;
+    const int rem = din_eff - (p->nkc[l] - 1) * 64;
     p->nks_last[l] = (rem + 15) / 16;
     p->tile_off[l] = off;
     off += p->nmb[l] * p->nkc[l] * 2;
@@ -99,8 +112,9 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const PrepArgs a) {
     uint16_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = kc * 64 + ch * 8 + i;
-      const float w = (f < dout && k < din) ? W[(size_t)k * dout + f] : 0.f;
+      int k = kc * 64 + ch * 8 + i;
+      if (l == 0) k = tc_in0_of_col(a.dims.obs_dim, a.dims.act_dim, k);
+      const float w = (f < dout && k >= 0 && k < din) ? W[(size_t)k * dout + f] : 0.f;
       umma::split_bf16(w, hi[i], lo[i]);
     }
     const uint32_t off = umma::sw128_offset(r, ch * 8);
@@ -126,6 +140,7 @@ struct TcArgs {
   int groups_per_env;
   float* returns;
   ReduceArgs red;
+  long long* timeline;          // diagnostics: clock64 stamps of CTA 0 at step 1 (null = off)
 };
 
 template <int NC>
@@ -134,23 +149,30 @@ struct TcSmem {
   static constexpr int kNCP = NC + 1;
   static constexpr size_t act_bytes = (size_t)2 * kTcMaxChunks * kChunkBytes;
   static constexpr size_t stage_off = act_bytes;
-  static constexpr size_t misc_off = stage_off + (size_t)kTcStages * kTcTileBytes;
+  static constexpr int kFit = (int)((232448 - (long long)act_bytes - 2048) / kTcTileBytes);
+  static constexpr int kStages = (kFit > kTcMaxStages ? kTcMaxStages : kFit) & ~1;
+  static_assert(kStages >= 2, "no room for the weight-tile ring");
+  static constexpr size_t misc_off = stage_off + (size_t)kStages * kTcTileBytes;
   static size_t total(int D, int A) {
-    size_t misc = sizeof(float) * ((size_t)D * kNCP + 4 * (size_t)D + 2 * (size_t)A) + 64 /*pad*/ + 16 * sizeof(uint64_t) + 64;
-    return misc_off + misc + 1024 /*alignment slack*/;
+    size_t misc = sizeof(float) * (4 * (size_t)D + 2 * (size_t)A) + 64 /*pad*/ + 32 * sizeof(uint64_t) + 64;
+    return misc_off + misc;       // the dynamic shared window is 1024-byte aligned (checked in the kernel)
   }
 };
+
+#define L2A_STAMP(slot) do { if (a.timeline && blockIdx.x == 0 && t == 1 && (threadIdx.x & 31) == 0) a.timeline[(slot)] = clock64(); } while (0)
 
 template <int NC>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs a) {
   using S = TcSmem<NC>;
   constexpr int kChunkBytes = S::kChunkBytes;
   constexpr int NCP = S::kNCP;
+  constexpr int kTcStages = S::kStages;
   constexpr uint32_t kIdesc = umma::make_idesc_bf16(128, NC);
   static_assert(NC % 16 == 0 && NC >= 16 && 6 * NC <= 512, "UMMA N constraint / six accumulator slots must fit the 512 TMEM columns");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  if ((umma::smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B atoms need 1024-byte alignment
   const MlpDims& md = a.dims;
   const TcPlan& plan = a.plan;
   const int D = md.obs_dim, A = md.act_dim, L = md.n_layers, H = a.horizon;
@@ -158,8 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   uint8_t* act_hi = smem;
   uint8_t* act_lo = smem + (size_t)kTcMaxChunks * kChunkBytes;
   uint8_t* stages = smem + S::stage_off;
-  float* state = reinterpret_cast<float*>(smem + S::misc_off);      // [D][NCP]
-  float* n_obs_mean = state + (size_t)D * NCP;
+  float* n_obs_mean = reinterpret_cast<float*>(smem + S::misc_off);
   float* n_obs_den = n_obs_mean + D;
   float* n_dmean = n_obs_den + D;
   float* n_dscale = n_dmean + D;
@@ -213,7 +234,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     n_dscale[i] = a.norm.delta_scale[i];
   }
   for (int i = tid; i < A; i += kTcThreads) { n_act_mean[i] = a.norm.act_mean[i]; n_act_den[i] = a.norm.act_den[i]; }
-  for (int i = tid; i < D * NC; i += kTcThreads) state[(i / NC) * NCP + (i % NC)] = a.obs0[(size_t)env * D + i / NC];
   umma::tc_fence_before();
   __syncthreads();
   if (ensemble) umma::cluster_sync_all();      // peers' barriers are initialised before any remote arrive
@@ -222,16 +242,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 
   if (warp == 4) {
     // ================================================================ TMA producer
-    if (lane == 0) {
-      int stage = 0;
+    // Two lanes issue alternate tiles (lane j owns stages j, j+2): the mbarrier / bulk-copy instruction latency of one
+    // issuing thread (~330 cycles per request) would otherwise cap the stream at 16 KB per 330 cycles.
+    if (lane < 2) {
+      static_assert(kTcStages % 2 == 0, "two producer lanes own alternate stages");
+      int stage = lane;
       uint32_t phase = 0;
-      for (int t = 0; t < H; ++t) {
-        for (int tile = 0; tile < plan.tiles_per_set; ++tile) {
-          umma::mbar_wait(&empty[stage], phase ^ 1u);
-          umma::mbar_arrive_expect_tx(&full[stage], kTcTileBytes);
-          umma::bulk_g2s(stages + (size_t)stage * kTcTileBytes, blob + (size_t)tile * kTcTileBytes, kTcTileBytes, &full[stage]);
-          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
-        }
+      const long long total_tiles = (long long)H * plan.tiles_per_set;
+      int tile = lane;
+      for (long long g = lane; g < total_tiles; g += 2) {
+        umma::mbar_wait(&empty[stage], phase ^ 1u);
+        umma::mbar_arrive_expect_tx(&full[stage], kTcTileBytes);
+        umma::bulk_g2s(stages + (size_t)stage * kTcTileBytes, blob + (size_t)tile * kTcTileBytes, kTcTileBytes, &full[stage]);
+        stage += 2;
+        if (stage >= kTcStages) { stage -= kTcStages; phase ^= 1u; }
+        tile += 2;
+        if (tile >= plan.tiles_per_set) tile -= plan.tiles_per_set;     // tiles_per_set is even (hi/lo pairs)
       }
     }
     __syncwarp();
@@ -298,11 +324,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           const int pair_b = (pair_a + 1) % 3;
           const int nsrc = (l == 0) ? 1 : plan.nmb[l - 1];          // readiness events of this layer's input
           const int cpe = (l == 0) ? nkc : 2;                       // activation chunks published per event
+          L2A_STAMP(4 * l + 0);
           // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
           for (int ev = 0; ev < nsrc; ++ev) {
             umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
             act_phase ^= (1u << ev);
             umma::tc_fence_after();
+            if (ev == 0) L2A_STAMP(4 * l + 3);
             const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * cpe);
             for (int kc = ev * cpe; kc < kc_end; ++kc) {
               const bool full_k = (kc != nkc - 1) || (nks_last == 4);
@@ -310,6 +338,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
                 tile_pair(tmem_base + (uint32_t)((2 * pair_a + mb) * NC), kc, kc == 0, full_k, nks_last);
             }
           }
+          L2A_STAMP(4 * l + 1);
           // phase B: every chunk is there and the previous layer's accumulators (pair_b) are drained
           for (int kc = 0; kc < nkc; ++kc) {
             const bool full_k = (kc != nkc - 1) || (nks_last == 4);
@@ -318,6 +347,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           }
           if (umma::elect_one()) umma::mma_commit(layer_full);
           __syncwarp();
+          L2A_STAMP(4 * l + 2);
           pair_a = (pair_a + 2) % 3;
         }
       }
@@ -334,6 +364,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
     float a_cur[kTcMaxAct];
+    float st[kTcMaxObs];                                 // this candidate's state, float32, in registers for the whole rollout
+#pragma unroll
+    for (int k = 0; k < kTcMaxObs; ++k) st[k] = (k < D) ? __ldg(a.obs0 + (size_t)env * D + k) : 0.f;
+    const int d8 = tc_obs_pad(D);
 
     auto load_actions = [&](int t) {
       const float* src = a.actions + (long long)t * a.act_stride_t + row * a.act_stride_row;
@@ -347,24 +381,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 #pragma unroll
         for (int j = 0; j < kTcMaxAct; ++j) s = fmaf(a_cur[j], a_cur[j], s);
         asq = s;
-        for (int g = 0; g < nkc0 * 8; ++g) {
-          uint16_t hi[8], lo[8];
+        // layer-0 input layout: [obs | pad8 | act | pad]  (tc_in0_of_col); groups of 8 features = one 16-byte store
+        auto store_group = [&](int g, const float (&v)[8]) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = g * 8 + i;
-            float v = 0.f;
-            if (k < D) v = (state[k * NCP + n] - n_obs_mean[k]) / n_obs_den[k];       // mlp_dynamics.py:265-266
-            else if (k < D + A) {
-              float av = 0.f;
+          for (int q = 0; q < 4; ++q) umma::split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+          const uint32_t off = umma::sw128_offset((uint32_t)n, (uint32_t)g * 8u);
+          *reinterpret_cast<uint4*>(act_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(act_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        };
 #pragma unroll
-              for (int j = 0; j < kTcMaxAct; ++j) av = (j == k - D) ? a_cur[j] : av;
-              v = (av - n_act_mean[k - D]) / n_act_den[k - D];
+        for (int g = 0; g < kTcMaxObs / 8; ++g) {
+          if (g * 8 < d8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int k = g * 8 + i;
+              v[i] = (k < D) ? (st[k] - n_obs_mean[k]) / n_obs_den[k] : 0.f;               // mlp_dynamics.py:265-266
             }
-            umma::split_bf16(v, hi[i], lo[i]);
+            store_group(g, v);
           }
-          const uint32_t off = (uint32_t)(g >> 3) * kChunkBytes + umma::sw128_offset(n, (g & 7) * 8);
-          *reinterpret_cast<uint4*>(act_hi + off) = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
-          *reinterpret_cast<uint4*>(act_lo + off) = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+        }
+#pragma unroll
+        for (int ga = 0; ga < kTcMaxAct / 8; ++ga) {
+          if (ga * 8 < A) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = ga * 8 + i;
+              v[i] = (j < A) ? (a_cur[j] - n_act_mean[j]) / n_act_den[j] : 0.f;
+            }
+            store_group(d8 / 8 + ga, v);
+          }
+        }
+        // zero the rest of the K range the MMAs read (nks_last 16-wide k-steps of the single chunk)
+        {
+          const int used = d8 / 8 + (A + 7) / 8, need = plan.nks_last[0] * 2;
+          const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int g = used; g < need; ++g) store_group(g, z);
         }
       }
       umma::fence_proxy_async_smem();
@@ -381,6 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         umma::mbar_wait(layer_full, lf_phase);
         lf_phase ^= 1u;
         umma::tc_fence_after();
+        if (warp == 0) L2A_STAMP(32 + 4 * l + 0);
         if (l == 0 && ensemble && t > 0) {               // peers have finished reading my dbuf (aliases act chunks >= 1)
           umma::mbar_wait_cluster(peer_free, pf_phase);
           pf_phase ^= 1u;
@@ -425,8 +480,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             umma::fence_proxy_async_smem();
             umma::tc_fence_before();
             umma::mbar_arrive(&act_ready[mb]);
+            if (warp == 0 && mb == 0) L2A_STAMP(32 + 4 * l + 1);
           }
         }
+        if (warp == 0) L2A_STAMP(32 + 4 * l + 2);
         pair_a = (pair_a + 2) % 3;
       }
       // ---------------- output layer: y -> denormalised delta -> exchange buffer
@@ -434,6 +491,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       umma::mbar_wait(layer_full, lf_phase);
       lf_phase ^= 1u;
       umma::tc_fence_after();
+      if (warp == 0) L2A_STAMP(60);
       if (warp * 32 < D) {
         const int f = tid;
         const bool frow = f < D;
@@ -455,48 +513,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       pair_a = (pair_a + 2) % 3;
       umma::tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0) L2A_STAMP(61);
       if (ensemble) {
         if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_ready), (uint32_t)tid));
         umma::mbar_wait_cluster(peer_ready, pr_phase);
         pr_phase ^= 1u;
       }
+      if (warp == 0) L2A_STAMP(62);
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
         const float inv_e = 1.0f / (float)csize;
         const uint32_t dbuf_addr = umma::smem_u32(dbuf);
-        for (int k0 = 0; k0 < D; k0 += 4) {
-          float dv[4];
-          if (ensemble) {
-            float pe[4][8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+        for (int k0 = 0; k0 < kTcMaxObs; k0 += 4) {
+          if (k0 < D) {
+            float dv[4];
+            if (ensemble) {
+              float pe[4][8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                pe[u][e] = (e < csize && k0 + u < D)
-                               ? umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)(((k0 + u) * NCP + n) * 4), (uint32_t)e))
-                               : 0.f;
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  pe[u][e] = (e < csize && k0 + u < D)
+                                 ? umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)(((k0 + u) * NCP + n) * 4), (uint32_t)e))
+                                 : 0.f;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float d = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d += pe[u][e];      // member order 0..E-1 (unused slots add +0)
+                dv[u] = d * inv_e;
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) dv[u] = (k0 + u < D) ? dbuf[(k0 + u) * NCP + n] : 0.f;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float d = 0.f;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) d += pe[u][e];        // member order 0..E-1 (unused slots add +0)
-              dv[u] = d * inv_e;
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dv[u] = (k0 + u < D) ? dbuf[(k0 + u) * NCP + n] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u;
-            if (k < D) {
-              const float d = dv[u];
-              const float s_new = state[k * NCP + n] + d;       // mlp_dynamics.py:220
-              state[k * NCP + n] = s_new;
-              if (k == D - 3) { dx = d; nx0 = s_new; }
-              if (k == D - 2) nx1 = s_new;
-              if (k == D - 1) nx2 = s_new;
+              const int k = k0 + u;
+              if (k < D) {
+                const float d = dv[u];
+                const float s_new = st[k] + d;                  // mlp_dynamics.py:220
+                st[k] = s_new;
+                if (k == D - 3) { dx = d; nx0 = s_new; }
+                if (k == D - 2) nx1 = s_new;
+                if (k == D - 1) nx2 = s_new;
+              }
             }
           }
         }
@@ -507,7 +570,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_free), (uint32_t)tid));
       }
+      if (warp == 0) L2A_STAMP(63);
       if (t + 1 < H) write_x();
+      if (warp == 0) L2A_STAMP(64);
     }
 
     // ---------------- per-CTA argmax; one CTA per cluster publishes

@@ -1,0 +1,37 @@
+"""Development probe: in-kernel timeline of CTA 0 during one horizon step of the headline rollout (run under gpurun)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import mpc_oracle as O  # noqa: E402
+from learning_to_adapt_b200.engine import PlanningEngine  # noqa: E402
+
+env, hidden, n, h, m, nsets, mode = "half_cheetah", (512, 512, 512), 2000, 20, 1, 5, 2
+prob = O.make_problem(env, hidden_sizes=hidden, n_sets=nsets, m=m, seed=0)
+eng = PlanningEngine(prob["obs_dim"], prob["act_dim"], hidden, n_sets=nsets)
+for i, p in enumerate(prob["param_sets"]):
+    eng.set_params(i, p)
+eng.set_normalization(prob["norm"])
+obs = eng._f32(prob["obs0"])
+low, high = eng._f32(prob["low"]), eng._f32(prob["high"])
+acts = torch.rand((h, n * m, prob["act_dim"]), device="cuda") * (high - low) + low
+tl = torch.zeros(128, dtype=torch.int64, device="cuda")
+eng.lib.l2a_debug_set_timeline(eng._ctx, C.c_void_p(tl.data_ptr()))
+for _ in range(3):
+    eng.rollout(obs, acts, n, h, prob["reward_kind"], prob["dt"], set_mode=mode, first_set=0, n_sets=nsets, want_returns=False)
+torch.cuda.synchronize()
+t = tl.cpu().numpy()
+t0 = t[0]
+L = len(hidden) + 1
+print("MMA warp (cycles since layer-0 start of step 1):")
+for l in range(L):
+    b = 4 * l
+    print("  layer %d: enter %7d  first-act-ready %7d  phaseA-done %7d  committed %7d" % (l, t[b] - t0, t[b + 3] - t0, t[b + 1] - t0, t[b + 2] - t0))
+print("epilogue warp 0:")
+for l in range(L - 1):
+    b = 32 + 4 * l
+    print("  layer %d: layer_full seen %7d  mb0 published %7d  all published %7d" % (l, t[b] - t0, t[b + 1] - t0, t[b + 2] - t0))
+print("  output: layer_full %7d  dbuf written %7d  peers ready %7d  env done %7d  x written %7d" % tuple(int(t[i] - t0) for i in (60, 61, 62, 63, 64)))
