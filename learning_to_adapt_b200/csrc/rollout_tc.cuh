@@ -24,7 +24,7 @@
 namespace l2a {
 
 constexpr int kTcTileBytes = 16384;     // one [128 x 64] bf16 weight tile (hi or lo part)
-constexpr int kTcMaxStages = 8;         // weight-tile ring depth is per NC: as many 16 KB stages as shared memory allows (even, <= 8)
+constexpr int kTcMaxStages = 4;         // weight-tile ring depth is per NC: as many 16 KB stages as shared memory allows (even, <= 8)
 constexpr int kTcMaxChunks = 8;         // activation width <= 512
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxAct = 16;           // action dim limit of this variant
@@ -149,10 +149,14 @@ struct TcSmem {
   static constexpr int kNCP = NC + 1;
   static constexpr size_t act_bytes = (size_t)2 * kTcMaxChunks * kChunkBytes;
   static constexpr size_t stage_off = act_bytes;
-  static constexpr int kFit = (int)((232448 - (long long)act_bytes - 2048) / kTcTileBytes);
-  static constexpr int kStages = (kFit > kTcMaxStages ? kTcMaxStages : kFit) & ~1;
+  // ring stage = one (hi, lo) tile pair = 32 KB = the three split-bf16 passes of a [128 x 64] weight block: one bulk copy,
+  // one full/empty handshake per 12 MMAs (the per-handshake mbarrier latency of the issuing threads, ~300 cycles, is what
+  // bounds a 16 KB-granular ring -- scripts/stream_probe.py)
+  static constexpr int kStageBytes = 2 * kTcTileBytes;
+  static constexpr int kFit = (int)((232448 - (long long)act_bytes - 2048) / kStageBytes);
+  static constexpr int kStages = kFit > kTcMaxStages ? kTcMaxStages : kFit;
   static_assert(kStages >= 2, "no room for the weight-tile ring");
-  static constexpr size_t misc_off = stage_off + (size_t)kStages * kTcTileBytes;
+  static constexpr size_t misc_off = stage_off + (size_t)kStages * kStageBytes;
   static size_t total(int D, int A) {
     size_t misc = sizeof(float) * (4 * (size_t)D + 2 * (size_t)A) + 64 /*pad*/ + 32 * sizeof(uint64_t) + 64;
     return misc_off + misc;       // the dynamic shared window is 1024-byte aligned (checked in the kernel)
@@ -229,11 +233,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   if (warp == 5) umma::tmem_alloc<512>(tmem_slot);
   for (int i = tid; i < D; i += kTcThreads) {
     n_obs_mean[i] = a.norm.obs_mean[i];
-    n_obs_den[i] = a.norm.obs_den[i];
+    n_obs_den[i] = 1.0f / a.norm.obs_den[i];              // reciprocal: x_n = (x - mean) * (1 / (std + 1e-10))
     n_dmean[i] = a.norm.delta_mean[i];
     n_dscale[i] = a.norm.delta_scale[i];
   }
-  for (int i = tid; i < A; i += kTcThreads) { n_act_mean[i] = a.norm.act_mean[i]; n_act_den[i] = a.norm.act_den[i]; }
+  for (int i = tid; i < A; i += kTcThreads) { n_act_mean[i] = a.norm.act_mean[i]; n_act_den[i] = 1.0f / a.norm.act_den[i]; }
   umma::tc_fence_before();
   __syncthreads();
   if (ensemble) umma::cluster_sync_all();      // peers' barriers are initialised before any remote arrive
@@ -242,22 +246,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 
   if (warp == 4) {
     // ================================================================ TMA producer
-    // Two lanes issue alternate tiles (lane j owns stages j, j+2): the mbarrier / bulk-copy instruction latency of one
-    // issuing thread (~330 cycles per request) would otherwise cap the stream at 16 KB per 330 cycles.
-    if (lane < 2) {
-      static_assert(kTcStages % 2 == 0, "two producer lanes own alternate stages");
-      int stage = lane;
+    if (lane == 0) {
+      int stage = 0;
       uint32_t phase = 0;
-      const long long total_tiles = (long long)H * plan.tiles_per_set;
-      int tile = lane;
-      for (long long g = lane; g < total_tiles; g += 2) {
-        umma::mbar_wait(&empty[stage], phase ^ 1u);
-        umma::mbar_arrive_expect_tx(&full[stage], kTcTileBytes);
-        umma::bulk_g2s(stages + (size_t)stage * kTcTileBytes, blob + (size_t)tile * kTcTileBytes, kTcTileBytes, &full[stage]);
-        stage += 2;
-        if (stage >= kTcStages) { stage -= kTcStages; phase ^= 1u; }
-        tile += 2;
-        if (tile >= plan.tiles_per_set) tile -= plan.tiles_per_set;     // tiles_per_set is even (hi/lo pairs)
+      const int pairs_per_set = plan.tiles_per_set / 2;
+      for (int t = 0; t < H; ++t) {
+        for (int pr = 0; pr < pairs_per_set; ++pr) {
+          umma::mbar_wait(&empty[stage], phase ^ 1u);
+          umma::mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
+          umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes, blob + (size_t)pr * S::kStageBytes, S::kStageBytes, &full[stage]);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
     __syncwarp();
@@ -270,43 +269,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       uint32_t phase = 0, act_phase = 0;
       const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
-      constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)kTcTileBytes >> 4;
+      constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)S::kStageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
       // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block
       auto tile_pair = [&](uint32_t d_tmem, int kc, bool first, bool full_k, int nks_last) {
         const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
-        // W_hi tile: W_hi*x_hi + W_hi*x_lo
         umma::mbar_wait(&full[stage], phase);
         umma::tc_fence_after();
-        uint32_t a_lo = st_lo32 + (uint32_t)stage * kStageStep;
+        const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         if (umma::elect_one()) {
           if (full_k) {
-            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, first ? 0u : 1u);
-            umma::mma_bf16_ss_lo(d_tmem, a_lo, bl, kIdesc, 1u);
+            umma::mma_bf16_ss_lo(d_tmem, a_hi, bh, kIdesc, first ? 0u : 1u);          // W_hi * x_hi
+            umma::mma_bf16_ss_lo(d_tmem, a_hi, bl, kIdesc, 1u);                       // W_hi * x_lo
+            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, 1u);                       // W_lo * x_hi
 #pragma unroll
             for (int ks = 1; ks < 4; ++ks) {
+              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
-              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
             }
           } else {
             for (int ks = 0; ks < nks_last; ++ks) {
-              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
-              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
+              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
             }
-          }
-          umma::mma_commit(&empty[stage]);
-        }
-        __syncwarp();
-        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
-        // W_lo tile: W_lo*x_hi
-        umma::mbar_wait(&full[stage], phase);
-        umma::tc_fence_after();
-        a_lo = st_lo32 + (uint32_t)stage * kStageStep;
-        if (umma::elect_one()) {
-          if (full_k) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
-          } else {
-            for (int ks = 0; ks < nks_last; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
           }
           umma::mma_commit(&empty[stage]);
         }
@@ -359,7 +345,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     const bool valid = n < nvalid;
     const long long row = (long long)env * a.n_candidates + c0 + (valid ? n : 0);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int nkc0 = plan.nkc[0];
     uint32_t lf_phase = 0, pr_phase = 0, pf_phase = 0;
     int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
@@ -397,7 +382,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int k = g * 8 + i;
-              v[i] = (k < D) ? (st[k] - n_obs_mean[k]) / n_obs_den[k] : 0.f;               // mlp_dynamics.py:265-266
+              v[i] = (k < D) ? (st[k] - n_obs_mean[k]) * n_obs_den[k] : 0.f;               // mlp_dynamics.py:265-266
             }
             store_group(g, v);
           }
@@ -409,7 +394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = ga * 8 + i;
-              v[i] = (j < A) ? (a_cur[j] - n_act_mean[j]) / n_act_den[j] : 0.f;
+              v[i] = (j < A) ? (a_cur[j] - n_act_mean[j]) * n_act_den[j] : 0.f;
             }
             store_group(d8 / 8 + ga, v);
           }
