@@ -209,7 +209,7 @@ def run_cuda(args):
         res = eng.rollout(obs_dev, pool[i % len(pool)], n, h, prob["reward_kind"], prob["dt"], set_mode=set_mode,
                           first_set=first_set, n_sets=n_sets, want_returns=False)
         if shard is not None:
-            return shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n)
+            return shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
         return res["best_ret"], res["best_idx"], res["best_act"]
 
     def barrier():
@@ -243,7 +243,7 @@ def run_cuda(args):
                           first_set=first_set, n_sets=n_sets, want_returns=False)
         k.record()
         if shard is not None:
-            shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n)
+            shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
         e.record()
         torch.cuda.synchronize()
         kern_ms.append(s.elapsed_time(k))

@@ -152,6 +152,17 @@ int l2a_cem_sample(l2a_ctx* ctx, const float* z, const double* mean, const doubl
 int l2a_cem_refit(l2a_ctx* ctx, const float* returns, const float* clipped, int n, int m, int ha, int num_elites,
                   double alpha, int compat, int32_t* rank_scratch, double* mean, double* std, void* stream);
 
+/* ---- K3: multi-GPU candidate shard (new; the reference is single-process) -------------------------
+ * Each rank rolls its slice of every env's candidates with l2a_rollout; the only exchange is ONE all-gather (NCCL,
+ * issued by the host through torch.distributed) of the packed per-env triple.
+ * l2a_shard_pack  : packed[m, 3+A] = (best_ret, (best_idx + idx_offset) >> 16, & 0xFFFF, best_act[A])   (fp32, exact)
+ * l2a_shard_select: gathered[G, m, 3+A] -> winner per env, np.argmax semantics over the concatenated candidates
+ *                   (policies/mpc_controller.py:128-129): max return, NaN wins, ties -> lowest global index. */
+int l2a_shard_pack(l2a_ctx* ctx, const float* best_ret, const int32_t* best_idx, const float* best_act, int64_t idx_offset,
+                   int m, int A, float* packed, void* stream);
+int l2a_shard_select(l2a_ctx* ctx, const float* gathered, int G, int m, int A, float* best_ret, int64_t* best_idx,
+                     float* best_act, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------------------------------------
  * Single tcgen05 GEMM tile through the same descriptor / TMEM code as the rollout kernel:
  * C[128, n] = A[128, k] * B[n, k]^T with A, B fp32 split into bf16 hi/lo on the device. */

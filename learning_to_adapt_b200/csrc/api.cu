@@ -15,6 +15,7 @@
 #include "debug_tile.cuh"
 #include "rollout_simt.cuh"
 #include "rollout_tc.cuh"
+#include "shard.cuh"
 
 using namespace l2a;
 
@@ -583,5 +584,28 @@ extern "C" int l2a_debug_stream(l2a_ctx* c, const void* blob, int n_tiles_per_pa
 extern "C" int l2a_debug_set_timeline(l2a_ctx* c, long long* buf128) {
   if (!c) return fail(L2A_ERR_INVALID, "NULL ctx");
   c->timeline = buf128;
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- K3 shard glue
+extern "C" int l2a_shard_pack(l2a_ctx* c, const float* best_ret, const int32_t* best_idx, const float* best_act,
+                              int64_t idx_offset, int m, int A, float* packed, void* stream) {
+  if (!c || !best_ret || !best_idx || !best_act || !packed) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (m < 1 || A < 1) return fail(L2A_ERR_INVALID, "m and A must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  shard_pack_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(best_ret, best_idx, best_act, idx_offset, m, A, packed);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+extern "C" int l2a_shard_select(l2a_ctx* c, const float* gathered, int G, int m, int A, float* best_ret, int64_t* best_idx,
+                                float* best_act, void* stream) {
+  if (!c || !gathered || !best_ret || !best_idx || !best_act) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (G < 1 || m < 1 || A < 1) return fail(L2A_ERR_INVALID, "G, m and A must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  shard_select_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gathered, G, m, A, best_ret, (long long*)best_idx, best_act);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
   return L2A_OK;
 }

@@ -36,14 +36,36 @@ __global__ void __launch_bounds__(128, 1) debug_umma_tile_kernel(const float* A,
     *reinterpret_cast<uint16_t*>(b_lo + off) = lo;
   }
   if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
-  if (warp == 0) umma::tmem_alloc<128>(tmem_slot);
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
   umma::fence_proxy_async_smem();
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int passes = (variant & 4) ? 1 : 3;              // variant bit 2: single bf16 pass (hi*hi only)
-  if (tid == 0) {
+  if (tid == 0 && (variant & 16)) {
+    // A operand staged into tensor memory with tcgen05.cp, then TS-mode MMAs (A from TMEM, B from shared memory)
+    const uint32_t idesc = umma::make_idesc_bf16(128, (uint32_t)n);
+    const uint32_t a_hi_t = tmem_base + 128u, a_lo_t = tmem_base + 128u + (uint32_t)(nkc * 32);
+    for (int kc = 0; kc < nkc; ++kc)
+      for (int ks = 0; ks < 4; ++ks) {
+        umma::tmem_cp_128x256b(a_hi_t + (uint32_t)(kc * 32 + ks * 8), umma::desc_lo32(umma::smem_u32(a_hi) + kc * 16384 + ks * 32));
+        umma::tmem_cp_128x256b(a_lo_t + (uint32_t)(kc * 32 + ks * 8), umma::desc_lo32(umma::smem_u32(a_lo) + kc * 16384 + ks * 32));
+      }
+    uint32_t acc = 0;
+    for (int kc = 0; kc < nkc; ++kc)
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t bh = umma::desc_lo32(umma::smem_u32(b_hi) + kc * b_chunk + ks * 32);
+        const uint32_t bl = umma::desc_lo32(umma::smem_u32(b_lo) + kc * b_chunk + ks * 32);
+        umma::mma_bf16_ts_lo(tmem_base, a_hi_t + (uint32_t)(kc * 32 + ks * 8), bh, idesc, acc);
+        acc = 1;
+        if (passes == 3) {
+          umma::mma_bf16_ts_lo(tmem_base, a_hi_t + (uint32_t)(kc * 32 + ks * 8), bl, idesc, 1u);
+          umma::mma_bf16_ts_lo(tmem_base, a_lo_t + (uint32_t)(kc * 32 + ks * 8), bh, idesc, 1u);
+        }
+      }
+    umma::mma_commit(bar);
+  } else if (tid == 0) {
     const uint32_t idesc = umma::make_idesc_bf16(128, (uint32_t)n);
     uint32_t acc = 0;
     for (int kc = 0; kc < nkc; ++kc)
@@ -89,7 +111,7 @@ __global__ void __launch_bounds__(128, 1) debug_umma_tile_kernel(const float* A,
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc<128>(tmem_base); }
+  if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc<512>(tmem_base); }
 }
 
 }  // namespace l2a

@@ -203,6 +203,26 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, u
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
       : "memory");
 }
+// A operand from TENSOR MEMORY (128 lanes x 8 columns per K=16 slice), B from shared memory.
+__device__ __forceinline__ void mma_bf16_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
+      : "memory");
+}
+// shared memory -> tensor memory copy of a [128 rows x 256 bit] slice (= one K=16 bf16 A-operand slice), source given by
+// the same matrix descriptor an SS-mode MMA would use.  Ordered with the issuing thread's other tcgen05.mma / cp ops.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t dst_tmem, uint32_t src_lo) {
+  asm volatile(
+      "{\n\t.reg .b64 ds;\n\t"
+      "mov.b64 ds, {%1, %2};\n\t"
+      "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n\t}" ::"r"(dst_tmem),
+      "r"(src_lo), "r"(kDescHi32)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -196,6 +196,23 @@ class PlanningEngine(object):
         N.check(self.lib.l2a_cem_refit(self._ctx, _ptr(returns), _ptr(clipped), int(n), int(m), int(ha), int(num_elites),
                                        float(alpha), 1 if compat else 0, _ptr(rank), _ptr(mean), _ptr(std), _stream()))
 
+    # ------------------------------------------------------------------ K3
+    def shard_pack(self, best_ret, best_idx, best_act, idx_offset):
+        m = best_ret.shape[0]
+        packed = torch.empty(m, 3 + self.act_dim, device=self.device, dtype=torch.float32)
+        N.check(self.lib.l2a_shard_pack(self._ctx, _ptr(best_ret), _ptr(best_idx), _ptr(best_act), int(idx_offset), int(m),
+                                        int(self.act_dim), _ptr(packed), _stream()))
+        return packed
+
+    def shard_select(self, gathered):
+        G, m, _ = gathered.shape
+        best_ret = torch.empty(m, device=self.device, dtype=torch.float32)
+        best_idx = torch.empty(m, device=self.device, dtype=torch.int64)
+        best_act = torch.empty(m, self.act_dim, device=self.device, dtype=torch.float32)
+        N.check(self.lib.l2a_shard_select(self._ctx, _ptr(gathered), int(G), int(m), int(self.act_dim), _ptr(best_ret),
+                                          _ptr(best_idx), _ptr(best_act), _stream()))
+        return best_ret, best_idx, best_act
+
     # ------------------------------------------------------------------ diagnostics
     def debug_umma_tile(self, A, B, variant=0):
         n, k = B.shape

@@ -66,7 +66,13 @@ class CandidateShard(object):
         dist.all_gather_into_tensor(out, packed, group=self.group)       # concatenated along dim 0 (NCCL and gloo)
         return out.view((self.world_size,) + tuple(packed.shape))
 
-    def combine(self, best_ret, best_idx_local, best_act, shard_lo):
+    def combine(self, best_ret, best_idx_local, best_act, shard_lo, engine=None):
+        """Per-rank best triples -> global winner on every rank.  With an engine (CUDA tensors) the pack / select steps are
+        the library's two small kernels around the one NCCL all-gather; without (CPU tensors, gloo tests) the same logic
+        runs as torch ops (pack_best / select_best)."""
+        if engine is not None and best_ret.is_cuda:
+            packed = engine.shard_pack(best_ret, best_idx_local, best_act, shard_lo)
+            return engine.shard_select(self.all_gather_best(packed))
         packed = pack_best(best_ret, best_idx_local.to(torch.int64) + int(shard_lo), best_act)
         return select_best(self.all_gather_best(packed))
 
@@ -89,7 +95,7 @@ class CandidateShard(object):
         res = eng.rollout(obs_dev, a_dev, n_loc, h, ctrl._reward_kind, ctrl._dt, discount=ctrl.discount,
                           set_mode=set_mode, first_set=first_set, n_sets=n_sets, layout="thra", want_returns=False,
                           kernel=ctrl.kernel)
-        best_ret, best_idx, best_act = self.combine(res["best_ret"], res["best_idx"], res["best_act"], lo)
+        best_ret, best_idx, best_act = self.combine(res["best_ret"], res["best_idx"], res["best_act"], lo, engine=eng)
         ctrl.last_plan = dict(best_ret=best_ret, best_idx=best_idx, best_act=best_act, returns=None)
         if ctrl.sampler == "numpy":
             idx = best_idx.cpu().numpy()

@@ -35,6 +35,9 @@ def test_umma_tile_matches_fp32_matmul(n, k):
     assert err < 2e-5, "split-bf16 tile error %.3e" % err
     got8 = eng.debug_umma_tile(dev(A), dev(B), variant=8).cpu().numpy()     # accumulator-fragment TMEM loads (16x256b)
     np.testing.assert_array_equal(got8, got)
+    if k <= 128:
+        got16 = eng.debug_umma_tile(dev(A), dev(B), variant=16).cpu().numpy()  # A operand via tcgen05.cp -> TMEM (TS-mode MMA)
+        np.testing.assert_array_equal(got16, got)
     got1 = eng.debug_umma_tile(dev(A), dev(B), variant=4).cpu().numpy()     # single bf16 pass: must be visibly worse
     err1 = np.abs(got1 - want).max() / np.abs(want).max()
     assert 1e-4 < err1 < 3e-2, "single-pass bf16 error %.3e" % err1
@@ -325,3 +328,35 @@ def test_cem_refit_matches_oracle(compat):
     np.testing.assert_allclose(d_mean.cpu().numpy(), mean, rtol=2e-3, atol=2e-3)
     np.testing.assert_allclose(d_std.cpu().numpy()[0], std, rtol=2e-3, atol=2e-3)
     assert_returns_close(res["returns"].cpu().numpy(), returns, rtol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ K3 shard glue
+def test_shard_pack_select_kernels_match_host_logic():
+    """The two library kernels around the NCCL all-gather agree with the torch restatement (parallel.pack_best /
+    select_best, which the gloo CPU tests pin to np.argmax semantics), including ties, NaN and indices >= 2**24."""
+    from learning_to_adapt_b200.engine import PlanningEngine
+    from learning_to_adapt_b200.parallel import pack_best, select_best
+    eng = PlanningEngine(20, 6, (32,), n_sets=1)
+    rng = np.random.RandomState(0)
+    G, m, A = 4, 7, 6
+    packs_k, packs_t = [], []
+    for g in range(G):
+        ret = rng.normal(size=m).astype(np.float32)
+        idx = rng.randint(0, 1000, size=m).astype(np.int32)
+        act = rng.normal(size=(m, A)).astype(np.float32)
+        if g in (1, 3):
+            ret[2] = 5.0                       # tie across ranks
+            ret[4] = np.nan                    # NaN on two ranks: lowest global index wins
+        off = g * (2 ** 24 + 7)
+        pk = eng.shard_pack(dev(ret), torch.as_tensor(idx, device="cuda"), dev(act), off)
+        pt = pack_best(torch.tensor(ret), torch.tensor(idx.astype(np.int64) + off), torch.tensor(act))
+        np.testing.assert_array_equal(pk.cpu().numpy(), pt.numpy())
+        packs_k.append(pk)
+        packs_t.append(pt)
+    r_k, i_k, a_k = eng.shard_select(torch.stack(packs_k).contiguous())
+    r_t, i_t, a_t = select_best(torch.stack(packs_t))
+    np.testing.assert_array_equal(i_k.cpu().numpy(), i_t.numpy())
+    np.testing.assert_array_equal(a_k.cpu().numpy(), a_t.numpy())
+    np.testing.assert_array_equal(np.isnan(r_k.cpu().numpy()), np.isnan(r_t.numpy()))
+    ok = ~np.isnan(r_t.numpy())
+    np.testing.assert_array_equal(r_k.cpu().numpy()[ok], r_t.numpy()[ok])
