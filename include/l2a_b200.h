@@ -175,6 +175,10 @@ int l2a_debug_umma_tile(l2a_ctx* ctx, const float* A, const float* B, float* C, 
 int l2a_debug_stream(l2a_ctx* ctx, const void* blob, int n_tiles_per_pass, int passes, int stages, int tile_bytes,
                      int hold_cycles, int grid, long long* cycles_out, void* stream);
 
+/* Tensor-pipe rate microbenchmark: SM cycles for `iters` tile pairs (12 split-bf16 MMAs, N = nc) with the A operand from
+ * shared memory (mode 0), from tensor memory (1), tcgen05.cp only (2), cp + TS-mode MMA pipelined (3). cycles_out: device int64[1]. */
+int l2a_debug_mma_rate(l2a_ctx* ctx, int nc, int mode, int iters, long long* cycles_out, void* stream);
+
 /* When set (device int64[128]), CTA 0 of the tcgen05 rollout records clock64() stamps of its pipeline events during
  * horizon step 1 (see L2A_STAMP slots in csrc/rollout_tc.cuh).  NULL switches it off. */
 int l2a_debug_set_timeline(l2a_ctx* ctx, long long* buf128);

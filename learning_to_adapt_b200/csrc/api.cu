@@ -609,3 +609,25 @@ extern "C" int l2a_shard_select(l2a_ctx* c, const float* gathered, int G, int m,
   CUDA_TRY(cudaGetLastError());
   return L2A_OK;
 }
+
+extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long long* cycles_out, void* stream) {
+  if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (mode < 0 || mode > 3 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t smem = 4 * 16384 + 2 * (size_t)nc * 128 + 64;
+  if (nc == 80) {
+    CUDA_TRY(cudaFuncSetAttribute(debug_mma_rate_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    debug_mma_rate_kernel<80><<<1, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_out);
+  } else if (nc == 64) {
+    CUDA_TRY(cudaFuncSetAttribute(debug_mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    debug_mma_rate_kernel<64><<<1, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_out);
+  } else if (nc == 128) {
+    CUDA_TRY(cudaFuncSetAttribute(debug_mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    debug_mma_rate_kernel<128><<<1, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_out);
+  } else {
+    return fail(L2A_ERR_INVALID, "nc must be 64, 80 or 128");
+  }
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}

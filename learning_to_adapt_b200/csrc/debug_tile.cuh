@@ -156,3 +156,92 @@ __global__ void __launch_bounds__(64, 1) debug_stream_kernel(const uint8_t* blob
   if (tid == 0) cycles_out[blockIdx.x] = clock64() - t0;
 }
 }  // namespace l2a
+
+namespace l2a {
+// Diagnostics: tensor-pipe timing of one "tile pair" (the 12 split-bf16 MMAs of a [128 x 64] weight block against NC
+// candidates) in four flavours, operands resident in shared memory (contents irrelevant):
+//   mode 0: SS  (A and B from shared memory)                                  -- what rollout_tc_kernel does
+//   mode 1: TS  (A pre-copied to TMEM once, only the MMAs are timed)
+//   mode 2: CP  (only the 8 tcgen05.cp of the hi and lo tile per pair)
+//   mode 3: CP+TS per pair, two TMEM staging slots (cp of pair p+1 issued before the MMAs of pair p)
+// cycles_out[0] = SM cycles for `iters` pairs.
+template <int NC>
+__global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t rate_smem[];
+  uint8_t* a_tiles = rate_smem;                       // 2 pairs x (hi 16 KB + lo 16 KB)
+  uint8_t* b_hi = rate_smem + 4 * 16384;              // [NC x 64] chunk
+  uint8_t* b_lo = b_hi + NC * 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + NC * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (4 * 16384 + 2 * NC * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(rate_smem)[i] = 0x3c003c00u;
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = umma::make_idesc_bf16(128, NC);
+  if (warp == 1) {
+    const uint32_t a0 = umma::desc_lo32(umma::smem_u32(a_tiles)), bh = umma::desc_lo32(umma::smem_u32(b_hi)), bl = umma::desc_lo32(umma::smem_u32(b_lo));
+    const uint32_t stage_step = 32768u >> 4, lo_step = 16384u >> 4;
+    const uint32_t t_stage = tmem_base + 384u;        // two staging slots of 64 columns (hi 32 + lo 32)
+    long long t0 = 0;
+    if (mode == 1 && umma::elect_one()) {
+      for (int ks = 0; ks < 4; ++ks) {
+        umma::tmem_cp_128x256b(t_stage + ks * 8, a0 + 2 * ks);
+        umma::tmem_cp_128x256b(t_stage + 32 + ks * 8, a0 + lo_step + 2 * ks);
+      }
+    }
+    __syncwarp();
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t st = (uint32_t)(it & 1);
+      const uint32_t a_hi = a0 + st * stage_step, a_lo = a_hi + lo_step;
+      const uint32_t d = tmem_base + (uint32_t)((it & 3) * NC);
+      if (umma::elect_one()) {
+        if (mode == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bh + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
+          }
+        } else if (mode == 1) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma::mma_bf16_ts_lo(d, t_stage + ks * 8, bh + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ts_lo(d, t_stage + ks * 8, bl + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ts_lo(d, t_stage + 32 + ks * 8, bh + 2 * ks, idesc, 1u);
+          }
+        } else {
+          const uint32_t ts_cur = t_stage + st * 64u;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma::tmem_cp_128x256b(ts_cur + ks * 8, a_hi + 2 * ks);
+            umma::tmem_cp_128x256b(ts_cur + 32 + ks * 8, a_lo + 2 * ks);
+          }
+          if (mode == 3) {
+            const uint32_t ts_prev = t_stage + (st ^ 1u) * 64u;     // MMAs of the previous pair (its cp was issued one iteration ago)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma::mma_bf16_ts_lo(d, ts_prev + ks * 8, bh + 2 * ks, idesc, 1u);
+              umma::mma_bf16_ts_lo(d, ts_prev + ks * 8, bl + 2 * ks, idesc, 1u);
+              umma::mma_bf16_ts_lo(d, ts_prev + 32 + ks * 8, bh + 2 * ks, idesc, 1u);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (umma::elect_one()) umma::mma_commit(bar);
+    __syncwarp();
+    umma::mbar_wait(bar, 0);
+    if ((tid & 31) == 0) cycles_out[0] = clock64() - t0;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc<512>(tmem_base); }
+}
+}  // namespace l2a

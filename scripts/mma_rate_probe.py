@@ -1,0 +1,21 @@
+"""Development probe: tensor-pipe cycles per tile pair, SS vs TS vs tcgen05.cp (run under gpurun)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from learning_to_adapt_b200 import _native as N  # noqa: E402
+
+lib = N.load()
+ctx = C.c_void_p()
+N.check(lib.l2a_ctx_create(0, C.byref(ctx)))
+out = torch.zeros(1, dtype=torch.int64, device="cuda")
+names = {0: "SS (A,B smem)", 1: "TS (A tmem)", 2: "cp only", 3: "cp + TS pipelined"}
+for nc in (64, 80, 128):
+    for mode in (0, 1, 2, 3):
+        for _ in range(2):
+            N.check(lib.l2a_debug_mma_rate(ctx, nc, mode, 400, C.c_void_p(out.data_ptr()), None))
+            torch.cuda.synchronize()
+        print("NC=%3d %-20s %7.1f cycles / tile pair (12 MMAs, ideal %d)" % (nc, names[mode], out.item() / 400.0, 12 * nc // 2))
