@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -284,6 +285,10 @@ static int launch_tc(l2a_ctx* c, const TcArgs& ta, int csize, cudaStream_t st) {
 
 static int pick_nc(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
   static const int opts[4] = {80, 64, 48, 32};
+  if (const char* ov = getenv("L2A_TC_NC")) {                   // tuning / experiments only
+    const int v = atoi(ov);
+    if (v == 80 || v == 64 || v == 48 || v == 32) return v;
+  }
   int best = 80;
   double best_cost = 1e300;
   const int slots = std::max(1, c->num_sms / csize);           // clusters resident at once (1 CTA / SM)

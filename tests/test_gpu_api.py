@@ -1,0 +1,172 @@
+"""GPU tests of the reference-facing API beyond single calls: the sampler's call order (samplers/sampler.py:81-91), pickling
+(meta_mlp_dynamics.py:434-445), fit -> plan, full-size CEM, and the 2-rank NCCL candidate shard."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpc_oracle as O
+from tests.helpers import RTOL, assert_argmax_consistent, assert_returns_close, dev, make_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(env_name="half_cheetah", hidden=(128, 128), mbs=4, lr=1e-2):
+    from learning_to_adapt_b200.dynamics.meta_mlp_dynamics import MetaMLPDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    env = SyntheticEnv(env_name)
+    model = MetaMLPDynamicsModel("dyn", env, hidden_sizes=hidden, meta_batch_size=mbs, inner_learning_rate=lr, seed=0)
+    return env, model
+
+
+def test_sampler_call_order_online_adaptation_loop():
+    """The GrBAL inner loop exactly as Sampler.obtain_samples drives it: per env step, once M+2 transitions exist,
+    switch_to_pre_adapt(); adapt(last M transitions per env); get_actions(obs) -- against the oracle at every step."""
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    num_envs, M, n, h, steps = 3, 6, 40, 4, 10
+    env, model = _models(mbs=num_envs)
+    prob = O.make_problem("half_cheetah", hidden_sizes=(128, 128), n_sets=1, m=num_envs, seed=11)
+    theta = prob["param_sets"][0]
+    model.set_params(theta)
+    model.set_normalization(prob["norm"])
+    ctrl = MPCController("policy", env, model, n_candidates=n, horizon=h)
+    rng = np.random.RandomState(0)
+    true_A = 0.02 * rng.normal(size=(prob["obs_dim"], prob["obs_dim"]))
+    obses = np.array(prob["obs0"])
+    paths = [dict(observations=[], actions=[]) for _ in range(num_envs)]
+    np.random.seed(5)
+    for step in range(steps):
+        adapted = None
+        if len(paths[0]["observations"]) > M + 1:                                          # sampler.py:82
+            a_obs = [np.stack(p["observations"][-M - 1:-1]) for p in paths]                 # :83-84
+            a_act = [np.stack(p["actions"][-M - 1:-1]) for p in paths]                      # :85-86
+            a_next = [np.stack(p["observations"][-M:]) for p in paths]                      # :87-88
+            model.switch_to_pre_adapt()                                                     # :89
+            model.adapt(a_obs, a_act, a_next)                                               # :90
+            adapted = O.adapt(a_obs, a_act, a_next, theta, prob["norm"], 1e-2)
+        state = np.random.get_state()
+        actions, infos = ctrl.get_actions(obses)                                           # :91
+        np.random.set_state(state)
+        cand = np.random.uniform(prob["low"], prob["high"], size=(h * n * num_envs, prob["act_dim"])).reshape(h, n * num_envs, -1)
+        sets, mode = ([theta], "shared") if adapted is None else (adapted, "per_env")
+        want, best, returns = O.rs_plan(obses, cand, sets, prob["norm"], prob["reward_kind"], prob["dt"], 1.0, mode)
+        assert_argmax_consistent(ctrl.last_plan["best_idx"].cpu().numpy(), returns)
+        if np.array_equal(ctrl.last_plan["best_idx"].cpu().numpy(), best):
+            np.testing.assert_array_equal(actions, want)
+        for k in range(num_envs):
+            paths[k]["observations"].append(obses[k])
+            paths[k]["actions"].append(actions[k])
+        obses = obses + obses @ true_A + 0.01 * rng.normal(size=obses.shape)                # stand-in for vec_env.step
+    assert model._adapted and model._num_adapted_models == num_envs
+
+
+def test_pickle_round_trip_keeps_weights_and_statistics():
+    """Snapshot layout of the reference: {'init_args', 'normalization', 'networks': [{'network_params': OrderedDict}]}
+    with 'hidden_i/kernel' ... keys (meta_mlp_dynamics.py:434-445, core/layers.py:103-113)."""
+    env, model = _models()
+    prob = O.make_problem("half_cheetah", hidden_sizes=(128, 128), n_sets=1, m=1, seed=3)
+    model.set_params(prob["param_sets"][0])
+    model.set_normalization(prob["norm"])
+    state = model.__getstate__()
+    assert set(state.keys()) == {"init_args", "normalization", "networks"}
+    assert list(state["networks"][0]["network_params"].keys()) == list(prob["param_sets"][0].keys())
+    clone = pickle.loads(pickle.dumps(model))
+    for k, v in prob["param_sets"][0].items():
+        np.testing.assert_array_equal(clone.get_params()[k], v)
+    rng = np.random.RandomState(1)
+    obs = prob["norm"]["obs"][0] + rng.normal(size=(5, prob["obs_dim"]))
+    act = rng.uniform(prob["low"], prob["high"], size=(5, prob["act_dim"]))
+    np.testing.assert_array_equal(clone.predict(obs, act), model.predict(obs, act))
+
+
+def test_fit_then_plan():
+    """fit() (torch glue, off the hot path) leaves the engine with trained weights + statistics the planner uses."""
+    from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    env = SyntheticEnv("half_cheetah")
+    model = MLPDynamicsModel("dyn", env, hidden_sizes=(128, 128), batch_size=100, seed=0)
+    rng = np.random.RandomState(0)
+    D, A = 20, 6
+    obs = rng.normal(size=(1500, D))
+    act = rng.uniform(-1, 1, size=(1500, A))
+    W = 0.05 * rng.normal(size=(D + A, D))
+    nxt = obs + np.tanh(np.concatenate([obs, act], 1) @ W)
+    before = None
+    model.compute_normalization(obs, act, nxt)
+    before = np.mean((model.predict(obs[:200], act[:200]) - nxt[:200]) ** 2)
+    model.fit(obs, act, nxt, epochs=15)
+    after = np.mean((model.predict(obs[:200], act[:200]) - nxt[:200]) ** 2)
+    assert after < 0.5 * before
+    ctrl = MPCController("policy", env, model, n_candidates=64, horizon=5, sampler="device")
+    a, _ = ctrl.get_actions(obs[:2])
+    assert a.shape == (2, A) and np.all(np.abs(a) <= 1.0)
+
+
+def test_cem_full_size_corrected_mode_improves_returns():
+    """BASELINE cfg4 shape (N=5000, 500 elites, 3 iters, H=30) on the tensor-core kernel; with the corrected elite
+    rule the planner's best return must not get worse across iterations' means (sanity), and the compat mode runs."""
+    from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=1, seed=2)
+    env = SyntheticEnv("half_cheetah")
+    model = MLPDynamicsModel("dyn", env, hidden_sizes=(512, 512))
+    model.set_params(prob["param_sets"][0])
+    model.set_normalization(prob["norm"])
+    best = {}
+    for compat in (True, False):
+        ctrl = MPCController("policy", env, model, use_cem=True, n_candidates=5000, horizon=30, num_cem_iters=3,
+                             percent_elites=0.1, alpha=0.1, sampler="device", cem_compat=compat)
+        torch.manual_seed(0)
+        a, _ = ctrl.get_actions(prob["obs0"])
+        assert a.shape == (1, 6) and np.all(np.isfinite(a))
+        best[compat] = float(ctrl.last_plan["best_ret"][0])
+        r = ctrl.last_plan["returns"].cpu().numpy()
+        assert r.shape == (1, 5000) and np.all(np.isfinite(r))
+    assert best[False] >= best[True] - 1e-3 * abs(best[True])      # true top-k elites cannot plan worse than the rank-mask subset here
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
+        from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+        from learning_to_adapt_b200.parallel import CandidateShard
+        from learning_to_adapt_b200.policies.mpc_controller import MPCController
+        prob = O.make_problem("half_cheetah", hidden_sizes=(128, 128), n_sets=1, m=2, seed=4)
+        env = SyntheticEnv("half_cheetah")
+        model = MLPDynamicsModel("dyn", env, hidden_sizes=(128, 128), device=rank)
+        model.set_params(prob["param_sets"][0])
+        model.set_normalization(prob["norm"])
+        n, h = 301, 5
+        ctrl = MPCController("policy", env, model, n_candidates=n, horizon=h, parallel=CandidateShard())
+        np.random.seed(9)
+        acts, _ = ctrl.get_actions(prob["obs0"])
+        cand = O.sample_rs_actions(9, prob["low"], prob["high"], h, n * 2)
+        want, best, returns = O.rs_plan(prob["obs0"], cand, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"])
+        ok = np.array_equal(ctrl.last_plan["best_idx"].cpu().numpy(), best) and np.array_equal(acts, want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_nccl_shard_equals_single_gpu_and_reference():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == [(0, True), (1, True)]
