@@ -152,6 +152,27 @@ int l2a_cem_sample(l2a_ctx* ctx, const float* z, const double* mean, const doubl
 int l2a_cem_refit(l2a_ctx* ctx, const float* returns, const float* clipped, int n, int m, int ha, int num_elites,
                   double alpha, int compat, int32_t* rank_scratch, double* mean, double* std, void* stream);
 
+/* ---- ReBAL: recurrent (single-layer LSTM) dynamics model and its planner rollout -----------
+ * Replaces RNNDynamicsModel.predict (dynamics/rnn_dynamics.py:233-252; cell = tf.nn.rnn_cell.LSTMCell, forget_bias 1, tanh,
+ * dynamics/core/utils.py:193-198, + dense output :227-234) and the H-step loop of RNNMPCController.get_rs_action
+ * (policies/rnn_mpc_controller.py:112-134) incl. repeat_hidden (:165-187): every candidate of env g starts from
+ * (hidden_c[g], hidden_h[g]).  cell_kernel [(D+A+Hs), 4*Hs] with gate order i, j, f, o; out_kernel [Hs, D].  fp32 SIMT. */
+typedef struct l2a_rnn_model l2a_rnn_model;
+int l2a_rnn_model_create(l2a_ctx* ctx, int obs_dim, int act_dim, int hidden, l2a_rnn_model** out);
+int l2a_rnn_model_destroy(l2a_ctx* ctx, l2a_rnn_model* model);
+int l2a_rnn_model_set_params(l2a_ctx* ctx, l2a_rnn_model* model, const float* cell_kernel, const float* cell_bias,
+                             const float* out_kernel, const float* out_bias, void* stream);
+int l2a_rnn_model_set_normalization(l2a_ctx* ctx, l2a_rnn_model* model, const float* obs_mean, const float* obs_den,
+                                    const float* act_mean, const float* act_den, const float* delta_mean,
+                                    const float* delta_scale, void* stream);
+/* p->set_mode / first_set / n_sets / kernel are ignored.  hidden_c, hidden_h: [m, Hs]. */
+int l2a_rnn_rollout(l2a_ctx* ctx, l2a_rnn_model* model, const l2a_rollout_params* p, const float* obs0, const float* hidden_c,
+                    const float* hidden_h, const float* actions, const float* discount_pow, float* returns, float* best_ret,
+                    int32_t* best_idx, float* best_act, void* stream);
+/* one step for n rows: delta_out [n, D] (denormalised), next state c_out, h_out [n, Hs] */
+int l2a_rnn_predict(l2a_ctx* ctx, l2a_rnn_model* model, const float* obs, const float* act, const float* hidden_c,
+                    const float* hidden_h, int n, float* delta_out, float* c_out, float* h_out, void* stream);
+
 /* ---- K3: multi-GPU candidate shard (new; the reference is single-process) -------------------------
  * Each rank rolls its slice of every env's candidates with l2a_rollout; the only exchange is ONE all-gather (NCCL,
  * issued by the host through torch.distributed) of the packed per-env triple.

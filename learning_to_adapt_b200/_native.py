@@ -15,7 +15,8 @@ EXPORTS = [
     "l2a_last_error", "l2a_version", "l2a_ctx_create", "l2a_ctx_destroy", "l2a_ctx_launch_count",
     "l2a_model_create", "l2a_model_destroy", "l2a_model_set_params", "l2a_model_get_params",
     "l2a_model_set_normalization", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
-    "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate",
+    "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
+    "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
 ]
 
 
@@ -65,6 +66,12 @@ def load():
     lib.l2a_cem_refit.argtypes = [vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp]
     lib.l2a_debug_umma_tile.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.l2a_debug_set_timeline.argtypes = [vp, vp]
+    lib.l2a_rnn_model_create.argtypes = [vp, i32, i32, i32, pp]
+    lib.l2a_rnn_model_destroy.argtypes = [vp, vp]
+    lib.l2a_rnn_model_set_params.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_rnn_model_set_normalization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_rnn_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_rnn_predict.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.l2a_debug_mma_rate.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.l2a_shard_pack.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.l2a_shard_select.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "debug_tile.cuh"
 #include "rollout_simt.cuh"
+#include "rollout_rnn_simt.cuh"
 #include "rollout_tc.cuh"
 #include "shard.cuh"
 
@@ -632,6 +633,142 @@ extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long 
   } else {
     return fail(L2A_ERR_INVALID, "nc must be 64, 80 or 128");
   }
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- ReBAL (LSTM) model
+struct l2a_rnn_model {
+  RnnDims dims;
+  float* params = nullptr;
+  float* norm = nullptr;
+  bool norm_set = false;
+  NormDev norm_dev() const {
+    const int D = dims.obs_dim, A = dims.act_dim;
+    NormDev n;
+    n.obs_mean = norm; n.obs_den = norm + D; n.act_mean = norm + 2 * D; n.act_den = norm + 2 * D + A;
+    n.delta_mean = norm + 2 * D + 2 * A; n.delta_scale = norm + 3 * D + 2 * A;
+    return n;
+  }
+};
+
+extern "C" int l2a_rnn_model_create(l2a_ctx* c, int obs_dim, int act_dim, int hidden, l2a_rnn_model** out) {
+  if (!c || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (obs_dim < 3 || act_dim < 1 || hidden < 1) return fail(L2A_ERR_INVALID, "bad obs_dim/act_dim/hidden");
+  CUDA_TRY(cudaSetDevice(c->device));
+  l2a_rnn_model* m = new (std::nothrow) l2a_rnn_model();
+  if (!m) return fail(L2A_ERR_INVALID, "out of host memory");
+  RnnDims& rd = m->dims;
+  rd.obs_dim = obs_dim; rd.act_dim = act_dim; rd.hidden = hidden;
+  int off = 0;
+  rd.wk_off = off; off += (obs_dim + act_dim + hidden) * 4 * hidden;
+  rd.bk_off = off; off += 4 * hidden;
+  rd.wo_off = off; off += hidden * obs_dim;
+  rd.bo_off = off; off += obs_dim;
+  rd.total = off;
+  if (rnn_smem_bytes(rd) > (size_t)c->max_smem_optin) { delete m; return fail(L2A_ERR_UNSUPPORTED, "LSTM width %d needs %zu B shared memory", hidden, rnn_smem_bytes(rd)); }
+  if (cudaMalloc(&m->params, sizeof(float) * (size_t)off) != cudaSuccess) { delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(rnn params)"); }
+  if (cudaMalloc(&m->norm, sizeof(float) * (size_t)(4 * obs_dim + 2 * act_dim)) != cudaSuccess) { cudaFree(m->params); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(rnn norm)"); }
+  *out = m;
+  return L2A_OK;
+}
+
+extern "C" int l2a_rnn_model_destroy(l2a_ctx* c, l2a_rnn_model* m) {
+  if (!m) return L2A_OK;
+  if (c) cudaSetDevice(c->device);
+  cudaFree(m->params);
+  cudaFree(m->norm);
+  delete m;
+  return L2A_OK;
+}
+
+extern "C" int l2a_rnn_model_set_params(l2a_ctx* c, l2a_rnn_model* m, const float* cell_kernel, const float* cell_bias,
+                                        const float* out_kernel, const float* out_bias, void* stream) {
+  if (!c || !m || !cell_kernel || !cell_bias || !out_kernel || !out_bias) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const RnnDims& rd = m->dims;
+  CUDA_TRY(cudaMemcpyAsync(m->params + rd.wk_off, cell_kernel, sizeof(float) * (size_t)(rd.obs_dim + rd.act_dim + rd.hidden) * 4 * rd.hidden, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(m->params + rd.bk_off, cell_bias, sizeof(float) * (size_t)4 * rd.hidden, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(m->params + rd.wo_off, out_kernel, sizeof(float) * (size_t)rd.hidden * rd.obs_dim, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(m->params + rd.bo_off, out_bias, sizeof(float) * (size_t)rd.obs_dim, cudaMemcpyDeviceToDevice, st));
+  return L2A_OK;
+}
+
+extern "C" int l2a_rnn_model_set_normalization(l2a_ctx* c, l2a_rnn_model* m, const float* obs_mean, const float* obs_den,
+                                               const float* act_mean, const float* act_den, const float* delta_mean,
+                                               const float* delta_scale, void* stream) {
+  if (!c || !m || !obs_mean || !obs_den || !act_mean || !act_den || !delta_mean || !delta_scale) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dims.obs_dim, A = m->dims.act_dim;
+  NormDev n = m->norm_dev();
+  CUDA_TRY(cudaMemcpyAsync((void*)n.obs_mean, obs_mean, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.obs_den, obs_den, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.act_mean, act_mean, sizeof(float) * A, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.act_den, act_den, sizeof(float) * A, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.delta_mean, delta_mean, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((void*)n.delta_scale, delta_scale, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  m->norm_set = true;
+  return L2A_OK;
+}
+
+extern "C" int l2a_rnn_rollout(l2a_ctx* c, l2a_rnn_model* m, const l2a_rollout_params* p, const float* obs0, const float* hidden_c,
+                               const float* hidden_h, const float* actions, const float* discount_pow, float* returns,
+                               float* best_ret, int32_t* best_idx, float* best_act, void* stream) {
+  if (!c || !m || !p || !obs0 || !hidden_c || !hidden_h || !actions || !discount_pow || !best_ret || !best_idx || !best_act)
+    return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!m->norm_set) return fail(L2A_ERR_INVALID, "normalization not set");
+  if (p->n_candidates < 1 || p->n_envs < 1 || p->horizon < 1) return fail(L2A_ERR_INVALID, "n_candidates/n_envs/horizon must be >= 1");
+  if (p->reward_kind < 0 || p->reward_kind > 2 || !(p->dt > 0.f)) return fail(L2A_ERR_INVALID, "bad reward_kind/dt");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = (p->n_candidates + kRnnRT - 1) / kRnnRT;
+  int rc = ensure_reduce_ws(c, (size_t)tiles * p->n_envs, p->n_envs, st);
+  if (rc) return rc;
+  RnnArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.dims = m->dims;
+  ra.norm = m->norm_dev();
+  ra.params = m->params;
+  ra.obs = obs0; ra.c0 = hidden_c; ra.h0 = hidden_h;
+  ra.actions = actions;
+  ra.act_stride_t = p->act_stride_t; ra.act_stride_row = p->act_stride_row;
+  ra.discount_pow = discount_pow;
+  ra.rows_per_group = p->n_candidates; ra.n_groups = p->n_envs; ra.horizon = p->horizon;
+  ra.reward_kind = p->reward_kind; ra.dt = p->dt;
+  ra.returns = returns;
+  ra.red.part_ret = c->part_ret; ra.red.part_idx = c->part_idx; ra.red.counters = c->counters;
+  ra.red.best_ret = best_ret; ra.red.best_idx = best_idx; ra.red.best_act = best_act;
+  ra.red.actions = actions; ra.red.act_stride_row = p->act_stride_row; ra.red.act_dim = m->dims.act_dim;
+  ra.red.n_candidates = p->n_candidates; ra.red.tiles_per_env = tiles;
+  const size_t smem = rnn_smem_bytes(m->dims);
+  CUDA_TRY(cudaFuncSetAttribute(rollout_rnn_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rollout_rnn_simt_kernel<false><<<(unsigned)(tiles * p->n_envs), kRnnThreads, smem, st>>>(ra);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
+extern "C" int l2a_rnn_predict(l2a_ctx* c, l2a_rnn_model* m, const float* obs, const float* act, const float* hidden_c,
+                               const float* hidden_h, int n, float* delta_out, float* c_out, float* h_out, void* stream) {
+  if (!c || !m || !obs || !act || !hidden_c || !hidden_h || !delta_out || !c_out || !h_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!m->norm_set) return fail(L2A_ERR_INVALID, "normalization not set");
+  if (n < 1) return fail(L2A_ERR_INVALID, "n must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  RnnArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.dims = m->dims;
+  ra.norm = m->norm_dev();
+  ra.params = m->params;
+  ra.obs = obs; ra.c0 = hidden_c; ra.h0 = hidden_h;
+  ra.actions = act; ra.act_stride_t = 0; ra.act_stride_row = m->dims.act_dim;
+  ra.rows_per_group = n; ra.n_groups = 1; ra.horizon = 1;
+  ra.delta_out = delta_out; ra.c_out = c_out; ra.h_out = h_out;
+  const size_t smem = rnn_smem_bytes(m->dims);
+  CUDA_TRY(cudaFuncSetAttribute(rollout_rnn_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rollout_rnn_simt_kernel<true><<<(unsigned)((n + kRnnRT - 1) / kRnnRT), kRnnThreads, smem, (cudaStream_t)stream>>>(ra);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return L2A_OK;

@@ -119,3 +119,60 @@ def fit_maml(np_params, obs_n, act_n, delta_n, epochs, batch_size, meta_batch_si
             break
         prev = avg
     return OrderedDict((k, p.detach().cpu().numpy()) for k, p in zip(np_params.keys(), params))
+
+
+def _lstm_forward(x, c, h, params):
+    """x [B, T, in]; TF LSTMCell semantics (gate order i, j, f, o; forget_bias 1)."""
+    wk, bk, wo, bo = params
+    hs = h.shape[1]
+    ys = []
+    for t in range(x.shape[1]):
+        z = torch.cat([x[:, t], h], dim=1) @ wk + bk
+        i, j, f, o = z[:, :hs], z[:, hs:2 * hs], z[:, 2 * hs:3 * hs], z[:, 3 * hs:]
+        c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        ys.append(h @ wo + bo)
+    return torch.stack(ys, dim=1), c, h
+
+
+def fit_lstm(np_params, obs_n, act_n, delta_n, epochs, batch_size, learning_rate, backprop_steps, valid_split_ratio,
+             rolling_average_persitency, device, verbose=False, seed=0):
+    """Truncated BPTT (chunks of `backprop_steps`, state carried and detached between chunks) with Adam on
+    mean((delta - f(x))^2), validation early stop -- the procedure of rnn_dynamics.py:95-231."""
+    rng = np.random.RandomState(seed)
+    x = torch.tensor(np.concatenate([obs_n, act_n], axis=2).astype(np.float32), device=device)
+    y = torch.tensor(delta_n.astype(np.float32), device=device)
+    n_paths, T = x.shape[0], x.shape[1]
+    tr, te = _split(n_paths, valid_split_ratio, rng)
+    if len(te) == 0:
+        te = tr
+    params = _to_params(np_params, device)
+    hs = params[2].shape[0]
+    opt = torch.optim.Adam(params, lr=learning_rate)
+    avg = prev = None
+    for epoch in range(epochs):
+        order = rng.permutation(tr)
+        for s in range(0, len(order), batch_size):
+            idx = torch.as_tensor(order[s:s + batch_size], device=device)
+            c = torch.zeros(len(idx), hs, device=device)
+            h = torch.zeros(len(idx), hs, device=device)
+            for t0 in range(0, T, backprop_steps):
+                opt.zero_grad()
+                pred, c, h = _lstm_forward(x[idx, t0:t0 + backprop_steps], c, h, params)
+                loss = torch.mean((pred - y[idx, t0:t0 + backprop_steps]) ** 2)
+                loss.backward()
+                opt.step()
+                c, h = c.detach(), h.detach()
+        with torch.no_grad():
+            idx = torch.as_tensor(te, device=device)
+            pred, _, _ = _lstm_forward(x[idx], torch.zeros(len(idx), hs, device=device), torch.zeros(len(idx), hs, device=device), params)
+            valid_loss = float(torch.mean((pred - y[idx]) ** 2))
+        if avg is None:
+            avg, prev = _early_stop_state(valid_loss)
+        avg = rolling_average_persitency * avg + (1.0 - rolling_average_persitency) * valid_loss
+        if verbose:
+            print("fit_lstm epoch %d valid %.5f avg %.5f" % (epoch, valid_loss, avg))
+        if prev < avg or epoch == epochs - 1:
+            break
+        prev = avg
+    return OrderedDict((k, p.detach().cpu().numpy()) for k, p in zip(np_params.keys(), params))

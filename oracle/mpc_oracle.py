@@ -335,3 +335,86 @@ def make_adapt_context(seed, prob, k, m_rows):
         act.append(a)
         nxt.append(o + d)
     return obs, act, nxt
+
+
+# --------------------------------------------------------------------------------------------------
+# ReBAL: recurrent dynamics model (single-layer LSTM) and its planner   
+#   dynamics/rnn_dynamics.py:233-252 (predict), dynamics/core/utils.py:145-238 (create_rnn: tf.nn.rnn_cell.LSTMCell +
+#   tf.layers.dense output), policies/rnn_mpc_controller.py:57-65, 112-134, 165-187.
+# TF 1.13 LSTMCell semantics (published; TensorFlow itself is not installable here -> PARITY UNPINNED for the cell math):
+#   z = [x, h_prev] @ kernel + bias ;  i, j, f, o = split(z, 4) ;  c = sigmoid(f + 1.0) * c_prev + sigmoid(i) * act(j) ;
+#   h = sigmoid(o) * act(c)            (forget_bias = 1.0, no peepholes / clipping / projection), act = tanh by default.
+# --------------------------------------------------------------------------------------------------
+def rnn_param_keys():
+    return ["rnn/lstm_cell/kernel", "rnn/lstm_cell/bias", "output/kernel", "output/bias"]
+
+
+def xavier_rnn_params(rng, in_dim, hidden, out_dim, out_scale=1.0):
+    params = OrderedDict()
+    lim = np.sqrt(6.0 / (in_dim + hidden + 4 * hidden))
+    params["rnn/lstm_cell/kernel"] = rng.uniform(-lim, lim, size=(in_dim + hidden, 4 * hidden)).astype(np.float32)
+    params["rnn/lstm_cell/bias"] = np.zeros(4 * hidden, np.float32)
+    lim = np.sqrt(6.0 / (hidden + out_dim))
+    params["output/kernel"] = (rng.uniform(-lim, lim, size=(hidden, out_dim)) * out_scale).astype(np.float32)
+    params["output/bias"] = np.zeros(out_dim, np.float32)
+    return params
+
+
+def _sigmoid32(x):
+    return (np.float32(1.0) / (np.float32(1.0) + np.exp(-x))).astype(np.float32)
+
+
+def lstm_step(x32, c_prev, h_prev, params):
+    """One LSTMCell step in float32.  x32 [n, in], c_prev/h_prev [n, H]  ->  (delta_norm [n, D], c, h)."""
+    hsz = h_prev.shape[1]
+    z = np.concatenate([x32, h_prev], axis=1).astype(np.float32) @ params["rnn/lstm_cell/kernel"] + params["rnn/lstm_cell/bias"]
+    i, j, f, o = z[:, :hsz], z[:, hsz:2 * hsz], z[:, 2 * hsz:3 * hsz], z[:, 3 * hsz:]
+    c = _sigmoid32(f + np.float32(1.0)) * c_prev + _sigmoid32(i) * np.tanh(j)
+    h = _sigmoid32(o) * np.tanh(c)
+    y = h.astype(np.float32) @ params["output/kernel"] + params["output/bias"]
+    return y.astype(np.float32), c.astype(np.float32), h.astype(np.float32)
+
+
+def rnn_predict(obs, act, hidden, params, norm):
+    """RNNDynamicsModel.predict (rnn_dynamics.py:233-252): hidden = (c [n,H], h [n,H]) float32.
+    Returns (next_obs float64 [n, D], (c, h))."""
+    obs = np.asarray(obs, np.float64)
+    act = np.asarray(act, np.float64)
+    obs_n = normalize(obs, *norm["obs"])
+    act_n = normalize(act, *norm["act"])
+    x32 = np.concatenate([obs_n, act_n], axis=1).astype(np.float32)
+    y, c, h = lstm_step(x32, np.asarray(hidden[0], np.float32), np.asarray(hidden[1], np.float32), params)
+    delta = denormalize(y, *norm["delta"])
+    return obs + delta, (c, h)
+
+
+def rnn_rollout_returns(observations, actions, hidden, params, norm, reward_kind, dt, discount=1.0):
+    """RNNMPCController.get_rs_action loop (rnn_mpc_controller.py:112-134): hidden = (c [m,H], h [m,H]) is repeated n
+    times per env (repeat_hidden :165-187)."""
+    observations = np.asarray(observations, np.float64)
+    actions = np.asarray(actions, np.float64)
+    hh, rows, _ = actions.shape
+    m = observations.shape[0]
+    n = rows // m
+    rew = reward_fn(reward_kind, dt)
+    returns = np.zeros((rows,))
+    observation = np.repeat(observations, n, axis=0)
+    hid = (np.repeat(np.asarray(hidden[0], np.float32), n, axis=0), np.repeat(np.asarray(hidden[1], np.float32), n, axis=0))
+    for t in range(hh):
+        next_observation, hid = rnn_predict(observation, actions[t], hid, params, norm)
+        rewards = rew(observation, actions[t], next_observation)
+        returns += discount ** t * rewards
+        observation = next_observation
+    return returns.reshape(m, n)
+
+
+def rnn_rs_plan(observations, actions, hidden, params, norm, reward_kind, dt, discount=1.0):
+    """Returns (chosen [m,A], best [m], returns [m,n], new_hidden) -- new_hidden = one predict on the REAL observations with
+    the chosen actions (rnn_mpc_controller.py:63)."""
+    returns = rnn_rollout_returns(observations, actions, hidden, params, norm, reward_kind, dt, discount)
+    m, n = returns.shape
+    cand_a = np.asarray(actions, np.float64)[0].reshape(m, n, -1)
+    best = np.argmax(returns, axis=1)
+    chosen = cand_a[range(m), best]
+    _, new_hidden = rnn_predict(np.asarray(observations, np.float64), chosen, hidden, params, norm)
+    return chosen, best, returns, new_hidden

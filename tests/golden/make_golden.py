@@ -40,7 +40,9 @@ class _Anything(types.ModuleType):
     def __getattr__(self, item):
         if item.startswith("__"):
             raise AttributeError(item)
-        return _Anything(self.__name__ + "." + item)
+        child = _Anything(self.__name__ + "." + item)
+        object.__setattr__(self, item, child)          # cache: attributes set on a child persist
+        return child
 
     def __call__(self, *a, **k):
         return _Anything(self.__name__ + "()")
@@ -287,6 +289,61 @@ def main():
     out["grbal_rs_actions"] = ctrl.get_random_action(4 * 24 * 3).reshape((4, 24 * 3, -1))
     out["grbal_rs_step_rewards"] = np.stack(env.step_rewards)
     out["grbal_rs_chosen"] = acts
+
+    # ------------------------------------------------------------------ ReBAL: verbatim RNNMPCController + LSTM stand-in
+    import collections
+    LSTMStateTuple = collections.namedtuple("LSTMStateTuple", ("c", "h"))
+    tf.nn.rnn_cell.LSTMStateTuple = LSTMStateTuple
+    tf.contrib.rnn.LSTMStateTuple = LSTMStateTuple
+    from learning_to_adapt.policies import rnn_mpc_controller as rnn_ctrl_mod
+    from learning_to_adapt.dynamics import rnn_dynamics as rnn_dyn_mod
+    rnn_ctrl_mod.tf = tf
+    RNNDynamicsModel = rnn_dyn_mod.RNNDynamicsModel
+    prob = O.make_problem("half_cheetah", hidden_sizes=(32,), n_sets=1, m=2, seed=61)
+    HS = 24
+    rparams = O.xavier_rnn_params(np.random.RandomState(62), prob["obs_dim"] + prob["act_dim"], HS, prob["obs_dim"], out_scale=0.1)
+
+    rnn_self = types.SimpleNamespace()
+    rnn_self.obs_space_dims = prob["obs_dim"]
+    rnn_self.action_space_dims = prob["act_dim"]
+    rnn_self.normalize_input = True
+    rnn_self.normalization = prob["norm"]
+
+    def f_delta_pred(obs3, act3, hidden):
+        # graph: concat -> dynamic_rnn (time axis of length 1) -> dense output; float32 feed
+        x = np.concatenate([obs3[:, 0, :], act3[:, 0, :]], axis=1).astype(np.float32)
+        y, c, h = O.lstm_step(x, np.asarray(hidden[0], np.float32), np.asarray(hidden[1], np.float32), rparams)   # repeat_hidden hands a [c, h] list
+        return y[:, None, :], LSTMStateTuple(c, h)
+
+    rnn_self.f_delta_pred = f_delta_pred
+    rnn_self._normalize_data = types.MethodType(RNNDynamicsModel._normalize_data, rnn_self)
+    rnn_self.predict = types.MethodType(RNNDynamicsModel.predict, rnn_self)
+    rnn_self.get_initial_hidden = lambda batch_size: LSTMStateTuple(np.zeros((batch_size, HS), np.float32),
+                                                                    np.zeros((batch_size, HS), np.float32))
+    env = FakeEnv(prob, "half_cheetah_env.py")
+    n_c, hor = 30, 4
+    rctrl = rnn_ctrl_mod.RNNMPCController("policy", env, rnn_self, n_candidates=n_c, horizon=hor)
+    rctrl.reset(dones=[True, True])
+    np.random.seed(171)
+    obs_t = np.array(prob["obs0"])
+    chosen_seq, hid_c, hid_h = [], [], []
+    for step in range(3):                       # three consecutive planning calls: the hidden state carries over
+        acts, _ = rctrl.get_actions(obs_t)
+        chosen_seq.append(np.array(acts))
+        hid_c.append(np.array(rctrl._hidden_state.c))
+        hid_h.append(np.array(rctrl._hidden_state.h))
+        obs_t = obs_t + 0.05 * np.random.RandomState(step).normal(size=obs_t.shape)
+    out["rebal_meta"] = np.array([n_c, hor, 2, 61, HS], np.int64)
+    out["rebal_chosen"] = np.stack(chosen_seq)
+    out["rebal_hidden_c"] = np.stack(hid_c)
+    out["rebal_hidden_h"] = np.stack(hid_h)
+    out["rebal_step_rewards"] = np.stack(env.step_rewards)          # [3*H, n*m]
+    # get_action on one observation returns ([1, A], {})
+    rctrl1 = rnn_ctrl_mod.RNNMPCController("policy", env, rnn_self, n_candidates=10, horizon=2)
+    rctrl1.reset(dones=[True])
+    np.random.seed(172)
+    a1, _ = rctrl1.get_action(prob["obs0"][0])
+    out["rebal_get_action_shape"] = np.array(a1.shape, np.int64)
 
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)

@@ -170,3 +170,58 @@ def test_two_rank_nccl_shard_equals_single_gpu_and_reference():
     for p in procs:
         p.join(timeout=60)
     assert results == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------------ ReBAL
+def test_rebal_recurrent_planner_matches_reference_golden(golden):
+    """RNNMPCController + RNNDynamicsModel on the fused LSTM kernel vs the verbatim reference controller's outputs over three
+    consecutive planning calls (hidden state carried), bit-identical chosen actions for the seeded numpy stream."""
+    from learning_to_adapt_b200.dynamics.rnn_dynamics import RNNDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from learning_to_adapt_b200.policies.rnn_mpc_controller import RNNMPCController
+    n, h, m, seed, hs = [int(v) for v in golden["rebal_meta"]]
+    prob = O.make_problem("half_cheetah", hidden_sizes=(32,), n_sets=1, m=m, seed=seed)
+    params = O.xavier_rnn_params(np.random.RandomState(62), prob["obs_dim"] + prob["act_dim"], hs, prob["obs_dim"], out_scale=0.1)
+    env = SyntheticEnv("half_cheetah")
+    model = RNNDynamicsModel("dyn", env, hidden_sizes=(hs,))
+    model.set_params(params)
+    model.set_normalization(prob["norm"])
+    ctrl = RNNMPCController("policy", env, model, n_candidates=n, horizon=h)
+    ctrl.reset(dones=[True] * m)
+    np.random.seed(171)
+    obs_t = np.array(prob["obs0"])
+    for step in range(3):
+        acts, info = ctrl.get_actions(obs_t)
+        assert info == {}
+        ref_ret = golden["rebal_step_rewards"][step * h:(step + 1) * h].sum(axis=0).reshape(m, n)
+        assert_argmax_consistent(ctrl.last_plan["best_idx"].cpu().numpy(), ref_ret)
+        np.testing.assert_array_equal(acts, golden["rebal_chosen"][step])
+        np.testing.assert_allclose(ctrl._hidden_state.c, golden["rebal_hidden_c"][step], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(ctrl._hidden_state.h, golden["rebal_hidden_h"][step], rtol=1e-4, atol=1e-5)
+        obs_t = obs_t + 0.05 * np.random.RandomState(step).normal(size=obs_t.shape)
+    a1, _ = RNNMPCController("policy", env, model, n_candidates=10, horizon=2).get_action(prob["obs0"][0])
+    assert a1.shape == tuple(golden["rebal_get_action_shape"])
+
+
+def test_rebal_rollout_matches_oracle_at_script_size():
+    """run_rebal.py shape: LSTM(256), N=500, H=10, 5 envs; returns within 1e-4 of the oracle, non-zero starting hidden."""
+    from learning_to_adapt_b200.dynamics.rnn_dynamics import RNNDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    n, h, m, hs = 500, 10, 5, 256
+    prob = O.make_problem("half_cheetah", hidden_sizes=(32,), n_sets=1, m=m, seed=8)
+    params = O.xavier_rnn_params(np.random.RandomState(3), prob["obs_dim"] + prob["act_dim"], hs, prob["obs_dim"], out_scale=0.1)
+    model = RNNDynamicsModel("dyn", SyntheticEnv("half_cheetah"), hidden_sizes=(hs,))
+    model.set_params(params)
+    model.set_normalization(prob["norm"])
+    rng = np.random.RandomState(1)
+    hidden = (0.3 * rng.normal(size=(m, hs)).astype(np.float32), 0.3 * rng.normal(size=(m, hs)).astype(np.float32))
+    actions = O.sample_rs_actions(5, prob["low"], prob["high"], h, n * m)
+    want = O.rnn_rollout_returns(prob["obs0"], actions, hidden, params, prob["norm"], prob["reward_kind"], prob["dt"], 0.95)
+    res = model.rollout(dev(prob["obs0"]), hidden, dev(actions), n, h, prob["reward_kind"], prob["dt"], discount=0.95, want_returns=True)
+    assert_returns_close(res["returns"].cpu().numpy(), want)
+    assert_argmax_consistent(res["best_idx"].cpu().numpy(), want)
+    nxt, hid = model.predict(prob["obs0"], actions[0].reshape(m, n, -1)[:, 0], hidden)
+    w_nxt, w_hid = O.rnn_predict(prob["obs0"], actions[0].reshape(m, n, -1)[:, 0], hidden, params, prob["norm"])
+    np.testing.assert_allclose(nxt, w_nxt, rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(hid.c, w_hid[0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(hid.h, w_hid[1], rtol=1e-4, atol=1e-5)

@@ -133,3 +133,24 @@ def test_ensemble_mean_reduces_to_single_model():
     b = O.rollout_returns(prob["obs0"], acts, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"],
                           mode="ensemble")
     np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+
+
+def test_rebal_recurrent_planner_matches_reference(golden):
+    """Verbatim RNNMPCController (random shooting, hidden state carried across three planning calls) vs the oracle's
+    LSTM restatement + planner."""
+    n, h, m, seed, hs = [int(v) for v in golden["rebal_meta"]]
+    prob = O.make_problem("half_cheetah", hidden_sizes=(32,), n_sets=1, m=m, seed=seed)
+    params = O.xavier_rnn_params(np.random.RandomState(62), prob["obs_dim"] + prob["act_dim"], hs, prob["obs_dim"], out_scale=0.1)
+    hidden = (np.zeros((m, hs), np.float32), np.zeros((m, hs), np.float32))
+    rng = np.random.RandomState(171)
+    obs_t = np.array(prob["obs0"])
+    for step in range(3):
+        actions = rng.uniform(prob["low"], prob["high"], size=(h * n * m, prob["act_dim"])).reshape(h, n * m, -1)
+        chosen, best, returns, hidden = O.rnn_rs_plan(obs_t, actions, hidden, params, prob["norm"], prob["reward_kind"], prob["dt"])
+        ref_ret = golden["rebal_step_rewards"][step * h:(step + 1) * h].sum(axis=0).reshape(m, n)
+        np.testing.assert_array_equal(returns, ref_ret)
+        np.testing.assert_array_equal(chosen, golden["rebal_chosen"][step])
+        np.testing.assert_array_equal(hidden[0], golden["rebal_hidden_c"][step])
+        np.testing.assert_array_equal(hidden[1], golden["rebal_hidden_h"][step])
+        obs_t = obs_t + 0.05 * np.random.RandomState(step).normal(size=obs_t.shape)
+    assert tuple(golden["rebal_get_action_shape"]) == (1, 6)
