@@ -1,17 +1,24 @@
 // K2: GrBAL one-step inner adaptation (dynamics/meta_mlp_dynamics.py:321-345, _adapt_sym 409-421, graph 96-120).
 //   theta'_k = theta - lr * d/dtheta mean_{M x D}((target_k - f_theta(x_k))^2)        for each task k < K.
-// Two phases:
-//   adapt_fwd_bwd_kernel : one CTA per task; forward over the M context rows keeping every activation, then the
-//                          backward chain of layer-output gradients g_l.  Tiny (M <= 32 rows), latency-bound.
-//   adapt_update_kernel  : grid over (task, layer, tiles); theta'[i][j] = theta[i][j] - lr * sum_r h_l[r][i] g_l[r][j].
+// Two kernels:
+//   adapt_fwd_bwd_kernel : a thread-block CLUSTER of kAdaptCluster CTAs per task walks the 2L-1 dependent stages (forward
+//                          layers, loss gradient, backward chain).  Every stage is a skinny product over the M <= 32 context
+//                          rows: each CTA computes a slice of the stage's output features from the full input (32 KB, re-read
+//                          from L2 into shared memory), publishes it to the global workspace and the cluster barrier
+//                          (release / acquire) hands it to the next stage.  Latency-bound: ~3 us per stage.
+//   adapt_update_kernel  : grid over (task, layer, tiles); theta'[i][j] = theta[i][j] - lr * sum_r h_l[i][r] g_l[r][j].
 //                          Pure streaming: reads theta once, writes theta' once -> HBM-bound (4 B in + 4 B out / param).
+// Workspace layouts: layer inputs h_l as [feature][M] (broadcast reads in the forward product), layer-output gradients g_l as
+// [M][feature] (coalesced reads in the backward product and in the update).
 #pragma once
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace l2a {
 
 constexpr int kAdaptMaxM = 32;
 constexpr int kAdaptThreads = 256;
+constexpr int kAdaptCluster = 8;
 
 struct AdaptArgs {
   MlpDims dims;
@@ -21,84 +28,174 @@ struct AdaptArgs {
   const float* target;      // [K, M, D] normalised delta
   int K, M;
   float lr;
-  float* acts;              // workspace [K][sum_l dims[l]][M]   (layer inputs h_l, feature-major)
-  float* grads;             // workspace [K][sum_l dims[l+1]][M] (layer-output gradients g_l)
-  int act_off[kMaxLayers + 1];
-  int grad_off[kMaxLayers + 1];
+  float* acts;              // workspace [K][sum_l dims[l]][M]      layer inputs h_l, [feature][M]
+  float* grads;             // workspace [K][M][sum_l dims[l+1]]    layer-output gradients g_l, each [M][dims[l+1]]
+  int act_off[kMaxLayers + 1];    // float offset of h_l inside a task's block (act_off[n_layers] = block size)
+  int grad_off[kMaxLayers + 1];   // float offset of g_l inside a task's block
   float* params_out;        // == params (sets dst_first_set + k)
 };
 
-// out[j][r] = act(b[j] + sum_i in[i][r] W[i][j]) for r < M (feature-major activations in global/L2)
+template <int MR>
 __global__ void __launch_bounds__(kAdaptThreads, 1) adapt_fwd_bwd_kernel(const AdaptArgs a) {
+  extern __shared__ __align__(16) float adapt_smem[];
   const MlpDims& md = a.dims;
-  const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, M = a.M;
+  const int M = a.M, W = md.max_width;
+  float* s_in = adapt_smem;                       // stage input: h_l as [feature][MR] or g_l as [MR][feature]
+  float* s_part = s_in + (size_t)W * MR;          // k-split partial sums [4 * kAdaptThreads][MR]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int crank = (int)umma::cluster_ctarank();
+  const int k = blockIdx.x / kAdaptCluster;       // task
   const float* P = a.params + (size_t)a.src_set * md.set_stride;
   float* A0 = a.acts + (size_t)k * (size_t)a.act_off[md.n_layers];
   float* G0 = a.grads + (size_t)k * (size_t)a.grad_off[md.n_layers];
-  const int din0 = md.dims[0];
-  // h_0 = x (transpose to feature-major)
-  for (int idx = tid; idx < din0 * M; idx += nt) {
-    const int i = idx / M, r = idx % M;
-    A0[a.act_off[0] + idx] = a.x[((size_t)k * M + r) * din0 + i];
+  const int L = md.n_layers;
+
+  // h_0 = x, transposed to [feature][M] (every CTA writes the same values of its own slice; rank 0 publishes)
+  if (crank == 0) {
+    const int din0 = md.dims[0];
+    for (int idx = tid; idx < din0 * M; idx += kAdaptThreads) {
+      const int i = idx / M, r = idx % M;
+      A0[a.act_off[0] + idx] = a.x[((size_t)k * M + r) * din0 + i];
+    }
   }
-  __syncthreads();
-  // forward: keep every layer input; the network output goes to the slot after the last input
-  for (int l = 0; l < md.n_layers; ++l) {
+  umma::cluster_sync_all();
+
+  // ------------------------------------------------------------------ forward
+  for (int l = 0; l < L; ++l) {
     const int din = md.dims[l], dout = md.dims[l + 1];
-    const float* W = P + md.w_off[l];
-    const float* b = P + md.b_off[l];
-    const float* in = A0 + a.act_off[l];
-    float* out = (l + 1 < md.n_layers) ? (A0 + a.act_off[l + 1]) : (G0 + a.grad_off[l]);   // y lands in g_L slot
-    for (int j = tid; j < dout; j += nt) {
-      float acc[kAdaptMaxM];
-#pragma unroll
-      for (int r = 0; r < kAdaptMaxM; ++r) acc[r] = b[j];
-      for (int i = 0; i < din; ++i) {
-        const float w = __ldg(&W[(size_t)i * dout + j]);
-#pragma unroll
-        for (int r = 0; r < kAdaptMaxM; ++r)
-          if (r < M) acc[r] = fmaf(in[(size_t)i * M + r], w, acc[r]);
+    const float* Wl = P + md.w_off[l];
+    const float* bl = P + md.b_off[l];
+    const float* h_in = A0 + a.act_off[l];
+    if (M == MR) {                                 // contiguous [din][M] block: 16-byte copies, all loads in flight
+      const int n4 = din * M / 4;
+      const float4* src = reinterpret_cast<const float4*>(h_in);
+      float4* dst = reinterpret_cast<float4*>(s_in);
+#pragma unroll 8
+      for (int idx = tid; idx < n4; idx += kAdaptThreads) dst[idx] = __ldcg(src + idx);
+    } else {
+      for (int idx = tid; idx < din * M; idx += kAdaptThreads) {
+        const int i = idx / M, r = idx % M;
+        s_in[i * MR + r] = __ldcg(h_in + idx);
       }
+    }
+    __syncthreads();
+    const int fs = (dout + kAdaptCluster - 1) / kAdaptCluster;          // output features per CTA
+    const int j0 = crank * fs, nf = max(0, min(fs, dout - j0));
+    // thread = (group of 4 adjacent output features, k-slice): one 16-byte weight load feeds 4 x MR FMAs, 8 loads in flight
+    const bool vec4 = (dout % 4 == 0) && (fs % 4 == 0);
+    const int fw = vec4 ? 4 : 1;
+    const int ngrp = (nf + fw - 1) / fw;
+    int ksplit = ngrp > 0 ? kAdaptThreads / ngrp : 1;
+    if (ksplit > 32) ksplit = 32;
+    if (ksplit > din) ksplit = din;
+    if (ksplit < 1) ksplit = 1;
+    const int kchunk = (din + ksplit - 1) / ksplit;
+    if (tid < ngrp * ksplit) {
+      const int fg = tid % ngrp, ks = tid / ngrp, j = j0 + fg * fw;
+      const int i0 = ks * kchunk, i1 = min(din, i0 + kchunk);
+      if (vec4) {
+        float acc[4][MR];
 #pragma unroll
-      for (int r = 0; r < kAdaptMaxM; ++r)
-        if (r < M) out[(size_t)j * M + r] = (l + 1 < md.n_layers) ? fmaxf(acc[r], 0.f) : acc[r];
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int r = 0; r < MR; ++r) acc[c][r] = 0.f;
+#pragma unroll 8
+        for (int i = i0; i < i1; ++i) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(&Wl[(size_t)i * dout + j]));
+          const float4* hv = reinterpret_cast<const float4*>(s_in + (size_t)i * MR);
+#pragma unroll
+          for (int q = 0; q < MR / 4; ++q) {
+            const float4 h = hv[q];
+            const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[0][4 * q + u] = fmaf(hh[u], w.x, acc[0][4 * q + u]);
+              acc[1][4 * q + u] = fmaf(hh[u], w.y, acc[1][4 * q + u]);
+              acc[2][4 * q + u] = fmaf(hh[u], w.z, acc[2][4 * q + u]);
+              acc[3][4 * q + u] = fmaf(hh[u], w.w, acc[3][4 * q + u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int r = 0; r < MR; ++r) s_part[((size_t)ks * nf + fg * 4 + c) * MR + r] = acc[c][r];
+      } else {
+        float acc[MR];
+#pragma unroll
+        for (int r = 0; r < MR; ++r) acc[r] = 0.f;
+#pragma unroll 8
+        for (int i = i0; i < i1; ++i) {
+          const float w = __ldg(&Wl[(size_t)i * dout + j]);
+#pragma unroll
+          for (int r = 0; r < MR; ++r) acc[r] = fmaf(s_in[(size_t)i * MR + r], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < MR; ++r) s_part[((size_t)ks * nf + fg) * MR + r] = acc[r];
+      }
     }
     __syncthreads();
-  }
-  // dL/dy = 2/(M*D) * (y - target)                                  (meta_mlp_dynamics.py:118)
-  {
-    const int L = md.n_layers - 1, dout = md.dims[md.n_layers];
-    float* g = G0 + a.grad_off[L];
-    const float scale = 2.0f / (float)(M * dout);
-    for (int idx = tid; idx < dout * M; idx += nt) {
-      const int j = idx / M, r = idx % M;
-      g[idx] = scale * (g[idx] - a.target[((size_t)k * M + r) * dout + j]);
+    for (int idx = tid; idx < nf * M; idx += kAdaptThreads) {
+      const int f = idx / M, r = idx % M, j = j0 + f;
+      float s = __ldg(&bl[j]);
+      for (int ks = 0; ks < ksplit; ++ks) s += s_part[((size_t)ks * nf + f) * MR + r];        // fixed order: deterministic
+      if (l + 1 < L) {
+        A0[a.act_off[l + 1] + j * M + r] = fmaxf(s, 0.f);                                     // ReLU dense
+      } else {
+        // dL/dy = 2 / (M * D) * (y - target)                                  (meta_mlp_dynamics.py:118)
+        G0[a.grad_off[l] + r * dout + j] = (2.0f / (float)(M * dout)) * (s - a.target[((size_t)k * M + r) * dout + j]);
+      }
     }
-    __syncthreads();
+    umma::cluster_sync_all();
   }
-  // backward chain: g_{l-1}[i][r] = relu'(h_l[i][r]) * sum_j g_l[j][r] W_l[i][j]
-  for (int l = md.n_layers - 1; l >= 1; --l) {
+
+  // ------------------------------------------------------------------ backward chain
+  //   g_{l-1}[r][i] = relu'(h_l[i][r]) * sum_j g_l[r][j] W_l[i][j]       (one warp per input feature i: W row read coalesced)
+  for (int l = L - 1; l >= 1; --l) {
     const int din = md.dims[l], dout = md.dims[l + 1];
-    const float* W = P + md.w_off[l];
-    const float* g = G0 + a.grad_off[l];
-    const float* h = A0 + a.act_off[l];
-    float* gp = G0 + a.grad_off[l - 1];
-    for (int i = tid; i < din; i += nt) {
-      float acc[kAdaptMaxM];
+    const float* Wl = P + md.w_off[l];
+    const float* g_in = G0 + a.grad_off[l];
+    const float* h_l = A0 + a.act_off[l];
+    float* g_out = G0 + a.grad_off[l - 1];
+    if (dout % 4 == 0 && W % 4 == 0) {
+      const int d4 = dout / 4;
+#pragma unroll 8
+      for (int idx = tid; idx < M * d4; idx += kAdaptThreads) {
+        const int r = idx / d4, q = idx % d4;
+        reinterpret_cast<float4*>(s_in + (size_t)r * W)[q] = __ldcg(reinterpret_cast<const float4*>(g_in + (size_t)r * dout) + q);
+      }
+    } else {
+      for (int idx = tid; idx < M * dout; idx += kAdaptThreads) {
+        const int r = idx / dout, j = idx % dout;
+        s_in[r * W + j] = __ldcg(g_in + idx);
+      }
+    }
+    __syncthreads();
+    const int is = (din + kAdaptCluster - 1) / kAdaptCluster;
+    const int i0 = crank * is, ni = max(0, min(is, din - i0));
+    for (int ii = warp; ii < ni; ii += kAdaptThreads / 32) {
+      const int i = i0 + ii;
+      const float* wrow = Wl + (size_t)i * dout;
+      float acc[MR];
 #pragma unroll
-      for (int r = 0; r < kAdaptMaxM; ++r) acc[r] = 0.f;
-      const float* wrow = W + (size_t)i * dout;
-      for (int j = 0; j < dout; ++j) {
+      for (int r = 0; r < MR; ++r) acc[r] = 0.f;
+#pragma unroll 8
+      for (int j = lane; j < dout; j += 32) {
         const float w = __ldg(&wrow[j]);
 #pragma unroll
-        for (int r = 0; r < kAdaptMaxM; ++r)
-          if (r < M) acc[r] = fmaf(g[(size_t)j * M + r], w, acc[r]);
+        for (int r = 0; r < MR; ++r) acc[r] = fmaf(s_in[r * W + j], w, acc[r]);
       }
 #pragma unroll
-      for (int r = 0; r < kAdaptMaxM; ++r)
-        if (r < M) gp[(size_t)i * M + r] = (h[(size_t)i * M + r] > 0.f) ? acc[r] : 0.f;
+      for (int r = 0; r < MR; ++r) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < MR; ++r) mine = (lane == r) ? acc[r] : mine;
+      if (lane < M) g_out[lane * din + i] = (__ldcg(&h_l[i * M + lane]) > 0.f) ? mine : 0.f;
     }
-    __syncthreads();
+    umma::cluster_sync_all();
   }
 }
 
@@ -109,22 +206,26 @@ __global__ void __launch_bounds__(256) adapt_update_kernel(const AdaptArgs a) {
   const int din = md.dims[l], dout = md.dims[l + 1];
   const float* P = a.params + (size_t)a.src_set * md.set_stride;
   float* Q = a.params_out + (size_t)(a.dst_first_set + k) * md.set_stride;
-  const float* h = a.acts + (size_t)k * (size_t)a.act_off[md.n_layers] + a.act_off[l];
-  const float* g = a.grads + (size_t)k * (size_t)a.grad_off[md.n_layers] + a.grad_off[l];
+  const float* h = a.acts + (size_t)k * (size_t)a.act_off[md.n_layers] + a.act_off[l];       // [din][M]
+  const float* g = a.grads + (size_t)k * (size_t)a.grad_off[md.n_layers] + a.grad_off[l];    // [M][dout]
   const int total = din * dout + dout;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     if (idx < din * dout) {
       const int i = idx / dout, j = idx % dout;
       float s = 0.f;
-      for (int r = 0; r < M; ++r) s = fmaf(h[(size_t)i * M + r], g[(size_t)j * M + r], s);
+      for (int r = 0; r < M; ++r) s = fmaf(h[(size_t)i * M + r], g[(size_t)r * dout + j], s);
       Q[md.w_off[l] + idx] = P[md.w_off[l] + idx] - a.lr * s;                 // _adapt_sym :416-417
     } else {
       const int j = idx - din * dout;
       float s = 0.f;
-      for (int r = 0; r < M; ++r) s += g[(size_t)j * M + r];
+      for (int r = 0; r < M; ++r) s += g[(size_t)r * dout + j];
       Q[md.b_off[l] + j] = P[md.b_off[l] + j] - a.lr * s;
     }
   }
+}
+
+inline size_t adapt_smem_bytes(const MlpDims& md, int mr) {
+  return sizeof(float) * ((size_t)md.max_width * mr + (size_t)4 * kAdaptThreads * mr);
 }
 
 }  // namespace l2a

@@ -516,9 +516,32 @@ extern "C" int l2a_adapt(l2a_ctx* c, l2a_model* m, const float* x, const float* 
   aa.lr = inner_lr;
   aa.acts = c->adapt_acts;
   aa.grads = c->adapt_grads;
-  adapt_fwd_bwd_kernel<<<K, kAdaptThreads, 0, st>>>(aa);
-  c->launches++;
-  CUDA_TRY(cudaGetLastError());
+  {
+    const int mr = (M <= 16) ? 16 : 32;
+    const size_t smem = adapt_smem_bytes(md, mr);
+    if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "adapt needs %zu B shared memory (layer width %d)", smem, md.max_width);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(K * kAdaptCluster));
+    cfg.blockDim = dim3(kAdaptThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kAdaptCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (mr == 16) {
+      CUDA_TRY(cudaFuncSetAttribute(adapt_fwd_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, adapt_fwd_bwd_kernel<16>, aa));
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(adapt_fwd_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, adapt_fwd_bwd_kernel<32>, aa));
+    }
+    c->launches++;
+  }
   int max_elems = 0;
   for (int l = 0; l < md.n_layers; ++l) max_elems = std::max(max_elems, md.dims[l] * md.dims[l + 1] + md.dims[l + 1]);
   dim3 grid((max_elems + 256 * 4 - 1) / (256 * 4), md.n_layers, K);
