@@ -119,6 +119,28 @@ def pick_blas_threads(O, prob, horizon):
     return best
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything any library writes to fd 1 (e.g. NCCL's version banner) to stderr; the one JSON line goes to the real
+    stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line_dict):
+    data = (json.dumps(line_dict) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def make_problem():
     from oracle import mpc_oracle as O
     w = WORKLOAD
@@ -156,7 +178,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit="rollouts/s", cores=cores, kind="port",
                                   sample="%d full planning calls of the workload (numpy planner + fp32 BLAS MLP, best of {4..%d} BLAS threads = %d)" % (args.steps, os.cpu_count(), cores)),
                 e2e=dict(value=value, unit="rollouts/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(gpus, sampler):
@@ -323,7 +345,7 @@ def run_cuda(args):
                               note="algorithmic FLOPs counted once; the kernel issues 3 bf16 MMA passes per product (split-bf16), so the "
                                    "attainable fraction of the bf16 peak is 1/3"),
                 cpu_baseline=cpu, clocks=clocks, wall_s_timed_region=wall)
-    print(json.dumps(line))
+    emit(line)
     if distributed:
         dist.destroy_process_group()
 
@@ -335,6 +357,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
