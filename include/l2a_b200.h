@@ -165,7 +165,8 @@ int l2a_rnn_model_set_params(l2a_ctx* ctx, l2a_rnn_model* model, const float* ce
 int l2a_rnn_model_set_normalization(l2a_ctx* ctx, l2a_rnn_model* model, const float* obs_mean, const float* obs_den,
                                     const float* act_mean, const float* act_den, const float* delta_mean,
                                     const float* delta_scale, void* stream);
-/* p->set_mode / first_set / n_sets / kernel are ignored.  hidden_c, hidden_h: [m, Hs]. */
+/* p->set_mode / first_set / n_sets are ignored; p->kernel: AUTO = tcgen05 when hidden is 128 or 256 (split-bf16 MMAs, gates of a
+ * unit combined in one thread), else the fp32 SIMT kernel.  hidden_c, hidden_h: [m, Hs]. */
 int l2a_rnn_rollout(l2a_ctx* ctx, l2a_rnn_model* model, const l2a_rollout_params* p, const float* obs0, const float* hidden_c,
                     const float* hidden_h, const float* actions, const float* discount_pow, float* returns, float* best_ret,
                     int32_t* best_idx, float* best_act, void* stream);

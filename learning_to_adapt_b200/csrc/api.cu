@@ -16,6 +16,7 @@
 #include "debug_tile.cuh"
 #include "rollout_simt.cuh"
 #include "rollout_rnn_simt.cuh"
+#include "rollout_rnn_tc.cuh"
 #include "rollout_tc.cuh"
 #include "shard.cuh"
 
@@ -664,6 +665,9 @@ extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long 
 // --------------------------------------------------------------------------------------------- ReBAL (LSTM) model
 struct l2a_rnn_model {
   RnnDims dims;
+  RnnTcPlan plan;
+  bool tc_ok = false;
+  uint8_t* blob = nullptr;     // tensor-core tile pairs (rnn_tc_prep_kernel)
   float* params = nullptr;
   float* norm = nullptr;
   bool norm_set = false;
@@ -693,6 +697,10 @@ extern "C" int l2a_rnn_model_create(l2a_ctx* c, int obs_dim, int act_dim, int hi
   if (rnn_smem_bytes(rd) > (size_t)c->max_smem_optin) { delete m; return fail(L2A_ERR_UNSUPPORTED, "LSTM width %d needs %zu B shared memory", hidden, rnn_smem_bytes(rd)); }
   if (cudaMalloc(&m->params, sizeof(float) * (size_t)off) != cudaSuccess) { delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(rnn params)"); }
   if (cudaMalloc(&m->norm, sizeof(float) * (size_t)(4 * obs_dim + 2 * act_dim)) != cudaSuccess) { cudaFree(m->params); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(rnn norm)"); }
+  m->tc_ok = rnn_tc_make_plan(obs_dim, act_dim, hidden, &m->plan);
+  if (m->tc_ok && cudaMalloc(&m->blob, (size_t)m->plan.pairs_per_set * 2 * kTcTileBytes) != cudaSuccess) {
+    cudaFree(m->params); cudaFree(m->norm); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(rnn blob)");
+  }
   *out = m;
   return L2A_OK;
 }
@@ -702,6 +710,7 @@ extern "C" int l2a_rnn_model_destroy(l2a_ctx* c, l2a_rnn_model* m) {
   if (c) cudaSetDevice(c->device);
   cudaFree(m->params);
   cudaFree(m->norm);
+  cudaFree(m->blob);
   delete m;
   return L2A_OK;
 }
@@ -716,6 +725,18 @@ extern "C" int l2a_rnn_model_set_params(l2a_ctx* c, l2a_rnn_model* m, const floa
   CUDA_TRY(cudaMemcpyAsync(m->params + rd.bk_off, cell_bias, sizeof(float) * (size_t)4 * rd.hidden, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(m->params + rd.wo_off, out_kernel, sizeof(float) * (size_t)rd.hidden * rd.obs_dim, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(m->params + rd.bo_off, out_bias, sizeof(float) * (size_t)rd.obs_dim, cudaMemcpyDeviceToDevice, st));
+  if (m->tc_ok) {
+    RnnPrepArgs pa;
+    pa.plan = m->plan;
+    pa.D = rd.obs_dim;
+    pa.A = rd.act_dim;
+    pa.wk = m->params + rd.wk_off;
+    pa.wo = m->params + rd.wo_off;
+    pa.blob = m->blob;
+    rnn_tc_prep_kernel<<<m->plan.pairs_per_set, 256, 0, st>>>(pa);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   return L2A_OK;
 }
 
@@ -747,6 +768,39 @@ extern "C" int l2a_rnn_rollout(l2a_ctx* c, l2a_rnn_model* m, const l2a_rollout_p
   if (p->reward_kind < 0 || p->reward_kind > 2 || !(p->dt > 0.f)) return fail(L2A_ERR_INVALID, "bad reward_kind/dt");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
+  int kernel = p->kernel;
+  if (kernel == L2A_KERNEL_AUTO) kernel = m->tc_ok ? L2A_KERNEL_TCGEN05 : L2A_KERNEL_SIMT;
+  if (kernel == L2A_KERNEL_TCGEN05) {
+    if (!m->tc_ok) return fail(L2A_ERR_UNSUPPORTED, "tcgen05 LSTM rollout needs hidden in {128, 256}, obs_dim <= 48, pad8(obs)+act <= 64");
+    constexpr int NC = 64;
+    const int groups = (p->n_candidates + NC - 1) / NC;
+    int rc2 = ensure_reduce_ws(c, (size_t)groups * p->n_envs, p->n_envs, st);
+    if (rc2) return rc2;
+    RnnTcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.plan = m->plan;
+    ta.D = m->dims.obs_dim; ta.A = m->dims.act_dim;
+    ta.norm = m->norm_dev();
+    ta.bk = m->params + m->dims.bk_off; ta.bo = m->params + m->dims.bo_off;
+    ta.blob = m->blob;
+    ta.obs0 = obs0; ta.c0 = hidden_c; ta.h0 = hidden_h;
+    ta.actions = actions; ta.act_stride_t = p->act_stride_t; ta.act_stride_row = p->act_stride_row;
+    ta.discount_pow = discount_pow;
+    ta.n_candidates = p->n_candidates; ta.n_envs = p->n_envs; ta.horizon = p->horizon; ta.reward_kind = p->reward_kind; ta.dt = p->dt;
+    ta.groups_per_env = groups;
+    ta.returns = returns;
+    ta.red.part_ret = c->part_ret; ta.red.part_idx = c->part_idx; ta.red.counters = c->counters;
+    ta.red.best_ret = best_ret; ta.red.best_idx = best_idx; ta.red.best_act = best_act;
+    ta.red.actions = actions; ta.red.act_stride_row = p->act_stride_row; ta.red.act_dim = m->dims.act_dim;
+    ta.red.n_candidates = p->n_candidates; ta.red.tiles_per_env = groups;
+    const size_t smem_tc = RnnTcSmem<NC>::total(m->dims.obs_dim, m->dims.act_dim, m->dims.hidden);
+    if ((int)smem_tc > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "tcgen05 LSTM rollout needs %zu B shared memory", smem_tc);
+    CUDA_TRY(cudaFuncSetAttribute(rollout_rnn_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+    rollout_rnn_tc_kernel<NC><<<(unsigned)(groups * p->n_envs), kRnnTcThreads, smem_tc, st>>>(ta);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return L2A_OK;
+  }
   const int tiles = (p->n_candidates + kRnnRT - 1) / kRnnRT;
   int rc = ensure_reduce_ws(c, (size_t)tiles * p->n_envs, p->n_envs, st);
   if (rc) return rc;

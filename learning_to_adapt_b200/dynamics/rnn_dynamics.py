@@ -132,7 +132,8 @@ class RNNDynamicsModel(Serializable):
                                          int(n), _ptr(delta), _ptr(c_out), _ptr(h_out), _stream()))
         return np.asarray(obs, np.float64) + delta.cpu().numpy(), LSTMStateTuple(c_out.cpu().numpy(), h_out.cpu().numpy())
 
-    def rollout(self, obs_dev, hidden, actions_dev, n_candidates, horizon, reward_kind, dt, discount=1.0, want_returns=False):
+    def rollout(self, obs_dev, hidden, actions_dev, n_candidates, horizon, reward_kind, dt, discount=1.0, want_returns=False,
+                kernel=N.KERNEL_AUTO):
         """Fused H-step planner rollout (kernel behind RNNMPCController.get_rs_action)."""
         m, A = obs_dev.shape[0], self.action_space_dims
         key = (float(discount), int(horizon))
@@ -140,7 +141,7 @@ class RNNDynamicsModel(Serializable):
             self._discount_cache[key] = self._f32(np.array([float(discount) ** t for t in range(horizon)], np.float64))
         p = N.RolloutParams()
         p.n_candidates, p.n_envs, p.horizon = int(n_candidates), int(m), int(horizon)
-        p.reward_kind, p.dt = int(reward_kind), float(dt)
+        p.reward_kind, p.dt, p.kernel = int(reward_kind), float(dt), int(kernel)
         p.act_stride_t, p.act_stride_row = n_candidates * m * A, A
         best_ret = torch.empty(m, device=self.device, dtype=torch.float32)
         best_idx = torch.empty(m, device=self.device, dtype=torch.int32)

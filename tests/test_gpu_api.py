@@ -217,9 +217,11 @@ def test_rebal_rollout_matches_oracle_at_script_size():
     hidden = (0.3 * rng.normal(size=(m, hs)).astype(np.float32), 0.3 * rng.normal(size=(m, hs)).astype(np.float32))
     actions = O.sample_rs_actions(5, prob["low"], prob["high"], h, n * m)
     want = O.rnn_rollout_returns(prob["obs0"], actions, hidden, params, prob["norm"], prob["reward_kind"], prob["dt"], 0.95)
-    res = model.rollout(dev(prob["obs0"]), hidden, dev(actions), n, h, prob["reward_kind"], prob["dt"], discount=0.95, want_returns=True)
-    assert_returns_close(res["returns"].cpu().numpy(), want)
-    assert_argmax_consistent(res["best_idx"].cpu().numpy(), want)
+    for kernel in (1, 2):                                       # fp32 SIMT and tcgen05 variants
+        res = model.rollout(dev(prob["obs0"]), hidden, dev(actions), n, h, prob["reward_kind"], prob["dt"], discount=0.95,
+                            want_returns=True, kernel=kernel)
+        assert_returns_close(res["returns"].cpu().numpy(), want)
+        assert_argmax_consistent(res["best_idx"].cpu().numpy(), want)
     nxt, hid = model.predict(prob["obs0"], actions[0].reshape(m, n, -1)[:, 0], hidden)
     w_nxt, w_hid = O.rnn_predict(prob["obs0"], actions[0].reshape(m, n, -1)[:, 0], hidden, params, prob["norm"])
     np.testing.assert_allclose(nxt, w_nxt, rtol=RTOL, atol=1e-5)
