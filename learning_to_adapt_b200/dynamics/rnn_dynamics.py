@@ -133,7 +133,7 @@ class RNNDynamicsModel(Serializable):
         return np.asarray(obs, np.float64) + delta.cpu().numpy(), LSTMStateTuple(c_out.cpu().numpy(), h_out.cpu().numpy())
 
     def rollout(self, obs_dev, hidden, actions_dev, n_candidates, horizon, reward_kind, dt, discount=1.0, want_returns=False,
-                kernel=N.KERNEL_AUTO):
+                kernel=N.KERNEL_AUTO, layout="thra"):
         """Fused H-step planner rollout (kernel behind RNNMPCController.get_rs_action)."""
         m, A = obs_dev.shape[0], self.action_space_dims
         key = (float(discount), int(horizon))
@@ -142,7 +142,10 @@ class RNNDynamicsModel(Serializable):
         p = N.RolloutParams()
         p.n_candidates, p.n_envs, p.horizon = int(n_candidates), int(m), int(horizon)
         p.reward_kind, p.dt, p.kernel = int(reward_kind), float(dt), int(kernel)
-        p.act_stride_t, p.act_stride_row = n_candidates * m * A, A
+        if layout == "thra":                     # [H, m*N, A] (random shooting)
+            p.act_stride_t, p.act_stride_row = n_candidates * m * A, A
+        else:                                    # 'nmha': [N, m, H*A] viewed as (N*m, H, A) (CEM, rnn_mpc_controller.py:87-88)
+            p.act_stride_t, p.act_stride_row = A, horizon * A
         best_ret = torch.empty(m, device=self.device, dtype=torch.float32)
         best_idx = torch.empty(m, device=self.device, dtype=torch.int32)
         best_act = torch.empty(m, A, device=self.device, dtype=torch.float32)

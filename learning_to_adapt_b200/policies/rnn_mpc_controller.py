@@ -33,9 +33,6 @@ class RNNMPCController(Policy, Serializable):
         if use_reward_model:
             raise NotImplementedError("use_reward_model=True: learned reward models are not on the fused path")
         assert hasattr(self.unwrapped_env, "reward"), "env must have a reward function"
-        if use_cem:
-            raise NotImplementedError("use_cem=True for the recurrent planner is not implemented on the fused path yet "
-                                      "(run_rebal.py ships use_cem=False); there is no CPU fallback")
         if not hasattr(dynamics_model, "rollout") or not getattr(dynamics_model, "recurrent", False):
             raise TypeError("dynamics_model must be learning_to_adapt_b200's RNNDynamicsModel; there is no CPU fallback")
         self._reward_kind, self._dt = reward_kind_of(self.unwrapped_env)
@@ -54,7 +51,7 @@ class RNNMPCController(Policy, Serializable):
         return action, dict()
 
     def get_actions(self, observations):
-        actions = self.get_rs_action(observations)
+        actions = self.get_cem_action(observations) if self.use_cem else self.get_rs_action(observations)
         _, self._hidden_state = self.dynamics_model.predict(np.array(observations), actions, self._hidden_state)   # :63
         return actions, dict()
 
@@ -79,6 +76,43 @@ class RNNMPCController(Policy, Serializable):
         if a_host is not None:
             best = res["best_idx"].cpu().numpy()
             return a_host[0].reshape((m, n, -1))[range(m), best]                         # :118, :134
+        return res["best_act"].cpu().numpy().astype(np.float64)
+
+    def get_cem_action(self, observations):
+        """CEM for the recurrent planner (rnn_mpc_controller.py:71-110): as MPCController's, bug-compatible elite mask included
+        (:106), but the mean is replaced, not smoothed (:107; alpha = 0) and percent_elites defaults to 0.05."""
+        import ctypes as C
+        from learning_to_adapt_b200 import _native as N
+        from learning_to_adapt_b200.engine import _ptr, _stream
+        observations = np.asarray(observations, np.float64)
+        n, m, h = self.n_candidates, len(observations), self.horizon
+        dm = self.dynamics_model
+        if self._hidden_state is None:
+            self.reset(dones=[True] * m)
+        act_dim = self.action_space.shape[0]
+        ha = h * act_dim
+        num_elites = max(int(n * self.percent_elites), 1)                                 # :78
+        mean = torch.zeros((m, ha), device=dm.device, dtype=torch.float64)
+        std = torch.ones((m, ha), device=dm.device, dtype=torch.float64)
+        clip_low = dm._f32(np.concatenate([self.action_space.low] * h))
+        clip_high = dm._f32(np.concatenate([self.action_space.high] * h))
+        obs_dev = dm._f32(observations)
+        rank = torch.empty(m, n, device=dm.device, dtype=torch.int32)
+        res = None
+        for _ in range(self.num_cem_iters):
+            if self.sampler == "numpy":
+                z = dm._f32(np.random.normal(size=(n, m, ha)))                            # :85
+            else:
+                z = torch.randn((n, m, ha), device=dm.device, dtype=torch.float32)
+            samples = torch.empty(n, m, ha, device=dm.device, dtype=torch.float32)
+            clipped = torch.empty_like(samples)
+            N.check(dm.lib.l2a_cem_sample(dm._ctx, _ptr(z), _ptr(mean), _ptr(std), _ptr(clip_low), _ptr(clip_high), int(n), int(m),
+                                          int(ha), _ptr(samples), _ptr(clipped), _stream()))
+            res = dm.rollout(obs_dev, self._hidden_state, samples, n, h, self._reward_kind, self._dt, discount=self.discount,
+                             want_returns=True, layout="nmha")
+            N.check(dm.lib.l2a_cem_refit(dm._ctx, _ptr(res["returns"]), _ptr(clipped), int(n), int(m), int(ha), int(num_elites),
+                                         0.0, 1, _ptr(rank), _ptr(mean), _ptr(std), _stream()))
+        self.last_plan = res
         return res["best_act"].cpu().numpy().astype(np.float64)
 
     def get_params_internal(self, **tags):

@@ -344,6 +344,16 @@ def main():
     np.random.seed(172)
     a1, _ = rctrl1.get_action(prob["obs0"][0])
     out["rebal_get_action_shape"] = np.array(a1.shape, np.int64)
+    # recurrent CEM (bug-compatible mask, mean replaced rather than smoothed)
+    env = FakeEnv(prob, "half_cheetah_env.py")
+    rcem = rnn_ctrl_mod.RNNMPCController("policy", env, rnn_self, n_candidates=40, horizon=3, use_cem=True, num_cem_iters=2,
+                                         percent_elites=0.2)
+    rcem.reset(dones=[True, True])
+    np.random.seed(173)
+    acts, _ = rcem.get_actions(np.array(prob["obs0"]))
+    out["rebal_cem_meta"] = np.array([40, 3, 2, 2], np.int64)
+    out["rebal_cem_chosen"] = np.array(acts)
+    out["rebal_cem_last_step_rewards"] = np.stack(env.step_rewards[-3:])
 
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)

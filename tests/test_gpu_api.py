@@ -227,3 +227,57 @@ def test_rebal_rollout_matches_oracle_at_script_size():
     np.testing.assert_allclose(nxt, w_nxt, rtol=RTOL, atol=1e-5)
     np.testing.assert_allclose(hid.c, w_hid[0], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(hid.h, w_hid[1], rtol=1e-4, atol=1e-5)
+
+
+def test_rebal_cem_matches_reference_golden(golden):
+    from learning_to_adapt_b200.dynamics.rnn_dynamics import RNNDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from learning_to_adapt_b200.policies.rnn_mpc_controller import RNNMPCController
+    n, h, m, iters = [int(v) for v in golden["rebal_cem_meta"]]
+    hs = int(golden["rebal_meta"][4])
+    prob = O.make_problem("half_cheetah", hidden_sizes=(32,), n_sets=1, m=m, seed=int(golden["rebal_meta"][3]))
+    params = O.xavier_rnn_params(np.random.RandomState(62), prob["obs_dim"] + prob["act_dim"], hs, prob["obs_dim"], out_scale=0.1)
+    env = SyntheticEnv("half_cheetah")
+    model = RNNDynamicsModel("dyn", env, hidden_sizes=(hs,))
+    model.set_params(params)
+    model.set_normalization(prob["norm"])
+    ctrl = RNNMPCController("policy", env, model, n_candidates=n, horizon=h, use_cem=True, num_cem_iters=iters, percent_elites=0.2)
+    ctrl.reset(dones=[True] * m)
+    np.random.seed(173)
+    acts, _ = ctrl.get_actions(np.array(prob["obs0"]))
+    ref_returns = golden["rebal_cem_last_step_rewards"].sum(axis=0).reshape(m, n)
+    got = ctrl.last_plan["returns"].cpu().numpy()
+    assert_returns_close(got, ref_returns, rtol=5e-4)
+    assert_argmax_consistent(ctrl.last_plan["best_idx"].cpu().numpy(), ref_returns, rtol=5e-4)
+    if np.array_equal(ctrl.last_plan["best_idx"].cpu().numpy(), np.argmax(ref_returns, axis=1)):
+        np.testing.assert_allclose(acts, golden["rebal_cem_chosen"], rtol=1e-5, atol=1e-6)
+
+
+def test_c_abi_rejects_bad_arguments():
+    """Error behaviour at the boundary: negative status + message, no exception across the C ABI, no CPU fallback."""
+    import ctypes as C
+    from learning_to_adapt_b200 import _native as N
+    from learning_to_adapt_b200.engine import PlanningEngine
+    eng = PlanningEngine(20, 6, (100, 128), n_sets=2)
+    lib = eng.lib
+    prob = O.make_problem("half_cheetah", hidden_sizes=(100, 128), n_sets=1, m=1, seed=0)
+    obs, acts = dev(prob["obs0"]), dev(O.sample_rs_actions(0, prob["low"], prob["high"], 2, 8))
+    with pytest.raises(RuntimeError, match="normalization not set"):
+        eng.rollout(obs, acts, 8, 2, 0, 0.01)
+    eng.set_params(0, prob["param_sets"][0])
+    eng.set_normalization(prob["norm"])
+    with pytest.raises(RuntimeError, match="multiples of 128"):
+        eng.rollout(obs, acts, 8, 2, 0, 0.01, kernel=N.KERNEL_TCGEN05)          # hidden 100 -> no tensor-core variant
+    with pytest.raises(RuntimeError, match="out of range"):
+        eng.rollout(obs, acts, 8, 2, 0, 0.01, first_set=5)
+    with pytest.raises(RuntimeError, match="reward_kind"):
+        eng.rollout(obs, acts, 8, 2, 7, 0.01)
+    with pytest.raises(RuntimeError, match="dt must be"):
+        eng.rollout(obs, acts, 8, 2, 0, 0.0)
+    x = torch.zeros(1, 40, 26, device="cuda")
+    with pytest.raises(RuntimeError, match="M <= 32"):
+        eng.adapt(x, torch.zeros(1, 40, 20, device="cuda"), 0.1, 0, 1)
+    assert lib.l2a_rollout(eng._ctx, eng._model, None, None, None, None, None, None, None, None, None) == -1
+    assert b"NULL" in lib.l2a_last_error()
+    res = eng.rollout(obs, acts, 8, 2, 0, 0.01)                                    # and the valid call still works (SIMT: hidden 100)
+    assert int(res["best_idx"][0]) >= 0
