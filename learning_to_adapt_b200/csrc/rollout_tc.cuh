@@ -3,15 +3,18 @@
 // Orientation: the dense layers are computed TRANSPOSED, Y^T[out, cand] = W^T[out, in] * X^T[in, cand], so that
 //   * the MMA "M" dimension (128 TMEM lanes) is the layer's output features  -> bias / ReLU are per-thread scalars,
 //   * the MMA "N" dimension is the CTA's NC candidates                       -> NC need only be a multiple of 16,
-//   * A = W^T tiles [128 out x 64 in] stream from L2 by TMA bulk copies of pre-swizzled 16 KB tiles (mbarrier ring),
-//   * B = activations [NC cand x K] live in shared memory for the whole rollout (K-major, 128B swizzle),
-//   * D = fp32 accumulators in TMEM (one 128 x NC block per 128 output features).
+//   * A = W^T tiles [128 out x 64 in] stream from L2 by TMA bulk copies of pre-swizzled (hi, lo) tile pairs (32 KB, one
+//     full/empty mbarrier handshake per pair = per 12 MMAs),
+//   * B = activations [NC cand x K] live in shared memory for the whole rollout (K-major, 128B swizzle), updated in place,
+//   * D = fp32 accumulators in TMEM: six 128 x NC slots, rotated so the epilogue of layer l overlaps the first MMAs of
+//     layer l+1 (K-outer "phase A" on the activation chunks as they are published).
 // Precision: split-bf16.  Every fp32 operand x is carried as hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits) and
 // each product is three MMA passes  W_hi*x_hi + W_hi*x_lo + W_lo*x_hi  accumulated in fp32 (measured return error
 // vs the fp32/fp64 reference: ~5e-6 relative).  A single bf16 pass misses the 1e-4 parity bar.
 //
-// Warp roles (192 threads): warps 0-3 epilogue + "env step" (TMEM -> regs -> bias/ReLU/split -> smem; state update,
-// reward, normalisation, argmax), warp 4 TMA producer (one lane), warp 5 MMA issuer (one lane) + TMEM owner.
+// Warp roles (192 threads): warps 0-3 epilogue + "env step" (16x256b TMEM fragments -> bias/ReLU/split -> stmatrix; the
+// candidate's state in registers, reward, normalisation, argmax), warp 4 TMA producer (one lane), warp 5 MMA issuer (the
+// whole warp walks the loops so descriptors stay in uniform registers; an elect.sync lane issues) + TMEM owner.
 // Ensemble mode (BASELINE "ensemble=E"): a thread-block cluster of E CTAs, one member each, same candidates; the E
 // denormalised deltas are exchanged through distributed shared memory every step and averaged in member order, so
 // all E CTAs carry bit-identical states.
@@ -24,7 +27,7 @@
 namespace l2a {
 
 constexpr int kTcTileBytes = 16384;     // one [128 x 64] bf16 weight tile (hi or lo part)
-constexpr int kTcMaxStages = 4;         // weight-tile ring depth is per NC: as many 16 KB stages as shared memory allows (even, <= 8)
+constexpr int kTcMaxStages = 4;         // ring depth is per NC: as many 32 KB (hi, lo) pair stages as shared memory allows (2 at NC=80)
 constexpr int kTcMaxChunks = 8;         // activation width <= 512
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxAct = 16;           // action dim limit of this variant
