@@ -262,11 +262,11 @@ static int ensure_reduce_ws(l2a_ctx* c, size_t n_part, size_t n_env, cudaStream_
 }
 
 // --------------------------------------------------------------------------------------------- rollout
-template <int NC>
+template <int NC, int DMAX>
 static int launch_tc(l2a_ctx* c, const TcArgs& ta, int csize, cudaStream_t st) {
   const size_t smem = TcSmem<NC>::total(ta.dims.obs_dim, ta.dims.act_dim);
   if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "tcgen05 rollout needs %zu B shared memory (> %d)", smem, c->max_smem_optin);
-  CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<NC, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(ta.n_envs * ta.groups_per_env * csize));
@@ -280,7 +280,7 @@ static int launch_tc(l2a_ctx* c, const TcArgs& ta, int csize, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, rollout_tc_kernel<NC>, ta));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, rollout_tc_kernel<NC, DMAX>, ta));
   c->launches++;
   return L2A_OK;
 }
@@ -412,11 +412,19 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   ta.returns = returns;
   ta.red = ra;
   ta.timeline = c->timeline;
+  if (m->dims.obs_dim <= 24) {
+    switch (nc) {
+      case 80: return launch_tc<80, 24>(c, ta, csize, st);
+      case 64: return launch_tc<64, 24>(c, ta, csize, st);
+      case 48: return launch_tc<48, 24>(c, ta, csize, st);
+      default: return launch_tc<32, 24>(c, ta, csize, st);
+    }
+  }
   switch (nc) {
-    case 80: return launch_tc<80>(c, ta, csize, st);
-    case 64: return launch_tc<64>(c, ta, csize, st);
-    case 48: return launch_tc<48>(c, ta, csize, st);
-    default: return launch_tc<32>(c, ta, csize, st);
+    case 80: return launch_tc<80, 48>(c, ta, csize, st);
+    case 64: return launch_tc<64, 48>(c, ta, csize, st);
+    case 48: return launch_tc<48, 48>(c, ta, csize, st);
+    default: return launch_tc<32, 48>(c, ta, csize, st);
   }
 }
 

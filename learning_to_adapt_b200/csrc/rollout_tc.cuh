@@ -168,7 +168,9 @@ struct TcSmem {
 
 #define L2A_STAMP(slot) do { if (a.timeline && blockIdx.x == 0 && t == 1 && (threadIdx.x & 31) == 0) a.timeline[(slot)] = clock64(); } while (0)
 
-template <int NC>
+// DMAX: compile-time bound of the observation dimension (24 or 48): sizes the register-resident candidate state and the
+// unrolled env-step code (a 48-wide instance costs HalfCheetah's D = 20 twice the instruction-cache footprint).
+template <int NC, int DMAX>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs a) {
   using S = TcSmem<NC>;
   constexpr int kChunkBytes = S::kChunkBytes;
@@ -352,9 +354,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
     float a_cur[kTcMaxAct];
-    float st[kTcMaxObs];                                 // this candidate's state, float32, in registers for the whole rollout
+    float st[DMAX];                                      // this candidate's state, float32, in registers for the whole rollout
 #pragma unroll
-    for (int k = 0; k < kTcMaxObs; ++k) st[k] = (k < D) ? __ldg(a.obs0 + (size_t)env * D + k) : 0.f;
+    for (int k = 0; k < DMAX; ++k) st[k] = (k < D) ? __ldg(a.obs0 + (size_t)env * D + k) : 0.f;
     const int d8 = tc_obs_pad(D);
 
     auto load_actions = [&](int t) {
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       for (int j = 0; j < kTcMaxAct; ++j) a_cur[j] = (j < A && valid && has_cand) ? __ldg(src + j) : 0.f;
     };
     // normalised network input of the candidate for the step whose actions are in a_cur: features [state | action | 0]
+    int t_stamp = -1;
     auto write_x = [&]() {
       if (has_cand) {
         float s = 0.f;
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           *reinterpret_cast<uint4*>(act_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         };
 #pragma unroll
-        for (int g = 0; g < kTcMaxObs / 8; ++g) {
+        for (int g = 0; g < DMAX / 8; ++g) {
           if (g * 8 < d8) {
             float v[8];
 #pragma unroll
@@ -409,7 +412,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           for (int g = used; g < need; ++g) store_group(g, z);
         }
       }
+      if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[70] = clock64();
       umma::fence_proxy_async_smem();
+      if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[71] = clock64();
       umma::tc_fence_before();
       umma::mbar_arrive(&act_ready[0]);
     };
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         const float inv_e = 1.0f / (float)csize;
         const uint32_t dbuf_addr = umma::smem_u32(dbuf);
 #pragma unroll
-        for (int k0 = 0; k0 < kTcMaxObs; k0 += 4) {
+        for (int k0 = 0; k0 < DMAX; k0 += 4) {
           if (k0 < D) {
             float dv[4];
             if (ensemble) {
@@ -559,6 +564,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_free), (uint32_t)tid));
       }
       if (warp == 0) L2A_STAMP(63);
+      t_stamp = t;
       if (t + 1 < H) write_x();
       if (warp == 0) L2A_STAMP(64);
     }

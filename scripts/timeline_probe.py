@@ -35,3 +35,4 @@ for l in range(L - 1):
     b = 32 + 4 * l
     print("  layer %d: layer_full seen %7d  mb0 published %7d  all published %7d" % (l, t[b] - t0, t[b + 1] - t0, t[b + 2] - t0))
 print("  output: layer_full %7d  dbuf written %7d  peers ready %7d  env done %7d  x written %7d" % tuple(int(t[i] - t0) for i in (60, 61, 62, 63, 64)))
+print("  write_x: stores done %7d  fence.proxy.async done %7d" % (int(t[70] - t0), int(t[71] - t0)))
