@@ -40,6 +40,8 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 struct l2a_ctx {
+  float* xch = nullptr;            // ensemble exchange scratch (global / L2), grown on demand
+  size_t xch_cap = 0;
   long long* timeline = nullptr;   // optional diagnostics buffer (l2a_debug_set_timeline)
   int device = 0;
   int num_sms = 0;
@@ -111,6 +113,7 @@ extern "C" int l2a_ctx_destroy(l2a_ctx* c) {
   cudaFree(c->counters);
   cudaFree(c->adapt_acts);
   cudaFree(c->adapt_grads);
+  cudaFree(c->xch);
   delete c;
   return L2A_OK;
 }
@@ -412,6 +415,18 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   ta.returns = returns;
   ta.red = ra;
   ta.timeline = c->timeline;
+  if (csize > 1) {
+    const size_t blk = ((size_t)m->dims.obs_dim * (nc + 1) + 3) / 4 * 4;              // floats per member block
+    const size_t need = (size_t)p->n_envs * groups * 2 * csize * blk;
+    if (need > c->xch_cap) {
+      cudaFree(c->xch);
+      c->xch = nullptr;
+      c->xch_cap = 0;
+      CUDA_TRY(cudaMalloc(&c->xch, need * sizeof(float)));
+      c->xch_cap = need;
+    }
+    ta.xch = c->xch;
+  }
   if (m->dims.obs_dim <= 24) {
     switch (nc) {
       case 80: return launch_tc<80, 24>(c, ta, csize, st);

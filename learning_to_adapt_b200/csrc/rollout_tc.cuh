@@ -143,6 +143,7 @@ struct TcArgs {
   int groups_per_env;
   float* returns;
   ReduceArgs red;
+  float* xch;                   // ensemble exchange scratch in global memory: [clusters][2][E][xch_blk] floats (L2-resident)
   long long* timeline;          // diagnostics: clock64 stamps of CTA 0 at step 1 (null = off)
 };
 
@@ -202,14 +203,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   uint64_t* act_ready = layer_full + 1;       // [4]: one barrier per readiness event (source M-block) of a layer's input, so the
                                               // MMA issuer can lag several events behind without mbarrier parity aliasing
   uint64_t* peer_ready = layer_full + 5;
-  uint64_t* peer_free = layer_full + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 7);
   float* red_v = reinterpret_cast<float*>(tmem_slot + 2);   // [4]
   int* red_i = reinterpret_cast<int*>(red_v + 4);           // [4]
   int* s_flag = red_i + 4;
   // the exchange buffer of denormalised deltas aliases activation chunks >= 1 (dead between the output layer's MMAs and
   // the next layer-0 epilogue)
-  float* dbuf = reinterpret_cast<float*>(act_hi + kChunkBytes);     // [D][NCP]
+  float* dbuf = reinterpret_cast<float*>(act_hi + kChunkBytes);     // [D][NCP]: this member's denormalised deltas (local)
+  const int blk_f4 = (D * S::kNCP + 3) / 4;                          // one member block in 16-byte units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool ensemble = (a.set_mode == L2A_SETS_ENSEMBLE_MEAN) && a.n_sets > 1;
@@ -232,7 +233,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     umma::mbar_init(layer_full, 1);
     for (int j = 0; j < 4; ++j) umma::mbar_init(&act_ready[j], 128);
     umma::mbar_init(peer_ready, csize);
-    umma::mbar_init(peer_free, csize);
     umma::fence_barrier_init();
   }
   if (warp == 5) umma::tmem_alloc<512>(tmem_slot);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     const bool valid = n < nvalid;
     const long long row = (long long)env * a.n_candidates + c0 + (valid ? n : 0);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    uint32_t lf_phase = 0, pr_phase = 0, pf_phase = 0;
+    uint32_t lf_phase = 0, pr_phase = 0;
     int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
     float a_cur[kTcMaxAct];
@@ -429,10 +429,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         lf_phase ^= 1u;
         umma::tc_fence_after();
         if (warp == 0) L2A_STAMP(32 + 4 * l + 0);
-        if (l == 0 && ensemble && t > 0) {               // peers have finished reading my dbuf (aliases act chunks >= 1)
-          umma::mbar_wait_cluster(peer_free, pf_phase);
-          pf_phase ^= 1u;
-        }
         // Accumulator fragments (16x256b TMEM loads: thread T holds features T/4, T/4+8 x candidate pairs) are turned into
         // the next layer's K-major B operand with transposed 8x8 stmatrix stores: 16-byte rows of 8 features per candidate.
         {
@@ -508,60 +504,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 0) L2A_STAMP(61);
       if (ensemble) {
+        // Exchange of the E members' delta blocks through L2: publish mine (coalesced 16-byte stores), cluster-scope
+        // release/acquire on the peers' mbarriers, then fetch the other E-1 blocks with coalesced 16-byte loads into the dead
+        // activation chunks.  (Pulling them through distributed shared memory measured ~4 B/clk per CTA -- 5x slower.)
+        // The scratch is double-buffered by step parity: a peer can only be one exchange behind.
+        float4* mine = reinterpret_cast<float4*>(a.xch + ((size_t)(cluster_id * 2 + (t & 1)) * csize + crank) * (size_t)(blk_f4 * 4));
+        const float4* dsrc = reinterpret_cast<const float4*>(dbuf);
+        for (int i = tid; i < blk_f4; i += 128) mine[i] = dsrc[i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_ready), (uint32_t)tid));
         umma::mbar_wait_cluster(peer_ready, pr_phase);
         pr_phase ^= 1u;
+        // mean over members in member order 0..E-1, reduced while staging and written over my own block in place
+        const float4* all = reinterpret_cast<const float4*>(a.xch + (size_t)(cluster_id * 2 + (t & 1)) * csize * (size_t)(blk_f4 * 4));
+        float4* dst = reinterpret_cast<float4*>(dbuf);
+        const float inv_e = 1.0f / (float)csize;
+        for (int i = tid; i < blk_f4; i += 128) {
+          float4 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < csize) v[e] = (e == crank) ? dst[i] : __ldcg(all + (size_t)e * blk_f4 + i);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < csize) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
+          dst[i] = make_float4(acc.x * inv_e, acc.y * inv_e, acc.z * inv_e, acc.w * inv_e);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       if (warp == 0) L2A_STAMP(62);
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
-        const float inv_e = 1.0f / (float)csize;
-        const uint32_t dbuf_addr = umma::smem_u32(dbuf);
 #pragma unroll
-        for (int k0 = 0; k0 < DMAX; k0 += 4) {
-          if (k0 < D) {
-            float dv[4];
-            if (ensemble) {
-              float pe[4][8];
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  pe[u][e] = (e < csize && k0 + u < D)
-                                 ? umma::ld_dsmem_f32(umma::map_to_cta(dbuf_addr + (uint32_t)(((k0 + u) * NCP + n) * 4), (uint32_t)e))
-                                 : 0.f;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                float d = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) d += pe[u][e];      // member order 0..E-1 (unused slots add +0)
-                dv[u] = d * inv_e;
-              }
-            } else {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) dv[u] = (k0 + u < D) ? dbuf[(k0 + u) * NCP + n] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int k = k0 + u;
-              if (k < D) {
-                const float d = dv[u];
-                const float s_new = st[k] + d;                  // mlp_dynamics.py:220
-                st[k] = s_new;
-                if (k == D - 3) { dx = d; nx0 = s_new; }
-                if (k == D - 2) nx1 = s_new;
-                if (k == D - 1) nx2 = s_new;
-              }
-            }
+        for (int k = 0; k < DMAX; ++k) {
+          if (k < D) {
+            const float d = dbuf[k * NCP + n];                  // ensemble: already the member mean
+            const float s_new = st[k] + d;                      // mlp_dynamics.py:220
+            st[k] = s_new;
+            if (k == D - 3) { dx = d; nx0 = s_new; }
+            if (k == D - 2) nx1 = s_new;
+            if (k == D - 1) nx2 = s_new;
           }
         }
         const float rew = reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2);
         ret = fmaf(__ldg(a.discount_pow + t), rew, ret);     // mpc_controller.py:126
-      }
-      if (ensemble) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_free), (uint32_t)tid));
       }
       if (warp == 0) L2A_STAMP(63);
       t_stamp = t;
