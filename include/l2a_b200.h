@@ -141,6 +141,35 @@ int l2a_predict(l2a_ctx* ctx, l2a_model* model, int set_mode, int first_set, int
 int l2a_adapt(l2a_ctx* ctx, l2a_model* model, const float* x, const float* target, int K, int M, float inner_lr,
               int src_set, int dst_first_set, void* stream);
 
+/* ---- f3: device-resident adaptation window ----------------------------------------------------
+ * Replaces the running-path list slicing of Sampler.obtain_samples (samplers/sampler.py:82-90: obs[-M-1:-1], act[-M-1:-1],
+ * obs[-M:] per env, np.stack, then the float64 normalisation + float32 feed of meta_mlp_dynamics.py:334-339) with a ring of
+ * the last M+1 (observation, action) pairs per env in HBM.  All calls are stream-ordered and launch only kernels (no host
+ * synchronisation), so window_push -> adapt_from_window -> l2a_rollout form one dependent chain on `stream`.
+ *   l2a_window_create:  n_envs rings of M+1 pairs; float64 storage (what the env returns).
+ *   l2a_window_set_normalization: HOST float64 means / stds (NOT std + 1e-10: the kernel adds it like mlp_dynamics.py:266).
+ *   l2a_window_push:    append one (observation, action) pair per env (sampler.py:109-110); obs [n_envs, D], act [n_envs, A]
+ *                       float64 DEVICE pointers.
+ *   l2a_window_reset:   path of `env` ended (sampler.py:128); env < 0 resets every env.
+ *   l2a_window_length:  host mirror of env's path length (appends since the last reset) -- the reference's
+ *                       `len(running_paths[0]['observations']) > M + 1` test (sampler.py:82) reads this for env 0.
+ *   l2a_window_gather:  write the normalised windows x [n_envs, M, D+A], target [n_envs, M, D] (float32, DEVICE) -- the
+ *                       arrays the reference feeds obs_ph|act_ph and delta_ph with (meta_mlp_dynamics.py:334-345).
+ *   l2a_adapt_from_window: l2a_window_gather into the window's own buffers, then exactly l2a_adapt with K = n_envs.
+ *                       Both: L2A_ERR_INVALID if any env's path is shorter than M+1 (the reference's np.stack would be ragged). */
+typedef struct l2a_window l2a_window;
+int l2a_window_create(l2a_ctx* ctx, int n_envs, int M, int obs_dim, int act_dim, l2a_window** out);
+int l2a_window_destroy(l2a_ctx* ctx, l2a_window* w);
+int l2a_window_set_normalization(l2a_ctx* ctx, l2a_window* w, const double* obs_mean, const double* obs_std,
+                                 const double* act_mean, const double* act_std, const double* delta_mean,
+                                 const double* delta_std, void* stream);
+int l2a_window_push(l2a_ctx* ctx, l2a_window* w, const double* obs, const double* act, void* stream);
+int l2a_window_reset(l2a_ctx* ctx, l2a_window* w, int env, void* stream);
+int l2a_window_length(l2a_ctx* ctx, const l2a_window* w, int env);
+int l2a_window_gather(l2a_ctx* ctx, l2a_window* w, float* x, float* target, void* stream);
+int l2a_adapt_from_window(l2a_ctx* ctx, l2a_model* model, l2a_window* w, float inner_lr, int src_set, int dst_first_set,
+                          void* stream);
+
 /* ---- K1c: CEM sampling / refit (policies/mpc_controller.py:84-104) -------------------------------------
  * l2a_cem_sample: a = mean + z*std (:86) -> samples [n, m, H*A] fp32 (rolled out UNclipped, :88-89) and
  *   clipped copy (:87).  mean/std are float64 [m, H*A]; z fp32 [n, m, H*A]; clip_low/high fp32 [H*A].

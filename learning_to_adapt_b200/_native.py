@@ -17,6 +17,8 @@ EXPORTS = [
     "l2a_model_set_normalization", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
     "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
+    "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
+    "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window",
 ]
 
 
@@ -62,6 +64,14 @@ def load():
     lib.l2a_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
     lib.l2a_adapt.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]
+    lib.l2a_window_create.argtypes = [vp, i32, i32, i32, i32, pp]
+    lib.l2a_window_destroy.argtypes = [vp, vp]
+    lib.l2a_window_set_normalization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_window_push.argtypes = [vp, vp, vp, vp, vp]
+    lib.l2a_window_reset.argtypes = [vp, vp, i32, vp]
+    lib.l2a_window_length.argtypes = [vp, vp, i32]
+    lib.l2a_window_gather.argtypes = [vp, vp, vp, vp, vp]
+    lib.l2a_adapt_from_window.argtypes = [vp, vp, vp, f32, i32, i32, vp]
     lib.l2a_cem_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.l2a_cem_refit.argtypes = [vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp]
     lib.l2a_debug_umma_tile.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]

@@ -19,6 +19,7 @@
 #include "rollout_rnn_tc.cuh"
 #include "rollout_tc.cuh"
 #include "shard.cuh"
+#include "window.cuh"
 
 using namespace l2a;
 
@@ -492,8 +493,8 @@ extern "C" int l2a_predict(l2a_ctx* c, l2a_model* m, int set_mode, int first_set
 }
 
 // --------------------------------------------------------------------------------------------- adapt
-extern "C" int l2a_adapt(l2a_ctx* c, l2a_model* m, const float* x, const float* target, int K, int M, float inner_lr,
-                         int src_set, int dst_first_set, void* stream) {
+static int adapt_impl(l2a_ctx* c, l2a_model* m, const float* x, const float* target, int K, int M, float inner_lr,
+                      int src_set, int dst_first_set, void* stream) {
   if (!c || !m || !x || !target) return fail(L2A_ERR_INVALID, "NULL argument");
   if (K < 1 || M < 1 || M > kAdaptMaxM) return fail(L2A_ERR_INVALID, "K=%d, M=%d: need K >= 1 and 1 <= M <= %d", K, M, kAdaptMaxM);
   if (src_set < 0 || src_set >= m->desc.n_sets || dst_first_set < 0 || dst_first_set + K > m->desc.n_sets)
@@ -576,6 +577,136 @@ extern "C" int l2a_adapt(l2a_ctx* c, l2a_model* m, const float* x, const float* 
 }
 
 // --------------------------------------------------------------------------------------------- CEM
+extern "C" int l2a_adapt(l2a_ctx* c, l2a_model* m, const float* x, const float* target, int K, int M, float inner_lr,
+                         int src_set, int dst_first_set, void* stream) {
+  return adapt_impl(c, m, x, target, K, M, inner_lr, src_set, dst_first_set, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ f3: adaptation window
+struct l2a_window {
+  WindowDev dev;
+  double* norm = nullptr;      // device copy of the float64 statistics
+  float* x = nullptr;          // [n_envs, M, D+A] normalised inputs
+  float* target = nullptr;     // [n_envs, M, D] normalised targets
+  int M = 0;
+  bool norm_set = false;
+  std::vector<int> length;     // host mirror of dev.count (push / reset are deterministic)
+};
+
+extern "C" int l2a_window_create(l2a_ctx* c, int n_envs, int M, int obs_dim, int act_dim, l2a_window** out) {
+  if (!c || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (n_envs < 1 || M < 1 || M > kAdaptMaxM || obs_dim < 1 || act_dim < 1)
+    return fail(L2A_ERR_INVALID, "n_envs=%d M=%d obs_dim=%d act_dim=%d: need n_envs >= 1, 1 <= M <= %d, dims >= 1", n_envs, M, obs_dim, act_dim, kAdaptMaxM);
+  CUDA_TRY(cudaSetDevice(c->device));
+  l2a_window* w = new l2a_window();
+  memset(&w->dev, 0, sizeof(w->dev));
+  w->M = M;
+  w->dev.n_envs = n_envs;
+  w->dev.cap = M + 1;
+  w->dev.D = obs_dim;
+  w->dev.A = act_dim;
+  w->length.assign(n_envs, 0);
+  const size_t pairs = (size_t)n_envs * (M + 1);
+  cudaError_t e = cudaMalloc(&w->dev.obs, pairs * obs_dim * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->dev.act, pairs * act_dim * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->dev.count, n_envs * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&w->norm, (size_t)(4 * obs_dim + 2 * act_dim) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->x, (size_t)n_envs * M * (obs_dim + act_dim) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&w->target, (size_t)n_envs * M * obs_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(w->dev.count, 0, n_envs * sizeof(int));
+  if (e != cudaSuccess) {
+    l2a_window_destroy(c, w);
+    return fail(L2A_ERR_CUDA, "window allocation failed: %s", cudaGetErrorString(e));
+  }
+  w->dev.norm = w->norm;
+  *out = w;
+  return L2A_OK;
+}
+
+extern "C" int l2a_window_destroy(l2a_ctx* c, l2a_window* w) {
+  if (!c || !w) return fail(L2A_ERR_INVALID, "NULL argument");
+  cudaSetDevice(c->device);
+  cudaFree(w->dev.obs);
+  cudaFree(w->dev.act);
+  cudaFree(w->dev.count);
+  cudaFree(w->norm);
+  cudaFree(w->x);
+  cudaFree(w->target);
+  delete w;
+  return L2A_OK;
+}
+
+extern "C" int l2a_window_set_normalization(l2a_ctx* c, l2a_window* w, const double* obs_mean, const double* obs_std,
+                                            const double* act_mean, const double* act_std, const double* delta_mean,
+                                            const double* delta_std, void* stream) {
+  if (!c || !w || !obs_mean || !obs_std || !act_mean || !act_std || !delta_mean || !delta_std) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = w->dev.D, A = w->dev.A;
+  std::vector<double> h((size_t)(4 * D + 2 * A));
+  memcpy(h.data(), obs_mean, D * sizeof(double));
+  memcpy(h.data() + D, obs_std, D * sizeof(double));
+  memcpy(h.data() + 2 * D, act_mean, A * sizeof(double));
+  memcpy(h.data() + 2 * D + A, act_std, A * sizeof(double));
+  memcpy(h.data() + 2 * D + 2 * A, delta_mean, D * sizeof(double));
+  memcpy(h.data() + 3 * D + 2 * A, delta_std, D * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(w->norm, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));     // h goes out of scope
+  w->norm_set = true;
+  return L2A_OK;
+}
+
+extern "C" int l2a_window_push(l2a_ctx* c, l2a_window* w, const double* obs, const double* act, void* stream) {
+  if (!c || !w || !obs || !act) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  window_push_kernel<<<w->dev.n_envs, 64, 0, (cudaStream_t)stream>>>(w->dev, obs, act);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  for (int& l : w->length) l += 1;
+  return L2A_OK;
+}
+
+extern "C" int l2a_window_reset(l2a_ctx* c, l2a_window* w, int env, void* stream) {
+  if (!c || !w) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (env >= w->dev.n_envs) return fail(L2A_ERR_INVALID, "env %d out of range [0,%d)", env, w->dev.n_envs);
+  CUDA_TRY(cudaSetDevice(c->device));
+  window_reset_kernel<<<(w->dev.n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dev, env);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  for (int i = 0; i < w->dev.n_envs; ++i)
+    if (env < 0 || env == i) w->length[i] = 0;
+  return L2A_OK;
+}
+
+extern "C" int l2a_window_length(l2a_ctx* c, const l2a_window* w, int env) {
+  if (!c || !w) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (env < 0 || env >= w->dev.n_envs) return fail(L2A_ERR_INVALID, "env %d out of range [0,%d)", env, w->dev.n_envs);
+  return w->length[env];
+}
+
+extern "C" int l2a_window_gather(l2a_ctx* c, l2a_window* w, float* x, float* target, void* stream) {
+  if (!c || !w || !x || !target) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!w->norm_set) return fail(L2A_ERR_INVALID, "window normalisation statistics are not set");
+  for (int i = 0; i < w->dev.n_envs; ++i)
+    if (w->length[i] < w->M + 1)
+      return fail(L2A_ERR_INVALID, "env %d has %d transitions on its running path, the adapt window needs %d", i, w->length[i], w->M + 1);
+  CUDA_TRY(cudaSetDevice(c->device));
+  window_gather_kernel<<<w->dev.n_envs, 128, 0, (cudaStream_t)stream>>>(w->dev, w->M, x, target);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return L2A_OK;
+}
+
+extern "C" int l2a_adapt_from_window(l2a_ctx* c, l2a_model* m, l2a_window* w, float inner_lr, int src_set, int dst_first_set,
+                                     void* stream) {
+  if (!c || !m || !w) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (w->dev.D != m->dims.obs_dim || w->dev.A != m->dims.act_dim)
+    return fail(L2A_ERR_INVALID, "window dims (%d, %d) do not match the model's (%d, %d)", w->dev.D, w->dev.A, m->dims.obs_dim, m->dims.act_dim);
+  const int rc = l2a_window_gather(c, w, w->x, w->target, stream);
+  if (rc != L2A_OK) return rc;
+  return adapt_impl(c, m, w->x, w->target, w->dev.n_envs, w->M, inner_lr, src_set, dst_first_set, stream);
+}
+
 extern "C" int l2a_cem_sample(l2a_ctx* c, const float* z, const double* mean, const double* std_, const float* clip_low,
                               const float* clip_high, int n, int m, int ha, float* samples, float* clipped, void* stream) {
   if (!c || !z || !mean || !std_ || !clip_low || !clip_high || !samples || !clipped) return fail(L2A_ERR_INVALID, "NULL argument");

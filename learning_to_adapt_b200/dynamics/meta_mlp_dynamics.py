@@ -6,7 +6,10 @@ Weight set 0 is the prior theta; sets 1..meta_batch_size hold the per-env adapte
 (:347-351).  After ``adapt`` with K tasks, ``predict`` and the fused rollout step row chunk k through theta'_k
 (:296-306) -- without re-uploading K x theta' every horizon step as the TF feed_dict did.
 """
+import ctypes as C
+
 import numpy as np
+import torch
 
 from learning_to_adapt_b200 import _native as N
 from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel, normalize
@@ -70,6 +73,25 @@ class MetaMLPDynamicsModel(MLPDynamicsModel):
         x = eng._f32(np.concatenate([obs_n, act_n], axis=2))
         target = eng._f32(delta_n)
         eng.adapt(x, target, self.inner_learning_rate, src_set=0, dst_first_set=1)
+        self._num_adapted_models = k
+        self._adapted = True
+
+    def make_adapt_window(self, n_envs, adapt_batch_size):
+        from learning_to_adapt_b200.samplers.window import AdaptWindow
+        return AdaptWindow(self._engine, n_envs, adapt_batch_size)
+
+    def adapt_from_window(self, window):
+        """adapt() on the windows held by a device-resident AdaptWindow (samplers/window.py): the gather of
+        obs[-M-1:-1] / act[-M-1:-1] / obs[-M:] (samplers/sampler.py:83-88) and the float64 normalisation (:334-339) run in a
+        kernel in front of K2; inputs to K2 are bit-identical to adapt()'s."""
+        k = window.n_envs
+        if k > self.meta_batch_size:
+            raise ValueError("window holds %d envs but meta_batch_size is %d" % (k, self.meta_batch_size))
+        if window._norm_src is not self.normalization:
+            window.set_normalization(self.normalization)
+        eng = self._engine
+        N.check(eng.lib.l2a_adapt_from_window(eng._ctx, eng._model, window._h, float(self.inner_learning_rate), 0, 1,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self._num_adapted_models = k
         self._adapted = True
 

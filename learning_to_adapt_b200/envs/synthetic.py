@@ -46,6 +46,40 @@ class SyntheticEnv(object):
         return -np.linalg.norm(next_obs[:, -3:], axis=1) - 0.005 * np.sum(np.square(action), axis=1)  # arm_7dof_env.py:91-99
 
 
+class LinearWorldEnv(SyntheticEnv):
+    """A steppable stand-in: obs' = obs + 5 dt (obs @ A_task + act @ B), a random stable linear system whose per-task perturbation
+    of A plays the role of the crippled leg / changed terrain of the paper's envs.  Gym-style reset() / step() -> (obs, reward,
+    done, info) like the reference envs (envs/half_cheetah_env.py:39-56); obs[-3] is the coordinate the reward differentiates.
+    It only produces transitions for the sampler: planning never steps it."""
+
+    def __init__(self, name="half_cheetah", seed=0):
+        SyntheticEnv.__init__(self, name)
+        self.rng = np.random.RandomState(seed)
+        D, A = self.observation_space.shape[0], self.action_space.shape[0]
+        self.A0 = -0.5 * np.eye(D) + 0.1 * self.rng.normal(size=(D, D))
+        self.B = 0.5 * self.rng.normal(size=(A, D))
+        self.B[:, -3] += 1.0
+        self.reset_task()
+        self.obs = np.zeros(D)
+
+    def seed(self, seed):
+        self.rng = np.random.RandomState(seed)
+
+    def reset_task(self, value=None):
+        self.A = self.A0 + 0.05 * self.rng.normal(size=self.A0.shape)
+
+    def reset(self):
+        self.obs = 0.1 * self.rng.normal(size=self.A.shape[0])
+        return self.obs.copy()
+
+    def step(self, action):
+        action = np.asarray(action, np.float64).reshape(-1)
+        nxt = self.obs + self.dt * 5.0 * (self.obs @ self.A + action @ self.B)
+        r = float(self.reward(self.obs[None], action[None], nxt[None])[0])
+        self.obs = nxt
+        return nxt.copy(), r, False, {}
+
+
 def reward_kind_of(env):
     """Reward family + dt of an env object (ours or one of the reference's classes)."""
     kind = getattr(env, "l2a_reward_kind", None)

@@ -49,8 +49,42 @@ for env_name, K, M, n, h in (("half_cheetah", 5, 16, 1000, 15), ("ant", 5, 16, 2
         step()
     torch.cuda.synchronize()
     e2e = (time.perf_counter() - t0) / 20
+    # the same env step with the adaptation windows resident on the device (f3): push + gather + K2 + K1
+    win = model.make_adapt_window(K, M)
+    rng = np.random.RandomState(1)
+    for j in range(M + 2):
+        win.push(np.stack([c[min(j, M - 1)] for c in ctx[0]]), np.stack([c[min(j, M - 1)] for c in ctx[1]]))
+    act_prev = np.zeros((K, prob["act_dim"]))
+    def step_window():
+        win.push(obs, act_prev)
+        model.switch_to_pre_adapt()
+        model.adapt_from_window(win)
+        return ctrl.get_actions(obs)
+    for _ in range(3):
+        step_window()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step_window()
+    torch.cuda.synchronize()
+    e2e_win = (time.perf_counter() - t0) / 20
+    # host formulation including the list slicing the reference's sampler does each step
+    paths = [dict(observations=list(rng.normal(size=(M + 4, prob["obs_dim"]))), actions=list(rng.normal(size=(M + 4, prob["act_dim"])))) for _ in range(K)]
+    def step_lists():
+        model.switch_to_pre_adapt()
+        model.adapt([np.stack(p["observations"][-M - 1:-1]) for p in paths], [np.stack(p["actions"][-M - 1:-1]) for p in paths],
+                    [np.stack(p["observations"][-M:]) for p in paths])
+        return ctrl.get_actions(obs)
+    for _ in range(3):
+        step_lists()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step_lists()
+    torch.cuda.synchronize()
+    e2e_lists = (time.perf_counter() - t0) / 20
     t0 = time.perf_counter()
     O.adapt(*ctx, prob["param_sets"][0], prob["norm"], 1e-3)
     cpu = time.perf_counter() - t0
     print(json.dumps(dict(cfg="%s K=%d M=%d N=%d H=%d" % (env_name, K, M, n, h), adapt_kernels_ms=float(np.median(tms)),
-                          grbal_step_e2e_ms=e2e * 1e3, cpu_oracle_adapt_ms=cpu * 1e3)), flush=True)
+                          grbal_step_e2e_ms=e2e * 1e3, grbal_step_lists_ms=e2e_lists * 1e3, grbal_step_device_window_ms=e2e_win * 1e3, cpu_oracle_adapt_ms=cpu * 1e3)), flush=True)
