@@ -11,9 +11,10 @@ MLP 26->512->512->512->20.  Weak scaling: every rank plans its own 2000 candidat
 
 value  : whole-job candidate-rollouts/s with the candidate tensor already resident in HBM, CUDA-event timed per step,
          L2 flushed (256 MB write) between steps, max over ranks.
-e2e    : the same metric through the public API call MPCController.get_actions(obs ndarray) -> ndarray, with the host->
-         device copy of the observations and the device->host copy of the chosen actions inside the timed region
-         (candidates are sampled on the device inside the call, sampler="device").
+e2e    : the same metric through the public API call MPCController.get_actions(obs ndarray) -> ndarray = ONE host-buffer
+         C-ABI call (l2a_plan_run): host->device copy of the observations, Philox candidate sampling on the device, K1,
+         device->host copy of the chosen actions -- all inside the timed region (sampler="device"; at N>1 GPUs the
+         candidate shard adds the NCCL all-gather).
 roofline: dominant kernel rollout_tc_kernel, tensor-pipe bound; achieved = algorithmic FLOPs per launch (N*H*E*F, counted once
          although split-bf16 issues 3 MMA passes) / mean launch duration.
 cpu_baseline: oracle port (numpy planner + float32 BLAS MLP) timed on the host cores on a bounded sample of the same workload.
@@ -291,6 +292,8 @@ def run_cuda(args):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e_value = world * n * m / e2e_s
     ctrl_np = MPCController("policy", env, model, n_candidates=n, horizon=h, sampler="numpy") if not distributed else None
+    if os.environ.get("L2A_BENCH_SKIP_CPU"):
+        ctrl_np = None
     e2e_numpy = None
     if ctrl_np is not None:
         np.random.seed(0)
@@ -308,7 +311,7 @@ def run_cuda(args):
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only), bounded sample
     cpu = None
-    if world == 1:
+    if world == 1 and not os.environ.get("L2A_BENCH_SKIP_CPU"):      # (development runs may skip the 15 s host leg)
         from threadpoolctl import threadpool_limits
         cores = pick_blas_threads(O, prob, h)
         calls = 0

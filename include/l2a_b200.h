@@ -125,6 +125,26 @@ int l2a_rollout(l2a_ctx* ctx, l2a_model* model, const l2a_rollout_params* p, con
                 const float* actions, const float* discount_pow, float* returns, float* best_ret,
                 int32_t* best_idx, float* best_act, void* stream);
 
+/* ---- host-buffer planning call: the reference-facing call --------------------------------------------------------------
+ * Replaces MPCController.get_actions for random shooting as its caller sees it (policies/mpc_controller.py:59-65, 108-129,
+ * incl. get_random_action :67-69): HOST observations in, HOST actions out.  A plan fixes p (N, m, H, weight sets, reward
+ * family, dt, kernel; the action strides are ignored -- the plan owns the [H, m*N, A] candidate tensor), the discount, the
+ * action bounds low/high (HOST float32 [A]) and the Philox seed.
+ * l2a_plan_run: obs HOST float64 [m, D] -> act_out HOST float64 [m, A] (+ optional ret_out float32 [m], idx_out int32 [m]).
+ *   Per call: H2D copy of obs from pinned memory -> candidate sampling U[low, high) on the device (Philox4x32-10, counter =
+ *   (element, call index)) -> K1 -> D2H of the result to pinned memory; after the first call the four stream operations
+ *   are one captured CUDA graph (env L2A_NO_GRAPH=1 issues them individually).  Work queued on `stream` before the call is
+ *   waited for; the call returns when the outputs are in the host buffers. */
+typedef struct l2a_plan l2a_plan;
+int l2a_plan_create(l2a_ctx* ctx, l2a_model* model, const l2a_rollout_params* p, float discount, const float* low,
+                    const float* high, uint64_t seed, l2a_plan** out);
+int l2a_plan_run(l2a_ctx* ctx, l2a_plan* plan, const double* obs, double* act_out, float* ret_out, int32_t* idx_out,
+                 void* stream);
+int l2a_plan_destroy(l2a_ctx* ctx, l2a_plan* plan);
+int l2a_plan_uses_graph(const l2a_plan* plan);   /* 1 once the call sequence has been captured and is being replayed */
+/* the candidate tensor the most recent l2a_plan_run drew, [H, m*N, A] float32, to a HOST buffer (tests / diagnostics) */
+int l2a_plan_copy_candidates(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
+
 /* ---- K4: one dynamics step (API compatibility) --------------------------------------------------------
  * Replaces (Meta)MLPDynamicsModel.predict (mlp_dynamics.py:204-222, meta_mlp_dynamics.py:276-306).
  * obs [n, D], act [n, A] raw (un-normalised).  set_mode SHARED: all rows use first_set; PER_ENV: n must be

@@ -19,6 +19,7 @@ EXPORTS = [
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window",
+    "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_uses_graph", "l2a_plan_copy_candidates",
 ]
 
 
@@ -62,6 +63,11 @@ def load():
     lib.l2a_model_get_params.argtypes = [vp, vp, i32, pp, pp, vp]
     lib.l2a_model_set_normalization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_plan_create.argtypes = [vp, vp, C.POINTER(RolloutParams), f32, vp, vp, C.c_uint64, pp]
+    lib.l2a_plan_run.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_plan_destroy.argtypes = [vp, vp]
+    lib.l2a_plan_uses_graph.argtypes = [vp]
+    lib.l2a_plan_copy_candidates.argtypes = [vp, vp, vp]
     lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
     lib.l2a_adapt.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]
     lib.l2a_window_create.argtypes = [vp, i32, i32, i32, i32, pp]

@@ -18,6 +18,7 @@
 #include "rollout_rnn_simt.cuh"
 #include "rollout_rnn_tc.cuh"
 #include "rollout_tc.cuh"
+#include "sample.cuh"
 #include "shard.cuh"
 #include "window.cuh"
 
@@ -48,6 +49,7 @@ struct l2a_ctx {
   int num_sms = 0;
   int max_smem_optin = 0;
   long long launches = 0;
+  long long ws_epoch = 0;          // bumped whenever a workspace pointer a captured graph may hold changes
   // per-env reduction workspace
   float* part_ret = nullptr;
   int* part_idx = nullptr;
@@ -185,7 +187,7 @@ static int launch_prep(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, cuda
   pa.params = m->params;
   pa.blobs = m->blobs;
   pa.first_set = first_set;
-  dim3 grid(m->plan.tiles_per_set / 2, n_sets);
+  dim3 grid(m->plan.hidden_pairs + m->plan.nkc[m->plan.n_layers - 1], n_sets);
   tc_prep_kernel<<<grid, 256, 0, st>>>(pa);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -252,6 +254,7 @@ static int ensure_reduce_ws(l2a_ctx* c, size_t n_part, size_t n_env, cudaStream_
     CUDA_TRY(cudaMalloc(&c->part_ret, cap * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->part_idx, cap * sizeof(int)));
     c->part_cap = cap;
+    c->ws_epoch++;
   }
   if (n_env > c->counter_cap) {
     cudaFree(c->counters);
@@ -261,6 +264,7 @@ static int ensure_reduce_ws(l2a_ctx* c, size_t n_part, size_t n_env, cudaStream_
     CUDA_TRY(cudaMalloc(&c->counters, cap * sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(c->counters, 0, cap * sizeof(unsigned int), st));
     c->counter_cap = cap;
+    c->ws_epoch++;
   }
   return L2A_OK;
 }
@@ -416,8 +420,9 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   ta.returns = returns;
   ta.red = ra;
   ta.timeline = c->timeline;
+  if (const char* fl = getenv("L2A_TC_FLAGS")) ta.flags = atoi(fl);                  // experiments only (see TcArgs::flags)
   if (csize > 1) {
-    const size_t blk = ((size_t)m->dims.obs_dim * (nc + 1) + 3) / 4 * 4;              // floats per member block
+    const size_t blk = (size_t)nc * (m->dims.obs_dim <= 24 ? 24 : 48);                // floats per member block: [NC][DMAX]
     const size_t need = (size_t)p->n_envs * groups * 2 * csize * blk;
     if (need > c->xch_cap) {
       cudaFree(c->xch);
@@ -425,6 +430,7 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
       c->xch_cap = 0;
       CUDA_TRY(cudaMalloc(&c->xch, need * sizeof(float)));
       c->xch_cap = need;
+      c->ws_epoch++;
     }
     ta.xch = c->xch;
   }
@@ -442,6 +448,176 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
     case 48: return launch_tc<48, 48>(c, ta, csize, st);
     default: return launch_tc<32, 48>(c, ta, csize, st);
   }
+}
+
+
+// --------------------------------------------------------------------------------------------- host-buffer planning call
+// One random-shooting planning call with HOST buffers on both sides (what MPCController.get_actions is to its caller,
+// policies/mpc_controller.py:59-65 + 108-129): H2D(obs, call index) -> Philox candidate sampling -> K1 -> D2H(result).
+// The four stream operations are captured once into a CUDA graph and replayed (one cudaGraphLaunch per call); the pinned
+// input block carries the call index so that every replay draws fresh candidates.
+struct l2a_plan {
+  l2a_model* model = nullptr;
+  l2a_rollout_params p;
+  int D = 0, A = 0;
+  uint64_t seed = 0, calls = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr;
+  float* in_host = nullptr;        // pinned: obs [m, D] fp32, then the 64-bit call index
+  float* in_dev = nullptr;
+  float* out_host = nullptr;       // pinned: best_ret [m], best_idx [m] (int32), best_act [m, A]
+  float* out_dev = nullptr;
+  float* actions = nullptr;        // [H, m*N, A]
+  float* low = nullptr;            // [A], high [A], discount_pow [H]
+  size_t in_bytes = 0, out_bytes = 0;
+  cudaGraphExec_t exec = nullptr;
+  long long graph_epoch = -1;
+  bool use_graph = true;
+};
+
+extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
+  if (!pl) return L2A_OK;
+  if (c) cudaSetDevice(c->device);
+  if (pl->stream) cudaStreamSynchronize(pl->stream);
+  if (pl->exec) cudaGraphExecDestroy(pl->exec);
+  if (pl->ev_in) cudaEventDestroy(pl->ev_in);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  cudaFreeHost(pl->in_host);
+  cudaFreeHost(pl->out_host);
+  cudaFree(pl->in_dev);
+  cudaFree(pl->out_dev);
+  cudaFree(pl->actions);
+  cudaFree(pl->low);
+  delete pl;
+  return L2A_OK;
+}
+
+extern "C" int l2a_plan_create(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p, float discount, const float* low,
+                               const float* high, uint64_t seed, l2a_plan** out) {
+  if (!c || !m || !p || !low || !high || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (p->n_candidates < 1 || p->n_envs < 1 || p->horizon < 1) return fail(L2A_ERR_INVALID, "n_candidates/n_envs/horizon must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  l2a_plan* pl = new (std::nothrow) l2a_plan();
+  if (!pl) return fail(L2A_ERR_INVALID, "out of host memory");
+  pl->model = m;
+  pl->p = *p;
+  pl->D = m->dims.obs_dim;
+  pl->A = m->dims.act_dim;
+  pl->seed = seed;
+  const int mm = p->n_envs, A = pl->A, H = p->horizon;
+  const long long rows = (long long)p->n_candidates * mm;
+  pl->p.act_stride_t = rows * A;                       // the plan owns the candidate tensor: [H, m*N, A] (mpc_controller.py:114)
+  pl->p.act_stride_row = A;
+  pl->in_bytes = sizeof(float) * (size_t)mm * pl->D + 8;
+  pl->out_bytes = sizeof(float) * (size_t)mm * (2 + A);
+  pl->use_graph = getenv("L2A_NO_GRAPH") == nullptr;
+  std::vector<float> consts((size_t)2 * A + H);
+  for (int j = 0; j < A; ++j) { consts[j] = low[j]; consts[A + j] = high[j]; }
+  double pw = 1.0;
+  for (int t = 0; t < H; ++t) { consts[2 * A + t] = (float)pw; pw *= (double)discount; }   // discount**t (mpc_controller.py:126)
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMallocHost(&pl->in_host, pl->in_bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&pl->out_host, pl->out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->in_dev, pl->in_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->out_dev, pl->out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->actions, sizeof(float) * (size_t)H * rows * A);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->low, sizeof(float) * consts.size());
+  if (e == cudaSuccess) e = cudaMemcpy(pl->low, consts.data(), sizeof(float) * consts.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    l2a_plan_destroy(c, pl);
+    return fail(L2A_ERR_CUDA, "l2a_plan_create: %s", cudaGetErrorString(e));
+  }
+  *out = pl;
+  return L2A_OK;
+}
+
+// the stream-ordered body of one planning call (captured into the graph, or issued directly)
+static int plan_enqueue(l2a_ctx* c, l2a_plan* pl) {
+  const int mm = pl->p.n_envs, A = pl->A, H = pl->p.horizon;
+  const long long total = (long long)H * pl->p.n_candidates * mm * A;
+  cudaStream_t st = pl->stream;
+  CUDA_TRY(cudaMemcpyAsync(pl->in_dev, pl->in_host, pl->in_bytes, cudaMemcpyHostToDevice, st));
+  const long long blocks = (total + 4 * 256 - 1) / (4 * 256);
+  sample_uniform_kernel<<<(unsigned)blocks, 256, 0, st>>>(pl->low, pl->low + A, pl->actions, total, A, pl->seed,
+                                                          reinterpret_cast<const uint32_t*>(pl->in_dev + (size_t)mm * pl->D));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  float* best_ret = pl->out_dev;
+  int32_t* best_idx = reinterpret_cast<int32_t*>(pl->out_dev + mm);
+  float* best_act = pl->out_dev + 2 * mm;
+  int rc = l2a_rollout(c, pl->model, &pl->p, pl->in_dev, pl->actions, pl->low + 2 * A, nullptr, best_ret, best_idx, best_act, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(pl->out_host, pl->out_dev, pl->out_bytes, cudaMemcpyDeviceToHost, st));
+  return L2A_OK;
+}
+
+extern "C" int l2a_plan_run(l2a_ctx* c, l2a_plan* pl, const double* obs, double* act_out, float* ret_out, int32_t* idx_out,
+                            void* stream) {
+  if (!c || !pl || !obs || !act_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int mm = pl->p.n_envs, A = pl->A, D = pl->D;
+  for (int i = 0; i < mm * D; ++i) pl->in_host[i] = (float)obs[i];                    // the float32 feed of mlp_dynamics.py:212-214
+  memcpy(pl->in_host + (size_t)mm * D, &pl->calls, 8);
+  // everything the caller queued on its stream (weight uploads, adapt) happens before this call
+  CUDA_TRY(cudaEventRecord(pl->ev_in, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->ev_in, 0));
+  bool done = false;
+  if (pl->use_graph && pl->calls > 0) {
+    if (pl->exec && pl->graph_epoch != c->ws_epoch) {             // a workspace the graph points into was reallocated
+      cudaGraphExecDestroy(pl->exec);
+      pl->exec = nullptr;
+    }
+    if (!pl->exec) {
+      // (the first call ran uncaptured and sized every workspace, so no allocation happens inside the capture)
+      cudaGraph_t g = nullptr;
+      const long long launches0 = c->launches, epoch0 = c->ws_epoch;
+      cudaError_t e = cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal);
+      int rc = L2A_OK;
+      if (e == cudaSuccess) {
+        rc = plan_enqueue(c, pl);
+        e = cudaStreamEndCapture(pl->stream, &g);
+      }
+      c->launches = launches0;
+      if (e == cudaSuccess && rc == L2A_OK && g && c->ws_epoch == epoch0) e = cudaGraphInstantiate(&pl->exec, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (e != cudaSuccess || rc != L2A_OK || !pl->exec || c->ws_epoch != epoch0) {
+        if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+        cudaGetLastError();
+        pl->use_graph = false;                                    // direct launches from now on (same kernels)
+      } else {
+        pl->graph_epoch = c->ws_epoch;
+      }
+    }
+    if (pl->exec) {
+      CUDA_TRY(cudaGraphLaunch(pl->exec, pl->stream));
+      c->launches += 2;                                           // sample + K1 per replay
+      done = true;
+    }
+  }
+  if (!done) {
+    int rc = plan_enqueue(c, pl);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(pl->stream));
+  pl->calls++;
+  const float* o = pl->out_host;
+  if (ret_out) memcpy(ret_out, o, sizeof(float) * mm);
+  if (idx_out) memcpy(idx_out, o + mm, sizeof(int32_t) * mm);
+  for (int i = 0; i < mm * A; ++i) act_out[i] = (double)o[2 * mm + i];
+  return L2A_OK;
+}
+
+extern "C" int l2a_plan_uses_graph(const l2a_plan* pl) { return (pl && pl->exec) ? 1 : 0; }
+
+extern "C" int l2a_plan_copy_candidates(l2a_ctx* c, l2a_plan* pl, float* host_out) {
+  if (!c || !pl || !host_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(pl->stream));
+  const size_t n = (size_t)pl->p.horizon * pl->p.n_candidates * pl->p.n_envs * pl->A;
+  CUDA_TRY(cudaMemcpy(host_out, pl->actions, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return L2A_OK;
 }
 
 // --------------------------------------------------------------------------------------------- predict
@@ -768,6 +944,7 @@ extern "C" int l2a_debug_stream(l2a_ctx* c, const void* blob, int n_tiles_per_pa
 extern "C" int l2a_debug_set_timeline(l2a_ctx* c, long long* buf128) {
   if (!c) return fail(L2A_ERR_INVALID, "NULL ctx");
   c->timeline = buf128;
+  c->ws_epoch++;
   return L2A_OK;
 }
 
@@ -796,7 +973,7 @@ extern "C" int l2a_shard_select(l2a_ctx* c, const float* gathered, int G, int m,
 
 extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long long* cycles_out, void* stream) {
   if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
-  if (mode < 0 || mode > 3 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
+  if (mode < 0 || mode > 8 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t smem = 4 * 16384 + 2 * (size_t)nc * 128 + 64;
   if (nc == 80) {

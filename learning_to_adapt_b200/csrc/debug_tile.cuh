@@ -164,6 +164,8 @@ namespace l2a {
 //   mode 1: TS  (A pre-copied to TMEM once, only the MMAs are timed)
 //   mode 2: CP  (only the 8 tcgen05.cp of the hi and lo tile per pair)
 //   mode 3: CP+TS per pair, two TMEM staging slots (cp of pair p+1 issued before the MMAs of pair p)
+//   mode 4: SS with the A-collector keep / reuse hints on the two W_hi passes           -- rollout_tc_kernel, hidden layers
+//   mode 5-8: the output layer's swapped-role shape (M = 128 candidates, N = 32 / 48 features) with / without the hints
 // cycles_out[0] = SM cycles for `iters` pairs.
 template <int NC>
 __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int iters, long long* cycles_out) {
@@ -207,6 +209,29 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
             umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bh + 2 * ks, idesc, 1u);
             umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
             umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
+          }
+        } else if (mode == 4) {
+          // SS with A-collector hints: W_hi is read from shared memory once for its two passes
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d, a_hi + 2 * ks, bh + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
+          }
+        } else if (mode >= 5 && mode <= 8) {
+          // output-layer shape (roles swapped): M = 128 candidates (A = a 16 KB activation chunk), N = 32 (modes 5, 6) or
+          // 48 (modes 7, 8) features; odd modes with the A-collector hints, even modes without
+          const uint32_t idesc_o = umma::make_idesc_bf16(128, mode <= 6 ? 32u : 48u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (mode & 1) {
+              umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d, a_hi + 2 * ks, bh + 2 * ks, idesc_o, 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + 2 * ks, bl + 2 * ks, idesc_o, 1u);
+            } else {
+              umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bh + 2 * ks, idesc_o, 1u);
+              umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bl + 2 * ks, idesc_o, 1u);
+            }
+            umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc_o, 1u);
           }
         } else if (mode == 1) {
 #pragma unroll

@@ -15,9 +15,15 @@
 // Warp roles (192 threads): warps 0-3 epilogue + "env step" (16x256b TMEM fragments -> bias/ReLU/split -> stmatrix; the
 // candidate's state in registers, reward, normalisation, argmax), warp 4 TMA producer (one lane), warp 5 MMA issuer (the
 // whole warp walks the loops so descriptors stay in uniform registers; an elect.sync lane issues) + TMEM owner.
-// Ensemble mode (BASELINE "ensemble=E"): a thread-block cluster of E CTAs, one member each, same candidates; the E
-// denormalised deltas are exchanged through distributed shared memory every step and averaged in member order, so
-// all E CTAs carry bit-identical states.
+// The OUTPUT layer runs with the roles swapped, D[cand, feat] = X[cand, in] * W[in, feat]: the resident activation chunks
+// are the A operand (M = 128 TMEM lanes = candidates; rows >= NC read whatever follows the chunk and land in unused lanes),
+// the weights are small [out_n x 64] B tiles (out_n = obs dim padded to 16).  The MMA N drops from NC to out_n, the weight
+// stream of the layer from 256 KB to 64 KB per step, and every candidate's D deltas arrive in the registers of its own
+// env-step thread with one tcgen05.ld -- no transposition through shared memory.
+// Ensemble mode (BASELINE "ensemble=E"): a thread-block cluster of E CTAs, one member each, same candidates; every step
+// each candidate thread publishes its member's denormalised delta row to an L2-resident scratch, the cluster meets on an
+// mbarrier, and the thread reads back its row of the other E-1 members and averages in member order, so all E CTAs carry
+// bit-identical states.
 //
 // Replaces policies/mpc_controller.py:116-129 + dynamics/mlp_dynamics.py:204-222 / meta_mlp_dynamics.py:296-306.
 #pragma once
@@ -44,8 +50,12 @@ struct TcPlan {
   int nkc[kMaxLayers];
   int nks_last[kMaxLayers];
   int tile_off[kMaxLayers];
-  int tiles_per_set;
-  long long set_bytes;
+  int hidden_pairs;      // 32 KB ring stages (tile pairs) of the hidden layers
+  int out_n;             // output layer: MMA N = obs dim padded to a multiple of 16
+  int out_kcs;           // output layer: K chunks ([out_n x 64] hi + lo tiles) packed into one 32 KB ring stage
+  int out_stages;        // output layer: ring stages
+  int stages_per_set;    // hidden_pairs + out_stages
+  long long set_bytes;   // stages_per_set * 32 KB
 };
 
 __host__ __device__ inline int tc_tile_index(const TcPlan& p, int l, int mb, int kc, int part) {
@@ -69,6 +79,7 @@ inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
   if (md.act_dim > kTcMaxAct || md.obs_dim > kTcMaxObs || md.obs_dim < 3) return false;
   if (tc_obs_pad(md.obs_dim) + md.act_dim > 64) return false;
   p->n_layers = md.n_layers;
+  if (md.n_layers < 2) return false;
   int off = 0;
   for (int l = 0; l < md.n_layers; ++l) {
     const int din = md.dims[l], dout = md.dims[l + 1];
@@ -82,16 +93,21 @@ inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
     const int rem = din_eff - (p->nkc[l] - 1) * 64;
     p->nks_last[l] = (rem + 15) / 16;
     p->tile_off[l] = off;
-    off += p->nmb[l] * p->nkc[l] * 2;
+    if (l + 1 < md.n_layers) off += p->nmb[l] * p->nkc[l] * 2;
   }
-  if (md.n_layers < 2) return false;
-  p->tiles_per_set = off;
-  p->set_bytes = (long long)off * kTcTileBytes;
+  p->hidden_pairs = off / 2;
+  // output layer (roles swapped): per K chunk one [out_n x 64] hi tile followed by the lo tile, out_kcs chunks per stage
+  p->out_n = (md.obs_dim + 15) / 16 * 16;
+  p->out_kcs = (2 * kTcTileBytes) / (2 * p->out_n * 128);
+  p->out_stages = (p->nkc[md.n_layers - 1] + p->out_kcs - 1) / p->out_kcs;
+  p->stages_per_set = p->hidden_pairs + p->out_stages;
+  p->set_bytes = (long long)p->stages_per_set * 2 * kTcTileBytes;
   return true;
 }
 
 // fp32 [in, out] kernels -> bf16 hi/lo tiles, transposed to [out, in] (K-major) and pre-swizzled (SWIZZLE_128B),
-// zero padded.  grid.x = (layer, mb, kc) triples of one set, grid.y = set.
+// zero padded.  grid.x = (layer, mb, kc) triples of the hidden layers, then one block per K chunk of the output layer;
+// grid.y = set.
 struct PrepArgs {
   MlpDims dims;
   TcPlan plan;
@@ -102,8 +118,34 @@ struct PrepArgs {
 
 __global__ void __launch_bounds__(256) tc_prep_kernel(const PrepArgs a) {
   const int set = a.first_set + blockIdx.y;
+  if ((int)blockIdx.x >= a.plan.hidden_pairs) {
+    // output layer: B-operand tile [out_n features x 64 inputs] of K chunk kc, hi part then lo part
+    const int l = a.plan.n_layers - 1;
+    const int kc = (int)blockIdx.x - a.plan.hidden_pairs;
+    const int din = a.dims.dims[l], dout = a.dims.dims[l + 1];
+    const float* W = a.params + (size_t)set * a.dims.set_stride + a.dims.w_off[l];
+    const int part_bytes = a.plan.out_n * 128;
+    uint8_t* tile_hi = a.blobs + (size_t)set * a.plan.set_bytes +
+                       (size_t)(a.plan.hidden_pairs + kc / a.plan.out_kcs) * (2 * kTcTileBytes) +
+                       (size_t)(kc % a.plan.out_kcs) * 2 * part_bytes;
+    uint8_t* tile_lo = tile_hi + part_bytes;
+    for (int item = threadIdx.x; item < a.plan.out_n * 8; item += blockDim.x) {
+      const int f = item % a.plan.out_n, ch = item / a.plan.out_n;
+      uint16_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc * 64 + ch * 8 + i;
+        const float w = (f < dout && k < din) ? W[(size_t)k * dout + f] : 0.f;
+        umma::split_bf16(w, hi[i], lo[i]);
+      }
+      const uint32_t off = umma::sw128_offset(f, ch * 8);
+      *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+      *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+    }
+    return;
+  }
   int l = 0, rem = blockIdx.x;
-  while (l + 1 < a.plan.n_layers && rem >= a.plan.nmb[l] * a.plan.nkc[l]) { rem -= a.plan.nmb[l] * a.plan.nkc[l]; ++l; }
+  while (l + 2 < a.plan.n_layers && rem >= a.plan.nmb[l] * a.plan.nkc[l]) { rem -= a.plan.nmb[l] * a.plan.nkc[l]; ++l; }
   const int mb = rem / a.plan.nkc[l], kc = rem % a.plan.nkc[l];
   const int din = a.dims.dims[l], dout = a.dims.dims[l + 1];
   const float* W = a.params + (size_t)set * a.dims.set_stride + a.dims.w_off[l];
@@ -143,7 +185,8 @@ struct TcArgs {
   int groups_per_env;
   float* returns;
   ReduceArgs red;
-  float* xch;                   // ensemble exchange scratch in global memory: [clusters][2][E][xch_blk] floats (L2-resident)
+  float* xch;                   // ensemble exchange scratch in global memory: [clusters][2][E][NC][DMAX] floats (L2-resident)
+  int flags;                    // experiments: bit 0 = no A-collector hints on the split-bf16 passes
   long long* timeline;          // diagnostics: clock64 stamps of CTA 0 at step 1 (null = off)
 };
 
@@ -162,7 +205,8 @@ struct TcSmem {
   static_assert(kStages >= 2, "no room for the weight-tile ring");
   static constexpr size_t misc_off = stage_off + (size_t)kStages * kStageBytes;
   static size_t total(int D, int A) {
-    size_t misc = sizeof(float) * (4 * (size_t)D + 2 * (size_t)A) + 64 /*pad*/ + 32 * sizeof(uint64_t) + 64;
+    (void)D; (void)A;
+    size_t misc = sizeof(float) * (5 * (size_t)kTcMaxObs + 2 * (size_t)kTcMaxAct) + 64 /*pad*/ + 32 * sizeof(uint64_t) + 64;
     return misc_off + misc;       // the dynamic shared window is 1024-byte aligned (checked in the kernel)
   }
 };
@@ -190,13 +234,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   uint8_t* act_hi = smem;
   uint8_t* act_lo = smem + (size_t)kTcMaxChunks * kChunkBytes;
   uint8_t* stages = smem + S::stage_off;
+  // per-feature constants, zero padded to DMAX / kTcMaxAct so the env step reads them as 16-byte vectors without bounds tests
   float* n_obs_mean = reinterpret_cast<float*>(smem + S::misc_off);
-  float* n_obs_den = n_obs_mean + D;
-  float* n_dmean = n_obs_den + D;
-  float* n_dscale = n_dmean + D;
-  float* n_act_mean = n_dscale + D;
-  float* n_act_den = n_act_mean + A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(n_act_den + A) + 15) & ~(uintptr_t)15);
+  float* n_obs_den = n_obs_mean + DMAX;
+  float* n_dmean = n_obs_den + DMAX;
+  float* n_dscale = n_dmean + DMAX;
+  float* n_bias_out = n_dscale + DMAX;        // output-layer bias of this CTA's weight set
+  float* n_act_mean = n_bias_out + DMAX;
+  float* n_act_den = n_act_mean + kTcMaxAct;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(n_act_den + kTcMaxAct) + 15) & ~(uintptr_t)15);
   uint64_t* full = bars;                      // [kTcStages]
   uint64_t* empty = bars + kTcStages;         // [kTcStages]
   uint64_t* layer_full = bars + 2 * kTcStages;
@@ -207,10 +253,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   float* red_v = reinterpret_cast<float*>(tmem_slot + 2);   // [4]
   int* red_i = reinterpret_cast<int*>(red_v + 4);           // [4]
   int* s_flag = red_i + 4;
-  // the exchange buffer of denormalised deltas aliases activation chunks >= 1 (dead between the output layer's MMAs and
-  // the next layer-0 epilogue)
-  float* dbuf = reinterpret_cast<float*>(act_hi + kChunkBytes);     // [D][NCP]: this member's denormalised deltas (local)
-  const int blk_f4 = (D * S::kNCP + 3) / 4;                          // one member block in 16-byte units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool ensemble = (a.set_mode == L2A_SETS_ENSEMBLE_MEAN) && a.n_sets > 1;
@@ -236,13 +278,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     umma::fence_barrier_init();
   }
   if (warp == 5) umma::tmem_alloc<512>(tmem_slot);
-  for (int i = tid; i < D; i += kTcThreads) {
-    n_obs_mean[i] = a.norm.obs_mean[i];
-    n_obs_den[i] = 1.0f / a.norm.obs_den[i];              // reciprocal: x_n = (x - mean) * (1 / (std + 1e-10))
-    n_dmean[i] = a.norm.delta_mean[i];
-    n_dscale[i] = a.norm.delta_scale[i];
+  for (int i = tid; i < DMAX; i += kTcThreads) {
+    const bool in = i < D;
+    n_obs_mean[i] = in ? a.norm.obs_mean[i] : 0.f;
+    n_obs_den[i] = in ? 1.0f / a.norm.obs_den[i] : 0.f;   // reciprocal: x_n = (x - mean) * (1 / (std + 1e-10))
+    n_dmean[i] = in ? a.norm.delta_mean[i] : 0.f;
+    n_dscale[i] = in ? a.norm.delta_scale[i] : 0.f;
+    n_bias_out[i] = in ? P[md.b_off[L - 1] + i] : 0.f;
   }
-  for (int i = tid; i < A; i += kTcThreads) { n_act_mean[i] = a.norm.act_mean[i]; n_act_den[i] = 1.0f / a.norm.act_den[i]; }
+  for (int i = tid; i < kTcMaxAct; i += kTcThreads) {
+    n_act_mean[i] = (i < A) ? a.norm.act_mean[i] : 0.f;
+    n_act_den[i] = (i < A) ? 1.0f / a.norm.act_den[i] : 0.f;
+  }
   umma::tc_fence_before();
   __syncthreads();
   if (ensemble) umma::cluster_sync_all();      // peers' barriers are initialised before any remote arrive
@@ -254,12 +301,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int pairs_per_set = plan.tiles_per_set / 2;
+      const int out_part2 = 2 * plan.out_n * 128;               // one K chunk of the output layer: hi + lo tile
+      const int out_nkc = plan.nkc[L - 1];
       for (int t = 0; t < H; ++t) {
-        for (int pr = 0; pr < pairs_per_set; ++pr) {
+        for (int pr = 0; pr < plan.stages_per_set; ++pr) {
+          uint32_t bytes = S::kStageBytes;
+          if (pr >= plan.hidden_pairs) bytes = (uint32_t)(min(plan.out_kcs, out_nkc - (pr - plan.hidden_pairs) * plan.out_kcs) * out_part2);
           umma::mbar_wait(&empty[stage], phase ^ 1u);
-          umma::mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
-          umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes, blob + (size_t)pr * S::kStageBytes, S::kStageBytes, &full[stage]);
+          umma::mbar_arrive_expect_tx(&full[stage], bytes);
+          umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes, blob + (size_t)pr * S::kStageBytes, bytes, &full[stage]);
           if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -275,6 +325,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)S::kStageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
+      const bool hints = !(a.flags & 1);
       // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block
       auto tile_pair = [&](uint32_t d_tmem, int kc, bool first, bool full_k, int nks_last) {
         const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
@@ -282,18 +333,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         umma::tc_fence_after();
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         if (umma::elect_one()) {
-          if (full_k) {
-            umma::mma_bf16_ss_lo(d_tmem, a_hi, bh, kIdesc, first ? 0u : 1u);          // W_hi * x_hi
-            umma::mma_bf16_ss_lo(d_tmem, a_hi, bl, kIdesc, 1u);                       // W_hi * x_lo
-            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, 1u);                       // W_lo * x_hi
+          if (full_k && hints) {
+            // the W_hi tile is fetched from shared memory once for the two passes that use it (A-collector keep / reuse)
+            umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi, bh, kIdesc, first ? 0u : 1u);    // W_hi * x_hi
+            umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi, bl, kIdesc, 1u);                // W_hi * x_lo
+            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, 1u);                                    // W_lo * x_hi
 #pragma unroll
             for (int ks = 1; ks < 4; ++ks) {
-              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, 1u);
-              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
             }
           } else {
-            for (int ks = 0; ks < nks_last; ++ks) {
+            const int nks = full_k ? 4 : nks_last;
+            for (int ks = 0; ks < nks; ++ks) {
               umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
@@ -308,14 +361,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       // {2,3} in pair b_i = a_i + 1; a_{i+1} = a_i + 2 (mod 3) is the pair layer i does not touch, so phase A of layer i+1
       // can run while layer i's epilogue is still draining a_i / b_i, and b_{i+1} = a_i is drained by the time phase B starts.
       int pair_a = 0;
+      const uint32_t idesc_out = umma::make_idesc_bf16(128, (uint32_t)plan.out_n);
+      const uint32_t out_part = (uint32_t)(plan.out_n * 128) >> 4;     // one [out_n x 64] tile in descriptor units
       for (int t = 0; t < H; ++t) {
-        for (int l = 0; l < L; ++l) {
+        for (int l = 0; l + 1 < L; ++l) {
           const int nmb = plan.nmb[l], nkc = plan.nkc[l], nks_last = plan.nks_last[l];
           const int nA = nmb < 2 ? nmb : 2;
           const int pair_b = (pair_a + 1) % 3;
           const int nsrc = (l == 0) ? 1 : plan.nmb[l - 1];          // readiness events of this layer's input
           const int cpe = (l == 0) ? nkc : 2;                       // activation chunks published per event
           L2A_STAMP(4 * l + 0);
+          if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64();   // step length
           // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
           for (int ev = 0; ev < nsrc; ++ev) {
             umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
@@ -335,6 +391,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             const bool full_k = (kc != nkc - 1) || (nks_last == 4);
             for (int mb = nA; mb < nmb; ++mb)
               tile_pair(tmem_base + (uint32_t)((2 * pair_b + (mb - nA)) * NC), kc, kc == 0, full_k, nks_last);
+          }
+          if (umma::elect_one()) umma::mma_commit(layer_full);
+          __syncwarp();
+          L2A_STAMP(4 * l + 2);
+          pair_a = (pair_a + 2) % 3;
+        }
+        // ---- output layer, roles swapped: D[cand, feat] (+)= X[cand, 64-chunk] * W[64-chunk, feat]; A = the resident
+        // activation chunk (x_hi is kept in the collector for its two passes), B = [out_n x 64] weight tiles, out_kcs K
+        // chunks per ring stage.  The accumulator is the first out_n columns of pair a.
+        {
+          const int l = L - 1;
+          const int nkc = plan.nkc[l], nsrc = plan.nmb[l - 1];
+          const uint32_t d_out = tmem_base + (uint32_t)(2 * pair_a * NC);
+          int j = 0;                                                // K chunk within the current ring stage
+          L2A_STAMP(4 * l + 0);
+          for (int ev = 0; ev < nsrc; ++ev) {
+            umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
+            act_phase ^= (1u << ev);
+            umma::tc_fence_after();
+            if (ev == 0) L2A_STAMP(4 * l + 3);
+            const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * 2);
+            for (int kc = ev * 2; kc < kc_end; ++kc) {
+              if (j == 0) {
+                umma::mbar_wait(&full[stage], phase);
+                umma::tc_fence_after();
+              }
+              const uint32_t xh = hi_lo32 + (uint32_t)kc * kChunkStep, xl = lo_lo32 + (uint32_t)kc * kChunkStep;
+              const uint32_t wh = st_lo32 + (uint32_t)stage * kStageStep + (uint32_t)j * 2u * out_part, wl = wh + out_part;
+              const bool last_in_stage = (j + 1 == plan.out_kcs) || (kc == nkc - 1);
+              if (umma::elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (hints) {
+                    umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_out, xh + 2 * ks, wh + 2 * ks, idesc_out, (kc == 0 && ks == 0) ? 0u : 1u);   // x_hi * W_hi
+                    umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_out, xh + 2 * ks, wl + 2 * ks, idesc_out, 1u);                              // x_hi * W_lo
+                  } else {
+                    umma::mma_bf16_ss_lo(d_out, xh + 2 * ks, wh + 2 * ks, idesc_out, (kc == 0 && ks == 0) ? 0u : 1u);
+                    umma::mma_bf16_ss_lo(d_out, xh + 2 * ks, wl + 2 * ks, idesc_out, 1u);
+                  }
+                  umma::mma_bf16_ss_lo(d_out, xl + 2 * ks, wh + 2 * ks, idesc_out, 1u);                                                    // x_lo * W_hi
+                }
+                if (last_in_stage) umma::mma_commit(&empty[stage]);
+              }
+              __syncwarp();
+              if (last_in_stage) {
+                j = 0;
+                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+              } else {
+                ++j;
+              }
+            }
           }
           if (umma::elect_one()) umma::mma_commit(layer_full);
           __syncwarp();
@@ -384,11 +491,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 #pragma unroll
         for (int g = 0; g < DMAX / 8; ++g) {
           if (g * 8 < d8) {
-            float v[8];
+            float mu[8], rd[8], v[8];
+            *reinterpret_cast<float4*>(&mu[0]) = *reinterpret_cast<const float4*>(n_obs_mean + g * 8);
+            *reinterpret_cast<float4*>(&mu[4]) = *reinterpret_cast<const float4*>(n_obs_mean + g * 8 + 4);
+            *reinterpret_cast<float4*>(&rd[0]) = *reinterpret_cast<const float4*>(n_obs_den + g * 8);
+            *reinterpret_cast<float4*>(&rd[4]) = *reinterpret_cast<const float4*>(n_obs_den + g * 8 + 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int k = g * 8 + i;
-              v[i] = (k < D) ? (st[k] - n_obs_mean[k]) * n_obs_den[k] : 0.f;               // mlp_dynamics.py:265-266
+              const float x = (st[g * 8 + i] - mu[i]) * rd[i];                              // mlp_dynamics.py:265-266
+              v[i] = (g * 8 + i < D) ? x : 0.f;
             }
             store_group(g, v);
           }
@@ -396,11 +507,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 #pragma unroll
         for (int ga = 0; ga < kTcMaxAct / 8; ++ga) {
           if (ga * 8 < A) {
-            float v[8];
+            float mu[8], rd[8], v[8];
+            *reinterpret_cast<float4*>(&mu[0]) = *reinterpret_cast<const float4*>(n_act_mean + ga * 8);
+            *reinterpret_cast<float4*>(&mu[4]) = *reinterpret_cast<const float4*>(n_act_mean + ga * 8 + 4);
+            *reinterpret_cast<float4*>(&rd[0]) = *reinterpret_cast<const float4*>(n_act_den + ga * 8);
+            *reinterpret_cast<float4*>(&rd[4]) = *reinterpret_cast<const float4*>(n_act_den + ga * 8 + 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int j = ga * 8 + i;
-              v[i] = (j < A) ? (a_cur[j] - n_act_mean[j]) * n_act_den[j] : 0.f;
+              const float x = (a_cur[ga * 8 + i] - mu[i]) * rd[i];
+              v[i] = (ga * 8 + i < A) ? x : 0.f;
             }
             store_group(d8 / 8 + ga, v);
           }
@@ -423,6 +538,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     write_x();
 
     for (int t = 0; t < H; ++t) {
+      const float disc_t = __ldg(a.discount_pow + t);       // discount**t, fetched a whole step before its use
       // ---------------- hidden layers: TMEM -> bias + ReLU -> split -> next layer's B operand (in place)
       for (int l = 0; l + 1 < L; ++l) {
         umma::mbar_wait(layer_full, lf_phase);
@@ -475,80 +591,107 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         if (warp == 0) L2A_STAMP(32 + 4 * l + 2);
         pair_a = (pair_a + 2) % 3;
       }
-      // ---------------- output layer: y -> denormalised delta -> exchange buffer
+      // ---------------- output layer: this candidate's D outputs (TMEM lane = candidate) -> denormalised delta, in registers
       if (t + 1 < H) load_actions(t + 1);                 // prefetch the next step's actions (HBM) under the MMA wait
       umma::mbar_wait(layer_full, lf_phase);
       lf_phase ^= 1u;
       umma::tc_fence_after();
       if (warp == 0) L2A_STAMP(60);
-      if (warp * 32 < D) {
-        const int f = tid;
-        const bool frow = f < D;
-        const float bias = frow ? __ldg(P + md.b_off[L - 1] + f) : 0.f;
-        const float sc = frow ? n_dscale[f] : 0.f, mu = frow ? n_dmean[f] : 0.f;
-        uint32_t r[NC / 16][16];
+      float dl[DMAX];
+      {
+        uint32_t r[DMAX];
+        const uint32_t t_addr = tmem_base + lane_base + (uint32_t)(2 * pair_a * NC);
 #pragma unroll
-        for (int c16 = 0; c16 < NC / 16; ++c16)
-          umma::tmem_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(2 * pair_a * NC + c16 * 16), r[c16]);
+        for (int g = 0; g < DMAX / 8; ++g) umma::tmem_ld_32x32b_x8(t_addr + (uint32_t)(g * 8), &r[g * 8]);
         umma::tmem_ld_wait();
-        if (frow) {
 #pragma unroll
-          for (int c16 = 0; c16 < NC / 16; ++c16)
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              dbuf[f * NCP + c16 * 16 + i] = (__uint_as_float(r[c16][i]) + bias) * sc + mu;   // mlp_dynamics.py:269-270
+        for (int q = 0; q < DMAX / 4; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(n_bias_out + 4 * q);
+          const float4 sc = *reinterpret_cast<const float4*>(n_dscale + 4 * q);
+          const float4 mu = *reinterpret_cast<const float4*>(n_dmean + 4 * q);
+          const float y0 = (__uint_as_float(r[4 * q]) + b.x) * sc.x + mu.x;                 // mlp_dynamics.py:269-270
+          const float y1 = (__uint_as_float(r[4 * q + 1]) + b.y) * sc.y + mu.y;
+          const float y2 = (__uint_as_float(r[4 * q + 2]) + b.z) * sc.z + mu.z;
+          const float y3 = (__uint_as_float(r[4 * q + 3]) + b.w) * sc.w + mu.w;
+          dl[4 * q] = (4 * q < D) ? y0 : 0.f;             // (columns >= D hold padding / stale accumulator data)
+          dl[4 * q + 1] = (4 * q + 1 < D) ? y1 : 0.f;
+          dl[4 * q + 2] = (4 * q + 2 < D) ? y2 : 0.f;
+          dl[4 * q + 3] = (4 * q + 3 < D) ? y3 : 0.f;
         }
       }
       pair_a = (pair_a + 2) % 3;
       umma::tc_fence_before();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 0) L2A_STAMP(61);
+      if (a.timeline && blockIdx.x < 8 && t == 1 && tid == 0) a.timeline[96 + 2 * blockIdx.x] = clock64();       // member skew
       if (ensemble) {
-        // Exchange of the E members' delta blocks through L2: publish mine (coalesced 16-byte stores), cluster-scope
-        // release/acquire on the peers' mbarriers, then fetch the other E-1 blocks with coalesced 16-byte loads into the dead
-        // activation chunks.  (Pulling them through distributed shared memory measured ~4 B/clk per CTA -- 5x slower.)
-        // The scratch is double-buffered by step parity: a peer can only be one exchange behind.
-        float4* mine = reinterpret_cast<float4*>(a.xch + ((size_t)(cluster_id * 2 + (t & 1)) * csize + crank) * (size_t)(blk_f4 * 4));
-        const float4* dsrc = reinterpret_cast<const float4*>(dbuf);
-        for (int i = tid; i < blk_f4; i += 128) mine[i] = dsrc[i];
+        // Exchange of the E members' deltas through L2: every candidate thread publishes its own row (DMAX floats, 16-byte
+        // stores), the cluster meets on the peers' mbarriers (release / acquire at cluster scope), then the thread reads
+        // the same row of the other E-1 members (ld.global.cg) and averages in member order 0..E-1 -- identical on every
+        // member.  The scratch is double-buffered by step parity: a peer can only be one exchange behind.
+        // Scratch layout [member][16-byte unit q][candidate]: a warp's accesses to one unit are 512 contiguous bytes.
+        constexpr int DQ = DMAX / 4;                         // 16-byte units per candidate row
+        const int dq = (D + 3) >> 2;                         // ... that carry data
+        float4* const blk0 = reinterpret_cast<float4*>(a.xch) + (size_t)(cluster_id * 2 + (t & 1)) * csize * (size_t)(NC * DQ);
+        if (has_cand) {
+          float4* mine = blk0 + (size_t)crank * (NC * DQ) + n;
+#pragma unroll
+          for (int q = 0; q < DQ; ++q)
+            if (q < dq) mine[q * NC] = make_float4(dl[4 * q], dl[4 * q + 1], dl[4 * q + 2], dl[4 * q + 3]);
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_ready), (uint32_t)tid));
         umma::mbar_wait_cluster(peer_ready, pr_phase);
         pr_phase ^= 1u;
-        // mean over members in member order 0..E-1, reduced while staging and written over my own block in place
-        const float4* all = reinterpret_cast<const float4*>(a.xch + (size_t)(cluster_id * 2 + (t & 1)) * csize * (size_t)(blk_f4 * 4));
-        float4* dst = reinterpret_cast<float4*>(dbuf);
-        const float inv_e = 1.0f / (float)csize;
-        for (int i = tid; i < blk_f4; i += 128) {
-          float4 v[8];
+        if (has_cand) {
+          const float inv_e = 1.0f / (float)csize;
+          const float4* rows = blk0 + n;
+          constexpr int QB = (DMAX <= 24) ? 3 : 2;           // units per member fetched in one batch (all loads in flight)
+          static_assert(DQ % QB == 0, "row batches");
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (e < csize) v[e] = (e == crank) ? dst[i] : __ldcg(all + (size_t)e * blk_f4 + i);
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int qb = 0; qb < DQ; qb += QB) {
+            if (qb < dq) {
+              float4 v[8][QB];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (e < csize) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
-          dst[i] = make_float4(acc.x * inv_e, acc.y * inv_e, acc.z * inv_e, acc.w * inv_e);
+              for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int q = 0; q < QB; ++q)
+                  if (e < csize && e != crank && qb + q < dq) v[e][q] = __ldcg(rows + (size_t)e * (NC * DQ) + (qb + q) * NC);
+#pragma unroll
+              for (int q = 0; q < QB; ++q) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int k0 = 4 * (qb + q);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (e < csize) {
+                    const bool own = (e == crank);
+                    acc.x += own ? dl[k0] : v[e][q].x;
+                    acc.y += own ? dl[k0 + 1] : v[e][q].y;
+                    acc.z += own ? dl[k0 + 2] : v[e][q].z;
+                    acc.w += own ? dl[k0 + 3] : v[e][q].w;
+                  }
+                if (qb + q < dq) { dl[k0] = acc.x * inv_e; dl[k0 + 1] = acc.y * inv_e; dl[k0 + 2] = acc.z * inv_e; dl[k0 + 3] = acc.w * inv_e; }
+              }
+            }
+          }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       if (warp == 0) L2A_STAMP(62);
+      if (a.timeline && blockIdx.x < 8 && t == 1 && tid == 0) a.timeline[97 + 2 * blockIdx.x] = clock64();
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
 #pragma unroll
         for (int k = 0; k < DMAX; ++k) {
-          if (k < D) {
-            const float d = dbuf[k * NCP + n];                  // ensemble: already the member mean
-            const float s_new = st[k] + d;                      // mlp_dynamics.py:220
-            st[k] = s_new;
-            if (k == D - 3) { dx = d; nx0 = s_new; }
-            if (k == D - 2) nx1 = s_new;
-            if (k == D - 1) nx2 = s_new;
-          }
+          const float d = dl[k];                                // ensemble: already the member mean; 0 for k >= D
+          const float s_new = st[k] + d;                        // mlp_dynamics.py:220
+          st[k] = s_new;
+          dx = (k == D - 3) ? d : dx;
+          nx0 = (k == D - 3) ? s_new : nx0;
+          nx1 = (k == D - 2) ? s_new : nx1;
+          nx2 = (k == D - 1) ? s_new : nx2;
         }
         const float rew = reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2);
-        ret = fmaf(__ldg(a.discount_pow + t), rew, ret);     // mpc_controller.py:126
+        ret = fmaf(disc_t, rew, ret);                        // mpc_controller.py:126
       }
       if (warp == 0) L2A_STAMP(63);
       t_stamp = t;

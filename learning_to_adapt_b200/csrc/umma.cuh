@@ -138,6 +138,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 consecutive fp32 columns (thread i: lane lane_base + i, columns [col, col+8)), into r[0..8)
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 // 16 lanes x (8 x REP) fp32 columns in the mma-accumulator fragment layout: for column block j (8 columns),
 // thread T holds  r[4j+0], r[4j+1] = (lane T/4,     columns 8j + 2(T%4), +1)
 //                 r[4j+2], r[4j+3] = (lane T/4 + 8, columns 8j + 2(T%4), +1)        (lanes relative to the address lane)
@@ -202,6 +209,36 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
       : "memory");
+}
+// Same with a collector hint for the A operand: kAKeep = this MMA's A tile stays in the collector buffer for the next MMA
+// (.collector::a::fill -> SASS UTCHMMA ...A_KEEP); kAReuse = this MMA takes A from the collector instead of re-reading shared
+// memory (.collector::a::lastuse -> A_REUSE).  The caller guarantees that a kAReuse MMA directly follows a kAKeep MMA with
+// the identical A descriptor.  An SS-mode MMA at N = 80 is shared-memory-bandwidth bound (4 KB of A + 2.5 KB of B per 40
+// tensor cycles), so not re-reading W_hi for the W_hi * x_lo pass removes a fifth of the operand traffic.
+enum : int { kANone = 0, kAKeep = 1, kAReuse = 2 };
+template <int HINT>
+__device__ __forceinline__ void mma_bf16_ss_lo_hint(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (HINT == kAKeep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
+        : "memory");
+  } else if (HINT == kAReuse) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
+        : "memory");
+  } else {
+    mma_bf16_ss_lo(d_tmem, a_lo, b_lo, idesc, accumulate);
+  }
 }
 // A operand from TENSOR MEMORY (128 lanes x 8 columns per K=16 slice), B from shared memory.
 __device__ __forceinline__ void mma_bf16_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {

@@ -56,9 +56,13 @@ class PlanningEngine(object):
             self._layer_shapes.append((sizes[l], sizes[l + 1]))
         self._discount_cache = {}
         self._norm = None
+        self._plans = {}
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
+        for plan in getattr(self, "_plans", {}).values():
+            self.lib.l2a_plan_destroy(self._ctx, plan["handle"])
+        self._plans = {}
         if getattr(self, "_model", None) is not None and self._model:
             self.lib.l2a_model_destroy(self._ctx, self._model)
             self._model = None
@@ -163,6 +167,50 @@ class PlanningEngine(object):
                                      _ptr(self._discount_pow(discount, horizon)), _ptr(returns), _ptr(best_ret),
                                      _ptr(best_idx), _ptr(best_act), _stream()))
         return dict(best_ret=best_ret, best_idx=best_idx, best_act=best_act, returns=returns)
+
+    # ------------------------------------------------------------------ host-buffer planning call (l2a_plan_*)
+    def plan_rs_host(self, observations, n_candidates, horizon, reward_kind, dt, low, high, discount=1.0,
+                     set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO, seed=0):
+        """One random-shooting planning call with HOST arrays on both sides (policies/mpc_controller.py:59-65, 108-129):
+        observations float64 [m, D] -> (actions float64 [m, A], best_ret float32 [m], best_idx int32 [m]).  The candidates
+        are drawn on the device (Philox); after the first call the whole sequence H2D -> sample -> K1 -> D2H is one CUDA
+        graph replay inside libl2a_b200."""
+        obs = np.ascontiguousarray(observations, dtype=np.float64)
+        m = obs.shape[0]
+        assert obs.shape == (m, self.obs_dim)
+        low32 = np.ascontiguousarray(low, dtype=np.float32)
+        high32 = np.ascontiguousarray(high, dtype=np.float32)
+        assert low32.shape == (self.act_dim,) and high32.shape == (self.act_dim,)
+        key = (m, int(n_candidates), int(horizon), int(reward_kind), float(dt), float(discount), int(set_mode), int(first_set),
+               int(n_sets), int(kernel), low32.tobytes(), high32.tobytes(), int(seed))
+        plan = self._plans.get(key)
+        if plan is None:
+            p = N.RolloutParams()
+            p.n_candidates, p.n_envs, p.horizon = int(n_candidates), int(m), int(horizon)
+            p.set_mode, p.first_set, p.n_sets = int(set_mode), int(first_set), int(n_sets)
+            p.reward_kind, p.dt, p.kernel = int(reward_kind), float(dt), int(kernel)
+            handle = C.c_void_p()
+            N.check(self.lib.l2a_plan_create(self._ctx, self._model, C.byref(p), float(discount),
+                                             low32.ctypes.data_as(C.c_void_p), high32.ctypes.data_as(C.c_void_p),
+                                             C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.byref(handle)))
+            plan = dict(handle=handle, act=np.empty((m, self.act_dim), np.float64), ret=np.empty(m, np.float32),
+                        idx=np.empty(m, np.int32), shape=(int(horizon), int(n_candidates) * m, self.act_dim))
+            self._plans[key] = plan
+        N.check(self.lib.l2a_plan_run(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p),
+                                      plan["act"].ctypes.data_as(C.c_void_p), plan["ret"].ctypes.data_as(C.c_void_p),
+                                      plan["idx"].ctypes.data_as(C.c_void_p), _stream()))
+        self._last_plan = plan
+        return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy()
+
+    def last_plan_candidates(self):
+        """[H, m*N, A] float32 candidates of the most recent plan_rs_host call (tests / diagnostics)."""
+        plan = self._last_plan
+        out = np.empty(plan["shape"], np.float32)
+        N.check(self.lib.l2a_plan_copy_candidates(self._ctx, plan["handle"], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def last_plan_uses_graph(self):
+        return bool(self.lib.l2a_plan_uses_graph(self._last_plan["handle"]))
 
     # ------------------------------------------------------------------ K4
     def predict_delta(self, obs, act, set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO):

@@ -10,8 +10,9 @@ Candidate sampling
   sampler="numpy" (default): the reference's own draw from the global numpy MT19937 stream
       (``np.random.uniform`` :67-69,114 / ``np.random.normal`` :85), uploaded as fp32 -> identical candidates,
       hence identical chosen actions for a fixed ``np.random.seed`` (parity mode).
-  sampler="device": Philox draws on the GPU (torch.rand / torch.randn) -> no host RNG, no H2D of candidates
-      (throughput mode; env var L2A_B200_SAMPLER=device selects it without touching the run scripts).
+  sampler="device": Philox draws on the GPU -> no host RNG, no H2D of candidates (throughput mode; env var
+      L2A_B200_SAMPLER=device selects it without touching the run scripts).  Random shooting then is ONE host-buffer C call
+      (l2a_plan_run: H2D obs -> sample -> K1 -> D2H action, replayed as a CUDA graph); CEM draws with torch.randn.
 """
 import os
 
@@ -27,7 +28,7 @@ from learning_to_adapt_b200.utils.serializable import Serializable
 class MPCController(Policy, Serializable):
     def __init__(self, name, env, dynamics_model, reward_model=None, discount=1, use_cem=False, n_candidates=1024,
                  horizon=10, num_cem_iters=8, percent_elites=0.1, use_reward_model=False, alpha=0.1, sampler=None,
-                 cem_compat=True, kernel=N.KERNEL_AUTO, parallel=None):
+                 cem_compat=True, kernel=N.KERNEL_AUTO, parallel=None, seed=0):
         self.dynamics_model = dynamics_model
         self.reward_model = reward_model
         self.discount = discount
@@ -44,6 +45,7 @@ class MPCController(Policy, Serializable):
         self.cem_compat = cem_compat
         self.kernel = kernel
         self.parallel = parallel          # optional learning_to_adapt_b200.parallel.CandidateShard
+        self.seed = seed                  # Philox seed of sampler="device"
 
         self.unwrapped_env = env
         while hasattr(self.unwrapped_env, "wrapped_env"):
@@ -92,25 +94,24 @@ class MPCController(Policy, Serializable):
         eng = self.dynamics_model._engine
         act_dim = self.action_space.shape[0]
         set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
+        if self.sampler == "device" and self.parallel is None:
+            acts, ret, idx = eng.plan_rs_host(observations, n, h, self._reward_kind, self._dt, self.action_space.low,
+                                              self.action_space.high, discount=self.discount, set_mode=set_mode,
+                                              first_set=first_set, n_sets=n_sets, kernel=self.kernel, seed=self.seed)
+            self.last_plan = dict(best_ret=ret, best_idx=idx, best_act=acts, returns=None)      # host arrays
+            return acts
         obs_dev = eng._f32(observations)
         if self.parallel is not None:
             return self.parallel.plan_rs(self, observations, obs_dev, set_mode, first_set, n_sets)
-        a_host = None
-        if self.sampler == "numpy":
-            a_host = self.get_random_action(h * n * m).reshape((h, n * m, -1))            # :114
-            a_dev = eng._f32(a_host)
-        else:
-            low = eng._f32(self.action_space.low)
-            high = eng._f32(self.action_space.high)
-            a_dev = torch.rand((h, n * m, act_dim), device=eng.device, dtype=torch.float32) * (high - low) + low
+        # parity mode: the reference's own draw from the global numpy stream, uploaded as float32
+        a_host = self.get_random_action(h * n * m).reshape((h, n * m, -1))                # :114
+        a_dev = eng._f32(a_host)
         res = eng.rollout(obs_dev, a_dev, n, h, self._reward_kind, self._dt, discount=self.discount, set_mode=set_mode,
                           first_set=first_set, n_sets=n_sets, layout="thra", want_returns=False, kernel=self.kernel)
         self.last_plan = res
-        if a_host is not None:
-            best = res["best_idx"].cpu().numpy()
-            cand_a = a_host[0].reshape((m, n, -1))                                        # :118
-            return cand_a[range(m), best]                                                 # :129, float64
-        return res["best_act"].cpu().numpy().astype(np.float64)
+        best = res["best_idx"].cpu().numpy()
+        cand_a = a_host[0].reshape((m, n, -1))                                            # :118
+        return cand_a[range(m), best]                                                     # :129, float64
 
     # ------------------------------------------------------------------ CEM (mpc_controller.py:71-106)
     def get_cem_action(self, observations):

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/c3_tests.log
+timeout 120 python scripts/timeline_probe.py > gpurun_out/c3_timeline.txt 2>&1
+L2A_BENCH_SKIP_CPU=1 timeout 200 python bench.py --steps 30 --warmup 3 > gpurun_out/c3_bench.json 2> gpurun_out/c3_bench.err
+tail -3 gpurun_out/c3_tests.log; cat gpurun_out/c3_bench.json | cut -c1-300

@@ -12,9 +12,10 @@ lib = N.load()
 ctx = C.c_void_p()
 N.check(lib.l2a_ctx_create(0, C.byref(ctx)))
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
-names = {0: "SS (A,B smem)", 1: "TS (A tmem)", 2: "cp only", 3: "cp + TS pipelined"}
+names = {0: "SS (A,B smem)", 1: "TS (A tmem)", 2: "cp only", 3: "cp + TS pipelined", 4: "SS + A keep/reuse",
+         5: "out M128 N32 hints", 6: "out M128 N32 plain", 7: "out M128 N48 hints", 8: "out M128 N48 plain"}
 for nc in (64, 80, 128):
-    for mode in (0, 1, 2, 3):
+    for mode in ((0, 1, 2, 3, 4, 5, 6, 7, 8) if nc == 80 else (0, 1, 4)):
         for _ in range(2):
             N.check(lib.l2a_debug_mma_rate(ctx, nc, mode, 400, C.c_void_p(out.data_ptr()), None))
             torch.cuda.synchronize()

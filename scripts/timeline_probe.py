@@ -27,12 +27,17 @@ t = tl.cpu().numpy()
 t0 = t[0]
 L = len(hidden) + 1
 print("MMA warp (cycles since layer-0 start of step 1):")
-for l in range(L):
+for l in range(L - 1):
     b = 4 * l
     print("  layer %d: enter %7d  first-act-ready %7d  phaseA-done %7d  committed %7d" % (l, t[b] - t0, t[b + 3] - t0, t[b + 1] - t0, t[b + 2] - t0))
+b = 4 * (L - 1)
+print("  output : enter %7d  first-act-ready %7d  committed %7d   | next step's layer 0 enter %7d" % (t[b] - t0, t[b + 3] - t0, t[b + 2] - t0, t[80] - t0))
 print("epilogue warp 0:")
 for l in range(L - 1):
     b = 32 + 4 * l
     print("  layer %d: layer_full seen %7d  mb0 published %7d  all published %7d" % (l, t[b] - t0, t[b + 1] - t0, t[b + 2] - t0))
-print("  output: layer_full %7d  dbuf written %7d  peers ready %7d  env done %7d  x written %7d" % tuple(int(t[i] - t0) for i in (60, 61, 62, 63, 64)))
+print("  output: layer_full %7d  deltas in registers %7d  member mean done %7d  env done %7d  x written %7d" % tuple(int(t[i] - t0) for i in (60, 61, 62, 63, 64)))
 print("  write_x: stores done %7d  fence.proxy.async done %7d" % (int(t[70] - t0), int(t[71] - t0)))
+print("first cluster, per member (SM clocks are per-SM counters; only the differences within a member are comparable):")
+for e in range(nsets):
+    print("  member %d: deltas ready -> member mean done: %7d cycles" % (e, int(t[97 + 2 * e] - t[96 + 2 * e])))

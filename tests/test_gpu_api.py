@@ -281,3 +281,63 @@ def test_c_abi_rejects_bad_arguments():
     assert b"NULL" in lib.l2a_last_error()
     res = eng.rollout(obs, acts, 8, 2, 0, 0.01)                                    # and the valid call still works (SIMT: hidden 100)
     assert int(res["best_idx"][0]) >= 0
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer planning call
+@pytest.mark.parametrize("graph", [True, False])
+def test_host_buffer_plan_call_matches_oracle_on_its_own_candidates(graph, monkeypatch):
+    """l2a_plan_run (HOST obs in, HOST action out; H2D -> Philox sampling -> K1 -> D2H, a CUDA graph from the second call):
+    every call's choice equals the oracle's argmax over the candidates that call drew, replayed or not; candidates are
+    uniform in [low, high) and fresh on every call."""
+    if not graph:
+        monkeypatch.setenv("L2A_NO_GRAPH", "1")
+    prob = O.make_problem("half_cheetah", hidden_sizes=(128, 128), n_sets=3, m=2, seed=21)
+    eng = make_engine(prob)
+    n, h = 150, 6
+    seen = []
+    for call in range(4):
+        obs = prob["obs0"] + 0.01 * call
+        acts, ret, idx = eng.plan_rs_host(obs, n, h, prob["reward_kind"], prob["dt"], prob["low"], prob["high"],
+                                          discount=0.95, set_mode=2, first_set=0, n_sets=3, seed=7)
+        cand = eng.last_plan_candidates()                       # [H, m*N, A] float32
+        assert cand.shape == (h, 2 * n, prob["act_dim"])
+        assert np.all(cand >= prob["low"].astype(np.float32)) and np.all(cand < prob["high"].astype(np.float32))
+        want = O.rollout_returns(obs.astype(np.float32).astype(np.float64), cand.astype(np.float64), prob["param_sets"],
+                                 prob["norm"], prob["reward_kind"], prob["dt"], 0.95, "ensemble")
+        assert_argmax_consistent(idx, want)
+        assert_returns_close(ret, want[range(2), idx])
+        np.testing.assert_array_equal(acts, cand[0].reshape(2, n, -1)[range(2), idx].astype(np.float64))
+        assert acts.dtype == np.float64
+        seen.append(cand)
+        assert eng.last_plan_uses_graph() == (graph and call >= 1)
+    for i in range(1, 4):
+        assert not np.array_equal(seen[i], seen[0])             # the call index advances the Philox counter
+    u = (np.concatenate([s.ravel() for s in seen]) - prob["low"][0]) / (prob["high"][0] - prob["low"][0])
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1.0 / 12.0) < 0.005
+
+
+def test_controller_device_sampler_is_one_host_buffer_call():
+    """MPCController(sampler="device").get_actions routes through l2a_plan_run and stays consistent after the model's
+    weights change (GrBAL adapt writes new sets between calls; the captured graph reads the same device buffers)."""
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    env, model = _models(hidden=(128, 128), mbs=2, lr=1e-2)
+    prob = O.make_problem("half_cheetah", hidden_sizes=(128, 128), n_sets=1, m=2, seed=4)
+    model.set_params(prob["param_sets"][0])
+    model.set_normalization(prob["norm"])
+    ctrl = MPCController("policy", env, model, n_candidates=96, horizon=4, sampler="device", seed=3)
+    eng = model._engine
+    for step in range(3):
+        if step == 1:
+            ctx = O.make_adapt_context(9, prob, 2, 16)
+            model.adapt(*ctx)
+        if step == 2:
+            model.switch_to_pre_adapt()
+        a, info = ctrl.get_actions(prob["obs0"])
+        assert info == {} and a.shape == (2, prob["act_dim"]) and a.dtype == np.float64
+        cand = eng.last_plan_candidates()
+        mode, first, nsets = model.planning_sets(2)
+        sets = [model._engine.get_params(first + k) for k in range(2)] if mode == 1 else [model._engine.get_params(first)]
+        want = O.rollout_returns(prob["obs0"].astype(np.float32).astype(np.float64), cand.astype(np.float64), sets, prob["norm"],
+                                 prob["reward_kind"], prob["dt"], 1.0, "per_env" if mode == 1 else "shared")
+        assert_argmax_consistent(ctrl.last_plan["best_idx"], want)
+        assert_returns_close(ctrl.last_plan["best_ret"], want[range(2), ctrl.last_plan["best_idx"]])
