@@ -241,10 +241,11 @@ int l2a_debug_umma_tile(l2a_ctx* ctx, const float* A, const float* B, float* C, 
                         void* stream);
 
 /* Weight-stream pipeline microbenchmark: every CTA of `grid` streams n_tiles_per_pass tiles of tile_bytes from `blob`
- * `passes` times through a `stages`-deep TMA/mbarrier ring (consumer holds each tile hold_cycles); cycles_out[grid] (device
- * int64) receives the SM cycles each CTA took. */
+ * `passes` times through a `stages`-deep TMA/mbarrier ring (consumer holds each tile hold_cycles; `producers` / `consumers`
+ * = 1 or 2 threads in different warps taking alternate tiles); cycles_out[grid] (device int64) receives the SM cycles each
+ * CTA took. */
 int l2a_debug_stream(l2a_ctx* ctx, const void* blob, int n_tiles_per_pass, int passes, int stages, int tile_bytes,
-                     int hold_cycles, int grid, long long* cycles_out, void* stream);
+                     int hold_cycles, int producers, int consumers, int grid, long long* cycles_out, void* stream);
 
 /* Tensor-pipe rate microbenchmark: SM cycles for `iters` tile pairs (12 split-bf16 MMAs, N = nc) with the A operand from
  * shared memory (mode 0), from tensor memory (1), tcgen05.cp only (2), cp + TS-mode MMA pipelined (3). cycles_out: device int64[1]. */

@@ -91,7 +91,7 @@ def load():
     lib.l2a_debug_mma_rate.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.l2a_shard_pack.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.l2a_shard_select.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
-    lib.l2a_debug_stream.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.l2a_debug_stream.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("l2a_last_error", "l2a_ctx_launch_count"):

@@ -927,15 +927,16 @@ extern "C" int l2a_debug_umma_tile(l2a_ctx* c, const float* A, const float* B, f
 }
 
 extern "C" int l2a_debug_stream(l2a_ctx* c, const void* blob, int n_tiles_per_pass, int passes, int stages, int tile_bytes,
-                                int hold_cycles, int grid, long long* cycles_out, void* stream) {
+                                int hold_cycles, int producers, int consumers, int grid, long long* cycles_out, void* stream) {
   if (!c || !blob || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
   if (stages < 1 || stages > 13 || tile_bytes % 1024 != 0 || grid < 1) return fail(L2A_ERR_INVALID, "bad stages/tile_bytes/grid");
+  if (producers < 1 || producers > 2 || consumers < 1 || consumers > 2) return fail(L2A_ERR_INVALID, "producers/consumers must be 1 or 2");
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t smem = (size_t)stages * tile_bytes + 2 * stages * sizeof(uint64_t) + 1024 + 64;
   if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "needs %zu B shared memory", smem);
   CUDA_TRY(cudaFuncSetAttribute(debug_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  debug_stream_kernel<<<grid, 64, smem, (cudaStream_t)stream>>>((const uint8_t*)blob, n_tiles_per_pass, passes, stages, tile_bytes,
-                                                               hold_cycles, cycles_out);
+  debug_stream_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const uint8_t*)blob, n_tiles_per_pass, passes, stages, tile_bytes,
+                                                                hold_cycles, producers, consumers, cycles_out);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return L2A_OK;

@@ -119,8 +119,9 @@ __global__ void __launch_bounds__(128, 1) debug_umma_tile_kernel(const float* A,
 namespace l2a {
 // Diagnostics: pure weight-stream pipeline (TMA bulk copies of `tile_bytes` through an `stages`-deep mbarrier ring, the
 // consumer only waits and releases, optionally holding each tile for `hold_cycles`).  Reports SM cycles per CTA.
-__global__ void __launch_bounds__(64, 1) debug_stream_kernel(const uint8_t* blob, int n_tiles_per_pass, int passes, int stages,
-                                                             int tile_bytes, int hold_cycles, long long* cycles_out) {
+__global__ void __launch_bounds__(128, 1) debug_stream_kernel(const uint8_t* blob, int n_tiles_per_pass, int passes, int stages,
+                                                              int tile_bytes, int hold_cycles, int producers, int consumers,
+                                                              long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * tile_bytes);
@@ -133,24 +134,35 @@ __global__ void __launch_bounds__(64, 1) debug_stream_kernel(const uint8_t* blob
   }
   __syncthreads();
   const long long t0 = clock64();
-  if (tid == 0) {
-    int stage = 0; uint32_t phase = 0;
-    for (int p = 0; p < passes; ++p)
-      for (int t = 0; t < n_tiles_per_pass; ++t) {
+  const int total = passes * n_tiles_per_pass;
+  // producers: threads 0 and 64 (different warps), consumers: threads 32 and 96; with two of a kind, each takes every other tile
+  if ((tid == 0) || (tid == 64 && producers == 2)) {
+    const int me = tid / 64;
+    int stage = 0, t = 0, turn = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < total; ++i) {
+      if (turn == me) {
         umma::mbar_wait(&empty[stage], phase ^ 1u);
         umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)tile_bytes);
         umma::bulk_g2s(smem + (size_t)stage * tile_bytes, blob + (size_t)t * tile_bytes, (uint32_t)tile_bytes, &full[stage]);
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-  } else if (tid == 32) {
-    int stage = 0; uint32_t phase = 0;
-    for (int p = 0; p < passes; ++p)
-      for (int t = 0; t < n_tiles_per_pass; ++t) {
+      if (++turn == producers) turn = 0;
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+      if (++t == n_tiles_per_pass) t = 0;
+    }
+  } else if ((tid == 32) || (tid == 96 && consumers == 2)) {
+    const int me = tid / 64;
+    int stage = 0, turn = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < total; ++i) {
+      if (turn == me) {
         umma::mbar_wait(&full[stage], phase);
         if (hold_cycles > 0) { const long long h0 = clock64(); while (clock64() - h0 < hold_cycles) {} }
         umma::mbar_arrive(&empty[stage]);
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
+      if (++turn == consumers) turn = 0;
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
   }
   __syncthreads();
   if (tid == 0) cycles_out[blockIdx.x] = clock64() - t0;
@@ -260,10 +272,11 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
       }
       __syncwarp();
     }
+    const long long t_issued = clock64();             // every MMA has been accepted by the tensor pipe's queue
     if (umma::elect_one()) umma::mma_commit(bar);
     __syncwarp();
     umma::mbar_wait(bar, 0);
-    if ((tid & 31) == 0) cycles_out[0] = clock64() - t0;
+    if ((tid & 31) == 0) { cycles_out[0] = clock64() - t0; cycles_out[1] = t_issued - t0; }
   }
   umma::tc_fence_before();
   __syncthreads();

@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       pair_a = (pair_a + 2) % 3;
       umma::tc_fence_before();
       if (warp == 0) L2A_STAMP(61);
-      if (a.timeline && blockIdx.x < 8 && t == 1 && tid == 0) a.timeline[96 + 2 * blockIdx.x] = clock64();       // member skew
+      if (a.timeline && blockIdx.x < 5 && t == 1 && tid == 0) a.timeline[86 + 2 * blockIdx.x] = clock64();       // member skew
       if (ensemble) {
         // Exchange of the E members' deltas through L2: every candidate thread publishes its own row (DMAX floats, 16-byte
         // stores), the cluster meets on the peers' mbarriers (release / acquire at cluster scope), then the thread reads
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         }
       }
       if (warp == 0) L2A_STAMP(62);
-      if (a.timeline && blockIdx.x < 8 && t == 1 && tid == 0) a.timeline[97 + 2 * blockIdx.x] = clock64();
+      if (a.timeline && blockIdx.x < 5 && t == 1 && tid == 0) a.timeline[87 + 2 * blockIdx.x] = clock64();
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;

@@ -11,7 +11,7 @@ from learning_to_adapt_b200 import _native as N  # noqa: E402
 lib = N.load()
 ctx = C.c_void_p()
 N.check(lib.l2a_ctx_create(0, C.byref(ctx)))
-out = torch.zeros(1, dtype=torch.int64, device="cuda")
+out = torch.zeros(2, dtype=torch.int64, device="cuda")
 names = {0: "SS (A,B smem)", 1: "TS (A tmem)", 2: "cp only", 3: "cp + TS pipelined", 4: "SS + A keep/reuse",
          5: "out M128 N32 hints", 6: "out M128 N32 plain", 7: "out M128 N48 hints", 8: "out M128 N48 plain"}
 for nc in (64, 80, 128):
@@ -19,4 +19,9 @@ for nc in (64, 80, 128):
         for _ in range(2):
             N.check(lib.l2a_debug_mma_rate(ctx, nc, mode, 400, C.c_void_p(out.data_ptr()), None))
             torch.cuda.synchronize()
-        print("NC=%3d %-20s %7.1f cycles / tile pair (12 MMAs, ideal %d)" % (nc, names[mode], out.item() / 400.0, 12 * nc // 2))
+        print("NC=%3d %-20s %7.1f cycles / tile pair (12 MMAs, ideal %d)" % (nc, names[mode], out[0].item() / 400.0, 12 * nc // 2))
+# queue depth of the tensor pipe: how far the issuing thread runs ahead of execution for a short burst of MMAs
+for iters in (1, 2, 3, 4, 8):
+    N.check(lib.l2a_debug_mma_rate(ctx, 80, 4, iters, C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    print("NC= 80 SS + hints, %d pair(s) = %2d MMAs: issued after %5d cycles, complete after %5d" % (iters, 12 * iters, out[1].item(), out[0].item()))

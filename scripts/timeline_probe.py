@@ -39,5 +39,5 @@ for l in range(L - 1):
 print("  output: layer_full %7d  deltas in registers %7d  member mean done %7d  env done %7d  x written %7d" % tuple(int(t[i] - t0) for i in (60, 61, 62, 63, 64)))
 print("  write_x: stores done %7d  fence.proxy.async done %7d" % (int(t[70] - t0), int(t[71] - t0)))
 print("first cluster, per member (SM clocks are per-SM counters; only the differences within a member are comparable):")
-for e in range(nsets):
-    print("  member %d: deltas ready -> member mean done: %7d cycles" % (e, int(t[97 + 2 * e] - t[96 + 2 * e])))
+for e in range(min(nsets, 5)):
+    print("  member %d: deltas ready -> member mean done: %7d cycles" % (e, int(t[87 + 2 * e] - t[86 + 2 * e])))
