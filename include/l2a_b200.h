@@ -145,6 +145,12 @@ int l2a_plan_uses_graph(const l2a_plan* plan);   /* 1 once the call sequence has
 /* the candidate tensor the most recent l2a_plan_run drew, [H, m*N, A] float32, to a HOST buffer (tests / diagnostics) */
 int l2a_plan_copy_candidates(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
 
+/* Candidate sampling alone (DEVICE pointers): out[rows, A] = U[low, high) from Philox4x32-10 keyed by seed, counter =
+ * (element block, call_index).  What l2a_plan_run uses internally; the multi-GPU candidate shard calls it with a per-rank seed.
+ * Replaces MPCController.get_random_action (policies/mpc_controller.py:67-69) in throughput mode. */
+int l2a_sample_uniform(l2a_ctx* ctx, const float* low, const float* high, float* out, int64_t rows, int A, uint64_t seed,
+                       uint64_t call_index, void* stream);
+
 /* ---- K4: one dynamics step (API compatibility) --------------------------------------------------------
  * Replaces (Meta)MLPDynamicsModel.predict (mlp_dynamics.py:204-222, meta_mlp_dynamics.py:276-306).
  * obs [n, D], act [n, A] raw (un-normalised).  set_mode SHARED: all rows use first_set; PER_ENV: n must be

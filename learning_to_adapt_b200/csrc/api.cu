@@ -533,6 +533,19 @@ extern "C" int l2a_plan_create(l2a_ctx* c, l2a_model* m, const l2a_rollout_param
   return L2A_OK;
 }
 
+extern "C" int l2a_sample_uniform(l2a_ctx* c, const float* low, const float* high, float* out, int64_t rows, int A, uint64_t seed,
+                                  uint64_t call_index, void* stream) {
+  if (!c || !low || !high || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (rows < 1 || A < 1) return fail(L2A_ERR_INVALID, "rows and A must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const long long total = (long long)rows * A;
+  const long long blocks = (total + 4 * 256 - 1) / (4 * 256);
+  sample_uniform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(low, high, out, total, A, seed, nullptr, call_index);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
+}
+
 // the stream-ordered body of one planning call (captured into the graph, or issued directly)
 static int plan_enqueue(l2a_ctx* c, l2a_plan* pl) {
   const int mm = pl->p.n_envs, A = pl->A, H = pl->p.horizon;
@@ -541,7 +554,7 @@ static int plan_enqueue(l2a_ctx* c, l2a_plan* pl) {
   CUDA_TRY(cudaMemcpyAsync(pl->in_dev, pl->in_host, pl->in_bytes, cudaMemcpyHostToDevice, st));
   const long long blocks = (total + 4 * 256 - 1) / (4 * 256);
   sample_uniform_kernel<<<(unsigned)blocks, 256, 0, st>>>(pl->low, pl->low + A, pl->actions, total, A, pl->seed,
-                                                          reinterpret_cast<const uint32_t*>(pl->in_dev + (size_t)mm * pl->D));
+                                                          reinterpret_cast<const uint32_t*>(pl->in_dev + (size_t)mm * pl->D), 0ull);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   float* best_ret = pl->out_dev;

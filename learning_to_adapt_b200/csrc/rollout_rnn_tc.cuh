@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(kRnnTcThreads, 1) rollout_rnn_tc_kernel(const 
       const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
       if (umma::elect_one()) {
         for (int ks = 0; ks < nks; ++ks) {
-          umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
-          umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+          // W_hi is fetched from shared memory once for its two passes (A-collector keep / reuse, see umma.cuh)
+          umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
+          umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
           umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
         }
         umma::mma_commit(&empty[stage]);
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(kRnnTcThreads, 1) rollout_rnn_tc_kernel(const 
     const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;
     const int fsel = ((lane >> 3) & 1) * 8;
     for (int t = 0; t < H; ++t) {
+      const float disc_t = __ldg(a.discount_pow + t);       // discount**t, fetched a whole step before its use
       // ---------------- LSTM cell: the four gate accumulators of a unit meet in this thread
       umma::mbar_wait(gates_full, gf_phase);
       gf_phase ^= 1u;
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(kRnnTcThreads, 1) rollout_rnn_tc_kernel(const 
             if (k == D - 1) nx2 = s_new;
           }
         }
-        ret = fmaf(__ldg(a.discount_pow + t), reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2), ret);
+        ret = fmaf(disc_t, reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2), ret);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");       // dbuf is rewritten by the next step's output epilogue
       if (t + 1 < H) write_x();

@@ -21,14 +21,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, u
 }
 
 // out[i] = low[i % A] + (high[i % A] - low[i % A]) * u_i, u_i in [0, 1) with 24 random bits; four values per Philox block.
-// call_index: device pointer to the 64-bit planning-call counter (two 32-bit words).
+// call_index: device pointer to the 64-bit planning-call counter (two 32-bit words), or NULL to use call_value.
 __global__ void __launch_bounds__(256) sample_uniform_kernel(const float* __restrict__ low, const float* __restrict__ high,
                                                              float* __restrict__ out, long long total, int A, uint64_t seed,
-                                                             const uint32_t* __restrict__ call_index) {
+                                                             const uint32_t* __restrict__ call_index, uint64_t call_value) {
   const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // Philox block = 4 consecutive elements
   const long long i0 = blk * 4;
   if (i0 >= total) return;
-  uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), call_index[0], call_index[1]};
+  const uint32_t c_lo = call_index ? call_index[0] : (uint32_t)call_value;
+  const uint32_t c_hi = call_index ? call_index[1] : (uint32_t)(call_value >> 32);
+  uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), c_lo, c_hi};
   philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
   float v[4];
 #pragma unroll

@@ -202,6 +202,18 @@ class PlanningEngine(object):
         self._last_plan = plan
         return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy()
 
+    def sample_uniform(self, low, high, rows, seed=0, call_index=0, out=None):
+        """[rows, A] float32 device tensor of U[low, high) draws (Philox4x32-10, this library's kernel)."""
+        key = ("bounds", np.asarray(low, np.float32).tobytes(), np.asarray(high, np.float32).tobytes())
+        if key not in self._discount_cache:
+            self._discount_cache[key] = (self._f32(low), self._f32(high))
+        lo, hi = self._discount_cache[key]
+        if out is None:
+            out = torch.empty((int(rows), self.act_dim), device=self.device, dtype=torch.float32)
+        N.check(self.lib.l2a_sample_uniform(self._ctx, _ptr(lo), _ptr(hi), _ptr(out), int(rows), int(self.act_dim),
+                                            C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_uint64(int(call_index)), _stream()))
+        return out
+
     def last_plan_candidates(self):
         """[H, m*N, A] float32 candidates of the most recent plan_rs_host call (tests / diagnostics)."""
         plan = self._last_plan

@@ -90,8 +90,10 @@ class CandidateShard(object):
             a_full = ctrl.get_random_action(h * n * m).reshape((h, m, n, act_dim))
             a_dev = eng._f32(np.ascontiguousarray(a_full[:, :, lo:hi]).reshape(h, m * n_loc, act_dim))
         else:
-            low, high = eng._f32(ctrl.action_space.low), eng._f32(ctrl.action_space.high)
-            a_dev = torch.rand((h, m * n_loc, act_dim), device=eng.device, dtype=torch.float32) * (high - low) + low
+            self._calls = getattr(self, "_calls", 0) + 1
+            a_dev = eng.sample_uniform(ctrl.action_space.low, ctrl.action_space.high, h * m * n_loc,
+                                       seed=(int(getattr(ctrl, "seed", 0)) << 8) + self.rank, call_index=self._calls)
+            a_dev = a_dev.view(h, m * n_loc, act_dim)
         res = eng.rollout(obs_dev, a_dev, n_loc, h, ctrl._reward_kind, ctrl._dt, discount=ctrl.discount,
                           set_mode=set_mode, first_set=first_set, n_sets=n_sets, layout="thra", want_returns=False,
                           kernel=ctrl.kernel)

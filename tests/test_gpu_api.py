@@ -281,6 +281,16 @@ def test_c_abi_rejects_bad_arguments():
     assert b"NULL" in lib.l2a_last_error()
     res = eng.rollout(obs, acts, 8, 2, 0, 0.01)                                    # and the valid call still works (SIMT: hidden 100)
     assert int(res["best_idx"][0]) >= 0
+    # host-buffer planning call
+    assert lib.l2a_plan_create(eng._ctx, eng._model, None, C.c_float(1.0), None, None, C.c_uint64(0), None) == -1
+    assert lib.l2a_plan_run(eng._ctx, None, None, None, None, None, None) == -1
+    assert lib.l2a_sample_uniform(eng._ctx, None, None, None, 1, 1, C.c_uint64(0), C.c_uint64(0), None) == -1
+    with pytest.raises(RuntimeError, match="must be >= 1"):
+        eng.plan_rs_host(prob["obs0"], 0, 2, 0, 0.01, prob["low"], prob["high"])
+    with pytest.raises(RuntimeError, match="reward_kind"):
+        eng.plan_rs_host(prob["obs0"], 8, 2, 9, 0.01, prob["low"], prob["high"])
+    a, r, i = eng.plan_rs_host(prob["obs0"], 8, 2, 0, 0.01, prob["low"], prob["high"])   # SIMT path behind the same call
+    assert a.shape == (1, 6) and 0 <= int(i[0]) < 8
 
 
 # ------------------------------------------------------------------------------------------------ host-buffer planning call

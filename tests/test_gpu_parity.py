@@ -169,6 +169,54 @@ def test_rollout_matches_oracle(env, hidden, n, h, m, n_sets, mode, kernel):
     np.testing.assert_array_equal(res["best_act"], actions[0].reshape(m, n, -1)[range(m), best].astype(np.float32))
 
 
+# edge shapes: single candidate / single step, exact and just-over tile boundaries, many nearly-empty envs, the largest
+# supported ensemble (cluster of 8), discount 0
+EDGE_CASES = [
+    # hidden, N, H, m, n_sets, mode, discount
+    ((128,), 1, 1, 1, 1, "shared", 1.0),
+    ((128, 128), 80, 3, 1, 1, "shared", 1.0),
+    ((128, 128), 81, 2, 2, 2, "per_env", 0.9),
+    ((128,), 3, 4, 37, 1, "shared", 1.0),
+    ((128,), 40, 2, 1, 8, "ensemble", 1.0),
+    ((256, 256), 33, 5, 1, 1, "shared", 0.0),
+]
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("hidden,n,h,m,n_sets,mode,discount", EDGE_CASES)
+def test_rollout_edge_shapes_match_oracle(hidden, n, h, m, n_sets, mode, discount, kernel):
+    prob = O.make_problem("half_cheetah", hidden_sizes=hidden, n_sets=n_sets, m=m, seed=31)
+    eng = make_engine(prob)
+    actions = O.sample_rs_actions(5, prob["low"], prob["high"], h, n * m)
+    want = O.rollout_returns(prob["obs0"], actions, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"],
+                             discount, mode)
+    res = _rollout(eng, prob, actions, n, h, discount, MODE[mode], 0, n_sets, kernel)
+    assert_returns_close(res["returns"], want)
+    assert_argmax_consistent(res["best_idx"], want)
+    best = res["best_idx"]
+    np.testing.assert_array_equal(res["best_act"], actions[0].reshape(m, n, -1)[range(m), best].astype(np.float32))
+
+
+@pytest.mark.parametrize("reward_kind", [0, 1, 2])
+def test_rollout_maximum_dimensions_of_the_tensor_core_variant(reward_kind):
+    """obs_dim 48 and act_dim 16 (the limits of the tcgen05 variant: state in registers, [obs | act] in one 64-wide chunk),
+    every reward family, an ensemble of 3 -- tcgen05 and SIMT kernels against the oracle."""
+    D, A, hidden, n_sets, m, n, h = 48, 16, (256, 128), 3, 2, 70, 4
+    low, high = -2.0 * np.ones(A), 2.0 * np.ones(A)
+    sets = [O.xavier_params(np.random.RandomState(77 + e), D + A, hidden, D, out_scale=0.1) for e in range(n_sets)]
+    norm = O.make_normalization(np.random.RandomState(78), D, A, low, high)
+    obs0 = norm["obs"][0] + norm["obs"][1] * np.random.RandomState(79).normal(size=(m, D))
+    prob = dict(obs_dim=D, act_dim=A, low=low, high=high, dt=0.02, reward_kind=reward_kind, param_sets=sets, norm=norm,
+                obs0=obs0, hidden_sizes=hidden)
+    eng = make_engine(prob)
+    actions = O.sample_rs_actions(6, low, high, h, n * m)
+    want = O.rollout_returns(obs0, actions, sets, norm, reward_kind, 0.02, 0.99, "ensemble")
+    for kernel in (1, 2):
+        res = _rollout(eng, prob, actions, n, h, 0.99, 2, 0, n_sets, kernel)
+        assert_returns_close(res["returns"], want)
+        assert_argmax_consistent(res["best_idx"], want)
+
+
 def test_rollout_kernels_agree_at_headline_size():
     """BASELINE headline (HC, N=2000, H=20, E=5): the tcgen05 and fp32 SIMT kernels agree within tolerance, and
     rolling the candidates in a permuted order permutes the returns (size-independent properties)."""
