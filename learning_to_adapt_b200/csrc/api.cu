@@ -420,7 +420,6 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   ta.returns = returns;
   ta.red = ra;
   ta.timeline = c->timeline;
-  if (const char* fl = getenv("L2A_TC_FLAGS")) ta.flags = atoi(fl);                  // experiments only (see TcArgs::flags)
   if (csize > 1) {
     const size_t blk = (size_t)nc * (m->dims.obs_dim <= 24 ? 24 : 48);                // floats per member block: [NC][DMAX]
     const size_t need = (size_t)p->n_envs * groups * 2 * csize * blk;

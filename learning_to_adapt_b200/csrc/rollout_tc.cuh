@@ -186,14 +186,12 @@ struct TcArgs {
   float* returns;
   ReduceArgs red;
   float* xch;                   // ensemble exchange scratch in global memory: [clusters][2][E][NC][DMAX] floats (L2-resident)
-  int flags;                    // experiments: bit 0 = no A-collector hints on the split-bf16 passes
   long long* timeline;          // diagnostics: clock64 stamps of CTA 0 at step 1 (null = off)
 };
 
 template <int NC>
 struct TcSmem {
   static constexpr int kChunkBytes = NC * 128;
-  static constexpr int kNCP = NC + 1;
   static constexpr size_t act_bytes = (size_t)2 * kTcMaxChunks * kChunkBytes;
   static constexpr size_t stage_off = act_bytes;
   // ring stage = one (hi, lo) tile pair = 32 KB = the three split-bf16 passes of a [128 x 64] weight block: one bulk copy,
@@ -219,7 +217,6 @@ template <int NC, int DMAX>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs a) {
   using S = TcSmem<NC>;
   constexpr int kChunkBytes = S::kChunkBytes;
-  constexpr int NCP = S::kNCP;
   constexpr int kTcStages = S::kStages;
   constexpr uint32_t kIdesc = umma::make_idesc_bf16(128, NC);
   static_assert(NC % 16 == 0 && NC >= 16 && 6 * NC <= 512, "UMMA N constraint / six accumulator slots must fit the 512 TMEM columns");
@@ -325,7 +322,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)S::kStageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
-      const bool hints = !(a.flags & 1);
       // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block
       auto tile_pair = [&](uint32_t d_tmem, int kc, bool first, bool full_k, int nks_last) {
         const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
@@ -333,11 +329,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         umma::tc_fence_after();
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         if (umma::elect_one()) {
-          if (full_k && hints) {
-            // the W_hi tile is fetched from shared memory once for the two passes that use it (A-collector keep / reuse)
-            umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi, bh, kIdesc, first ? 0u : 1u);    // W_hi * x_hi
-            umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi, bl, kIdesc, 1u);                // W_hi * x_lo
-            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, 1u);                                    // W_lo * x_hi
+          // per 16-wide k-step: W_hi * x_hi, W_hi * x_lo (the W_hi slice is fetched from shared memory once for the two:
+          // A-collector keep / reuse), W_lo * x_hi
+          if (full_k) {
+            umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi, bh, kIdesc, first ? 0u : 1u);
+            umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi, bl, kIdesc, 1u);
+            umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, 1u);
 #pragma unroll
             for (int ks = 1; ks < 4; ++ks) {
               umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, 1u);
@@ -345,10 +342,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
             }
           } else {
-            const int nks = full_k ? 4 : nks_last;
-            for (int ks = 0; ks < nks; ++ks) {
-              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
-              umma::mma_bf16_ss_lo(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+            for (int ks = 0; ks < nks_last; ++ks) {
+              umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
             }
           }
@@ -362,6 +358,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       // can run while layer i's epilogue is still draining a_i / b_i, and b_{i+1} = a_i is drained by the time phase B starts.
       int pair_a = 0;
       const uint32_t idesc_out = umma::make_idesc_bf16(128, (uint32_t)plan.out_n);
+      const uint32_t idesc_out2 = umma::make_idesc_bf16(128, (uint32_t)(2 * plan.out_n));
+      const bool out_stacked = (2 * plan.out_n <= 2 * NC);             // x_hi * [W_hi; W_lo] as ONE N = 2*out_n MMA (see below)
       const uint32_t out_part = (uint32_t)(plan.out_n * 128) >> 4;     // one [out_n x 64] tile in descriptor units
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l + 1 < L; ++l) {
@@ -423,14 +421,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
               if (umma::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                  if (hints) {
-                    umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_out, xh + 2 * ks, wh + 2 * ks, idesc_out, (kc == 0 && ks == 0) ? 0u : 1u);   // x_hi * W_hi
-                    umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_out, xh + 2 * ks, wl + 2 * ks, idesc_out, 1u);                              // x_hi * W_lo
+                  const uint32_t acc0 = (kc == 0 && ks == 0) ? 0u : 1u;
+                  if (out_stacked) {
+                    // the W_hi and W_lo tiles of a chunk are adjacent = one [2*out_n x 64] B operand: columns [0, out_n) of the
+                    // accumulator take x_hi * W_hi (+ x_lo * W_hi below), columns [out_n, 2*out_n) take x_hi * W_lo; the epilogue
+                    // adds the halves.  Two MMAs per k-step instead of three (a small-N MMA costs its 4 KB A read, not N).
+                    umma::mma_bf16_ss_lo(d_out, xh + 2 * ks, wh + 2 * ks, idesc_out2, acc0);
                   } else {
-                    umma::mma_bf16_ss_lo(d_out, xh + 2 * ks, wh + 2 * ks, idesc_out, (kc == 0 && ks == 0) ? 0u : 1u);
-                    umma::mma_bf16_ss_lo(d_out, xh + 2 * ks, wl + 2 * ks, idesc_out, 1u);
+                    umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_out, xh + 2 * ks, wh + 2 * ks, idesc_out, acc0);    // x_hi * W_hi
+                    umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_out, xh + 2 * ks, wl + 2 * ks, idesc_out, 1u);     // x_hi * W_lo
                   }
-                  umma::mma_bf16_ss_lo(d_out, xl + 2 * ks, wh + 2 * ks, idesc_out, 1u);                                                    // x_lo * W_hi
+                  umma::mma_bf16_ss_lo(d_out, xl + 2 * ks, wh + 2 * ks, idesc_out, 1u);                             // x_lo * W_hi
                 }
                 if (last_in_stage) umma::mma_commit(&empty[stage]);
               }
@@ -603,6 +604,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         const uint32_t t_addr = tmem_base + lane_base + (uint32_t)(2 * pair_a * NC);
 #pragma unroll
         for (int g = 0; g < DMAX / 8; ++g) umma::tmem_ld_32x32b_x8(t_addr + (uint32_t)(g * 8), &r[g * 8]);
+        if (2 * plan.out_n <= 2 * NC) {                     // stacked output MMAs: add the x_hi * W_lo half (columns out_n ..)
+          uint32_t r2[DMAX];
+#pragma unroll
+          for (int g = 0; g < DMAX / 8; ++g) umma::tmem_ld_32x32b_x8(t_addr + (uint32_t)(plan.out_n + g * 8), &r2[g * 8]);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < DMAX; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+        }
         umma::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < DMAX / 4; ++q) {
