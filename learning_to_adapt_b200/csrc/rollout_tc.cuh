@@ -12,9 +12,13 @@
 // each product is three MMA passes  W_hi*x_hi + W_hi*x_lo + W_lo*x_hi  accumulated in fp32 (measured return error
 // vs the fp32/fp64 reference: ~5e-6 relative).  A single bf16 pass misses the 1e-4 parity bar.
 //
-// Warp roles (192 threads): warps 0-3 epilogue + "env step" (16x256b TMEM fragments -> bias/ReLU/split -> stmatrix; the
-// candidate's state in registers, reward, normalisation, argmax), warp 4 TMA producer (one lane), warp 5 MMA issuer (the
-// whole warp walks the loops so descriptors stay in uniform registers; an elect.sync lane issues) + TMEM owner.
+// Warp roles (384 threads = three warpgroups): warps 0-3 epilogue + "env step" (16x256b TMEM fragments -> bias/ReLU/split ->
+// stmatrix; the candidate's state in registers, reward, normalisation, argmax), warp 4 TMA producer (one lane), warp 5 MMA
+// issuer (the whole warp walks the loops so descriptors stay in uniform registers; an elect.sync lane issues) + TMEM owner,
+// warps 6-9 epilogue helpers: warp w shares TMEM lane quadrant w % 4 with epilogue warp w % 4 and converts the upper
+// candidate blocks of every hidden-layer M-block (one warp per scheduler cannot hide its own ALU latency: the epilogue of
+// an M-block took 1.35 k cycles, and the output layer, which needs the whole previous epilogue, was bound by it).
+// Registers: launched at 168 per thread; warpgroups 1 and 2 release down to 128 (setmaxnreg.dec: 2 x 128 x 40 registers back to the CTA pool), warpgroup 0 grows to 240 (needs 128 x 72).
 // The OUTPUT layer runs with the roles swapped, D[cand, feat] = X[cand, in] * W[in, feat]: the resident activation chunks
 // are the A operand (M = 128 TMEM lanes = candidates; rows >= NC read whatever follows the chunk and land in unused lanes),
 // the weights are small [out_n x 64] B tiles (out_n = obs dim padded to 16).  The MMA N drops from NC to out_n, the weight
@@ -35,7 +39,7 @@ namespace l2a {
 constexpr int kTcTileBytes = 16384;     // one [128 x 64] bf16 weight tile (hi or lo part)
 constexpr int kTcMaxStages = 4;         // ring depth is per NC: as many 32 KB (hi, lo) pair stages as shared memory allows (2 at NC=80)
 constexpr int kTcMaxChunks = 8;         // activation width <= 512
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 384;         // three warpgroups: 0 = epilogue + env step, 1 = producer / MMA issuer / helpers, 2 = helpers
 constexpr int kTcMaxAct = 16;           // action dim limit of this variant
 constexpr int kTcMaxObs = 48;           // obs dim limit of this variant (candidate state lives in registers)
 
@@ -209,6 +213,8 @@ struct TcSmem {
   }
 };
 
+template <int V> struct IntTag { static constexpr int value = V; };
+
 #define L2A_STAMP(slot) do { if (a.timeline && blockIdx.x == 0 && t == 1 && (threadIdx.x & 31) == 0) a.timeline[(slot)] = clock64(); } while (0)
 
 // DMAX: compile-time bound of the observation dimension (24 or 48): sizes the register-resident candidate state and the
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   uint64_t* act_ready = layer_full + 1;       // [4]: one barrier per readiness event (source M-block) of a layer's input, so the
                                               // MMA issuer can lag several events behind without mbarrier parity aliasing
   uint64_t* peer_ready = layer_full + 5;
+  uint64_t* x_ready = layer_full + 6;         // the layer-0 input of the next step is written (the 128 env-step threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 7);
   float* red_v = reinterpret_cast<float*>(tmem_slot + 2);   // [4]
   int* red_i = reinterpret_cast<int*>(red_v + 4);           // [4]
@@ -270,7 +277,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
     umma::mbar_init(layer_full, 1);
-    for (int j = 0; j < 4; ++j) umma::mbar_init(&act_ready[j], 128);
+    for (int j = 0; j < 4; ++j) umma::mbar_init(&act_ready[j], 256);   // epilogue warps + helper warps
+    umma::mbar_init(x_ready, 128);
     umma::mbar_init(peer_ready, csize);
     umma::fence_barrier_init();
   }
@@ -293,8 +301,78 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  // Hidden-layer epilogue of one layer for the candidate blocks [CB0, CB1) (16 candidates each) of this warp's TMEM lane
+  // quadrant wq: accumulator fragments (16x256b TMEM loads: thread T holds features T/4, T/4+8 x candidate pairs) -> bias +
+  // ReLU -> bf16 hi/lo split -> the next layer's K-major B operand with transposed 8x8 stmatrix stores (16-byte rows of 8
+  // features per candidate), in place; one readiness event per M-block (chunks 2mb, 2mb+1 of the next layer's input).
+  constexpr int kCbAll = NC / 16, kCbMain = (kCbAll + 1) / 2;          // the epilogue warps take the lower blocks, the helpers the rest
+  auto hidden_epilogue = [&](auto cb0_tag, auto cb1_tag, int t, int l, int pair_a, int wq, bool stamps) {
+    constexpr int CB0 = decltype(cb0_tag)::value, CB1 = decltype(cb1_tag)::value;
+    const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
+    const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;          // stmatrix row owned by this lane (within 16 candidates)
+    const int fsel = ((lane >> 3) & 1) * 8;                         // ... of the feature-group matrix 0 / +8
+    for (int mb = 0; mb < plan.nmb[l]; ++mb) {
+      const int slot = (mb < 2) ? (2 * pair_a + mb) : (2 * ((pair_a + 1) % 3) + (mb - 2));
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int fbase = mb * 128 + wq * 32 + half * 16;           // 16 features handled by this (warp, half)
+        const float bias_a = __ldg(P + md.b_off[l] + fbase + (lane >> 2));
+        const float bias_b = __ldg(P + md.b_off[l] + fbase + (lane >> 2) + 8);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32 + half * 16) << 16) + (uint32_t)(slot * NC);
+        const uint32_t chunk_off = (uint32_t)(fbase >> 6) * kChunkBytes;
+        const uint32_t fcol = (uint32_t)((fbase & 63) + fsel) >> 3;  // 16-byte column of this lane's matrix rows
+        uint32_t r[CB1 - CB0][8];
+#pragma unroll
+        for (int cb = CB0; cb < CB1; ++cb) umma::tmem_ld_16x256b_x2(t_addr + (uint32_t)(cb * 16), r[cb - CB0]);
+        umma::tmem_ld_wait();                                        // one wait for the whole block
+#pragma unroll
+        for (int cb = CB0; cb < CB1; ++cb) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float b = (q & 1) ? bias_b : bias_a;
+            const float v0 = fmaxf(__uint_as_float(r[cb - CB0][2 * q]) + b, 0.f);      // core/utils.py:119-126 (ReLU dense)
+            const float v1 = fmaxf(__uint_as_float(r[cb - CB0][2 * q + 1]) + b, 0.f);
+            umma::split_bf16x2(v0, v1, hi[q], lo[q]);
+          }
+          const uint32_t cand = (uint32_t)(cb * 16 + cand_l);
+          const uint32_t off = chunk_off + cand * 128u + (((fcol ^ cand) & 7u) << 4);
+          umma::stmatrix_x4_trans(act_hi_addr + off, hi[0], hi[1], hi[2], hi[3]);
+          umma::stmatrix_x4_trans(act_lo_addr + off, lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_before();
+      umma::mbar_arrive(&act_ready[mb]);
+      if (stamps && mb == 0) L2A_STAMP(32 + 4 * l + 1);
+    }
+  };
+
+  // Register re-partitioning between the warpgroups (see the header): the env-step warps need ~240, everything else < 128.
+  // Each setmaxnreg sits at the top of its role's branch so that ptxas allocates the branch with that budget.
+  if (warp >= 6) {
+    // ================================================================ epilogue helpers (warps 6-9; 10, 11 idle)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    if (warp < 10 && kCbMain < kCbAll) {
+      const int wq = warp & 3;
+      uint32_t lf_phase = 0;
+      int pair_a = 0;
+      for (int t = 0; t < H; ++t) {
+        for (int l = 0; l + 1 < L; ++l) {
+          umma::mbar_wait(layer_full, lf_phase);
+          lf_phase ^= 1u;
+          umma::tc_fence_after();
+          hidden_epilogue(IntTag<kCbMain>{}, IntTag<kCbAll>{}, t, l, pair_a, wq, false);
+          pair_a = (pair_a + 2) % 3;
+        }
+        umma::mbar_wait(layer_full, lf_phase);                       // the output layer's completion: keeps the phase in step
+        lf_phase ^= 1u;
+        pair_a = (pair_a + 2) % 3;
+      }
+    }
+  } else if (warp == 4) {
     // ================================================================ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -313,12 +391,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     }
     __syncwarp();
   } else if (warp == 5) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
     // ================================================================ MMA issuer
     // The WHOLE warp walks the loops (so every descriptor is computed warp-uniformly and lands in uniform registers);
     // only the elected lane issues tcgen05.mma / tcgen05.commit.
     {
       int stage = 0;
-      uint32_t phase = 0, act_phase = 0;
+      uint32_t phase = 0, act_phase = 0, xr_phase = 0;
       const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)S::kStageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
@@ -372,8 +451,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64();   // step length
           // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
           for (int ev = 0; ev < nsrc; ++ev) {
-            umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
-            act_phase ^= (1u << ev);
+            if (l == 0) {
+              umma::mbar_wait(x_ready, xr_phase);
+              xr_phase ^= 1u;
+            } else {
+              umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
+              act_phase ^= (1u << ev);
+            }
             umma::tc_fence_after();
             if (ev == 0) L2A_STAMP(4 * l + 3);
             const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * cpe);
@@ -453,6 +537,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     }
   } else {
     // ================================================================ epilogue + env step (warps 0-3, 128 threads)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int n = tid;                                  // candidate owned in the env phase
     const bool has_cand = n < NC;
     const bool valid = n < nvalid;
@@ -532,7 +617,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       umma::fence_proxy_async_smem();
       if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[71] = clock64();
       umma::tc_fence_before();
-      umma::mbar_arrive(&act_ready[0]);
+      umma::mbar_arrive(x_ready);
     };
 
     load_actions(0);
@@ -546,49 +631,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         lf_phase ^= 1u;
         umma::tc_fence_after();
         if (warp == 0) L2A_STAMP(32 + 4 * l + 0);
-        // Accumulator fragments (16x256b TMEM loads: thread T holds features T/4, T/4+8 x candidate pairs) are turned into
-        // the next layer's K-major B operand with transposed 8x8 stmatrix stores: 16-byte rows of 8 features per candidate.
-        {
-          const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
-          const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;          // stmatrix row owned by this lane (within 16 candidates)
-          const int fsel = ((lane >> 3) & 1) * 8;                         // ... of the feature-group matrix 0 / +8
-          for (int mb = 0; mb < plan.nmb[l]; ++mb) {
-            const int slot = (mb < 2) ? (2 * pair_a + mb) : (2 * ((pair_a + 1) % 3) + (mb - 2));
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int fbase = mb * 128 + warp * 32 + half * 16;         // 16 features handled by this (warp, half)
-              const float bias_a = __ldg(P + md.b_off[l] + fbase + (lane >> 2));
-              const float bias_b = __ldg(P + md.b_off[l] + fbase + (lane >> 2) + 8);
-              const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32 + half * 16) << 16) + (uint32_t)(slot * NC);
-              const uint32_t chunk_off = (uint32_t)(fbase >> 6) * kChunkBytes;
-              const uint32_t fcol = (uint32_t)((fbase & 63) + fsel) >> 3;  // 16-byte column of this lane's matrix rows
-              uint32_t r[NC / 16][8];
-#pragma unroll
-              for (int cb = 0; cb < NC / 16; ++cb) umma::tmem_ld_16x256b_x2(t_addr + (uint32_t)(cb * 16), r[cb]);
-              umma::tmem_ld_wait();                                        // one wait for the whole 16 x NC block
-#pragma unroll
-              for (int cb = 0; cb < NC / 16; ++cb) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float b = (q & 1) ? bias_b : bias_a;
-                  const float v0 = fmaxf(__uint_as_float(r[cb][2 * q]) + b, 0.f);      // core/utils.py:119-126 (ReLU dense)
-                  const float v1 = fmaxf(__uint_as_float(r[cb][2 * q + 1]) + b, 0.f);
-                  umma::split_bf16x2(v0, v1, hi[q], lo[q]);
-                }
-                const uint32_t cand = (uint32_t)(cb * 16 + cand_l);
-                const uint32_t off = chunk_off + cand * 128u + (((fcol ^ cand) & 7u) << 4);
-                umma::stmatrix_x4_trans(act_hi_addr + off, hi[0], hi[1], hi[2], hi[3]);
-                umma::stmatrix_x4_trans(act_lo_addr + off, lo[0], lo[1], lo[2], lo[3]);
-              }
-            }
-            // chunks 2mb, 2mb+1 of the next layer's input are complete: publish them (one readiness event per M-block)
-            umma::fence_proxy_async_smem();
-            umma::tc_fence_before();
-            umma::mbar_arrive(&act_ready[mb]);
-            if (warp == 0 && mb == 0) L2A_STAMP(32 + 4 * l + 1);
-          }
-        }
+        hidden_epilogue(IntTag<0>{}, IntTag<kCbMain>{}, t, l, pair_a, warp, warp == 0);
         if (warp == 0) L2A_STAMP(32 + 4 * l + 2);
         pair_a = (pair_a + 2) % 3;
       }

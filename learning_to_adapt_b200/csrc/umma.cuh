@@ -40,11 +40,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef L2A_WATCHDOG_CYCLES
 #define L2A_WATCHDOG_CYCLES 4000000000ll
 #endif
+// (No printf by default: a call to a shared non-inlined function from warp-specialised branches makes ptxas allocate every
+// branch with the smallest setmaxnreg budget of the kernel.  -DL2A_WATCHDOG_PRINTF restores the message for debugging.)
+#ifdef L2A_WATCHDOG_PRINTF
 __device__ __noinline__ void watchdog_fail(uint32_t bar_addr, uint32_t parity) {
   printf("l2a_b200 watchdog: mbarrier 0x%x parity %u never completed (block %d thread %d)\n", bar_addr, parity,
          (int)blockIdx.x, (int)threadIdx.x);
   __trap();
 }
+#else
+__device__ __forceinline__ void watchdog_fail(uint32_t, uint32_t) { __trap(); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
