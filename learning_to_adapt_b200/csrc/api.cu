@@ -421,7 +421,8 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   ta.red = ra;
   ta.timeline = c->timeline;
   if (csize > 1) {
-    const size_t blk = (size_t)nc * (m->dims.obs_dim <= 24 ? 24 : 48);                // floats per member block: [NC][DMAX]
+    const bool small = m->dims.obs_dim <= 24 && m->dims.act_dim <= 8;
+    const size_t blk = (size_t)nc * (small ? 24 : 48);                                // floats per member block: [NC][DMAX]
     const size_t need = (size_t)p->n_envs * groups * 2 * csize * blk;
     if (need > c->xch_cap) {
       cudaFree(c->xch);
@@ -433,7 +434,7 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
     }
     ta.xch = c->xch;
   }
-  if (m->dims.obs_dim <= 24) {
+  if (m->dims.obs_dim <= 24 && m->dims.act_dim <= 8) {
     switch (nc) {
       case 80: return launch_tc<80, 24>(c, ta, csize, st);
       case 64: return launch_tc<64, 24>(c, ta, csize, st);

@@ -217,7 +217,7 @@ template <int V> struct IntTag { static constexpr int value = V; };
 
 #define L2A_STAMP(slot) do { if (a.timeline && blockIdx.x == 0 && t == 1 && (threadIdx.x & 31) == 0) a.timeline[(slot)] = clock64(); } while (0)
 
-// DMAX: compile-time bound of the observation dimension (24 or 48): sizes the register-resident candidate state and the
+// DMAX: compile-time bound of the observation dimension (24 with act_dim <= 8, or 48): sizes the register-resident candidate state and the
 // unrolled env-step code (a 48-wide instance costs HalfCheetah's D = 20 twice the instruction-cache footprint).
 template <int NC, int DMAX>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs a) {
@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     uint32_t lf_phase = 0, pr_phase = 0;
     int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
-    float a_cur[kTcMaxAct];
+    constexpr int AMAX = (DMAX <= 24) ? 8 : kTcMaxAct;    // the small instance serves act_dim <= 8 (see launch dispatch)
+    float a_cur[AMAX];
     float st[DMAX];                                      // this candidate's state, float32, in registers for the whole rollout
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) st[k] = (k < D) ? __ldg(a.obs0 + (size_t)env * D + k) : 0.f;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     auto load_actions = [&](int t) {
       const float* src = a.actions + (long long)t * a.act_stride_t + row * a.act_stride_row;
 #pragma unroll
-      for (int j = 0; j < kTcMaxAct; ++j) a_cur[j] = (j < A && valid && has_cand) ? __ldg(src + j) : 0.f;
+      for (int j = 0; j < AMAX; ++j) a_cur[j] = (j < A && valid && has_cand) ? __ldg(src + j) : 0.f;
     };
     // normalised network input of the candidate for the step whose actions are in a_cur: features [state | action | 0]
     int t_stamp = -1;
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       if (has_cand) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < kTcMaxAct; ++j) s = fmaf(a_cur[j], a_cur[j], s);
+        for (int j = 0; j < AMAX; ++j) s = fmaf(a_cur[j], a_cur[j], s);
         asq = s;
         // layer-0 input layout: [obs | pad8 | act | pad]  (tc_in0_of_col); groups of 8 features = one 16-byte store
         auto store_group = [&](int g, const float (&v)[8]) {
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           }
         }
 #pragma unroll
-        for (int ga = 0; ga < kTcMaxAct / 8; ++ga) {
+        for (int ga = 0; ga < AMAX / 8; ++ga) {
           if (ga * 8 < A) {
             float mu[8], rd[8], v[8];
             *reinterpret_cast<float4*>(&mu[0]) = *reinterpret_cast<const float4*>(n_act_mean + ga * 8);
@@ -691,40 +692,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             if (q < dq) mine[q * NC] = make_float4(dl[4 * q], dl[4 * q + 1], dl[4 * q + 2], dl[4 * q + 3]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0) L2A_STAMP(65);
         if (tid < csize) umma::mbar_arrive_remote(umma::map_to_cta(umma::smem_u32(peer_ready), (uint32_t)tid));
+        if (warp == 0) L2A_STAMP(66);
         umma::mbar_wait_cluster(peer_ready, pr_phase);
         pr_phase ^= 1u;
+        if (warp == 0) L2A_STAMP(67);
         if (has_cand) {
           const float inv_e = 1.0f / (float)csize;
           const float4* rows = blk0 + n;
-          constexpr int QB = (DMAX <= 24) ? 3 : 2;           // units per member fetched in one batch (all loads in flight)
-          static_assert(DQ % QB == 0, "row batches");
+          // All rows of one batch are in flight together; a batch is bounded by the register budget (EM members x QB units x 4).
+          // Up to five members (BASELINE's ensemble) and a small obs dim: the whole exchange is ONE batch = one L2 round trip.
+          auto mean_rows = [&](auto em_tag, auto qb_tag) {
+            constexpr int EM = decltype(em_tag)::value, QB = decltype(qb_tag)::value;
 #pragma unroll
-          for (int qb = 0; qb < DQ; qb += QB) {
-            if (qb < dq) {
-              float4 v[8][QB];
+            for (int qb = 0; qb < DQ; qb += QB) {
+              if (qb < dq) {
+                float4 v[EM][QB];
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < EM; ++e)
 #pragma unroll
-                for (int q = 0; q < QB; ++q)
-                  if (e < csize && e != crank && qb + q < dq) v[e][q] = __ldcg(rows + (size_t)e * (NC * DQ) + (qb + q) * NC);
+                  for (int q = 0; q < QB; ++q)
+                    if (qb + q < DQ && e < csize && e != crank && qb + q < dq) v[e][q] = __ldcg(rows + (size_t)e * (NC * DQ) + (qb + q) * NC);
 #pragma unroll
-              for (int q = 0; q < QB; ++q) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int k0 = 4 * (qb + q);
+                for (int q = 0; q < QB; ++q) {
+                  if (qb + q >= DQ) continue;
+                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                  const int k0 = 4 * (qb + q);
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (e < csize) {
-                    const bool own = (e == crank);
-                    acc.x += own ? dl[k0] : v[e][q].x;
-                    acc.y += own ? dl[k0 + 1] : v[e][q].y;
-                    acc.z += own ? dl[k0 + 2] : v[e][q].z;
-                    acc.w += own ? dl[k0 + 3] : v[e][q].w;
-                  }
-                if (qb + q < dq) { dl[k0] = acc.x * inv_e; dl[k0 + 1] = acc.y * inv_e; dl[k0 + 2] = acc.z * inv_e; dl[k0 + 3] = acc.w * inv_e; }
+                  for (int e = 0; e < EM; ++e)
+                    if (e < csize) {
+                      const bool own = (e == crank);
+                      acc.x += own ? dl[k0] : v[e][q].x;
+                      acc.y += own ? dl[k0 + 1] : v[e][q].y;
+                      acc.z += own ? dl[k0 + 2] : v[e][q].z;
+                      acc.w += own ? dl[k0 + 3] : v[e][q].w;
+                    }
+                  if (qb + q < dq) { dl[k0] = acc.x * inv_e; dl[k0 + 1] = acc.y * inv_e; dl[k0 + 2] = acc.z * inv_e; dl[k0 + 3] = acc.w * inv_e; }
+                }
               }
             }
-          }
+          };
+          if (csize <= 5) mean_rows(IntTag<5>{}, IntTag<(DMAX <= 24) ? 5 : 2>{});
+          else mean_rows(IntTag<8>{}, IntTag<1>{});          // 6-8 members: one unit per batch (register budget)
         }
       }
       if (warp == 0) L2A_STAMP(62);

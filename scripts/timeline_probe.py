@@ -37,6 +37,7 @@ for l in range(L - 1):
     b = 32 + 4 * l
     print("  layer %d: layer_full seen %7d  mb0 published %7d  all published %7d" % (l, t[b] - t0, t[b + 1] - t0, t[b + 2] - t0))
 print("  output: layer_full %7d  deltas in registers %7d  member mean done %7d  env done %7d  x written %7d" % tuple(int(t[i] - t0) for i in (60, 61, 62, 63, 64)))
+print("  exchange: rows stored + CTA barrier %7d  release-arrive on the peers issued %7d  all members arrived %7d" % tuple(int(t[i] - t0) for i in (65, 66, 67)))
 print("  write_x: stores done %7d  fence.proxy.async done %7d" % (int(t[70] - t0), int(t[71] - t0)))
 print("first cluster, per member (SM clocks are per-SM counters; only the differences within a member are comparable):")
 for e in range(min(nsets, 5)):
