@@ -43,11 +43,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("L2A_B200_LIB", LIB_PATH)      # development: A/B two builds on the same box
+    if not os.path.exists(path):
         raise ImportError(
             "learning_to_adapt_b200: %s is missing. Build it with `python -m learning_to_adapt_b200.build` "
             "(nvcc, sm_100a). There is no CPU fallback for the planning path." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     pp = C.POINTER(vp)
     lib.l2a_last_error.restype = C.c_char_p

@@ -18,7 +18,8 @@
 // warps 6-9 epilogue helpers: warp w shares TMEM lane quadrant w % 4 with epilogue warp w % 4 and converts the upper
 // candidate blocks of every hidden-layer M-block (one warp per scheduler cannot hide its own ALU latency: the epilogue of
 // an M-block took 1.35 k cycles, and the output layer, which needs the whole previous epilogue, was bound by it).
-// Registers: launched at 168 per thread; warpgroups 1 and 2 release down to 128 (setmaxnreg.dec: 2 x 128 x 40 registers back to the CTA pool), warpgroup 0 grows to 240 (needs 128 x 72).
+// Registers: launched at 168 per thread; warpgroups 1 and 2 release down to 128 (setmaxnreg.dec: 2 x 128 x 40 registers back
+// to the CTA pool), warpgroup 0 grows to 240 (needs 128 x 72).
 // The OUTPUT layer runs with the roles swapped, D[cand, feat] = X[cand, in] * W[in, feat]: the resident activation chunks
 // are the A operand (M = 128 TMEM lanes = candidates; rows >= NC read whatever follows the chunk and land in unused lanes),
 // the weights are small [out_n x 64] B tiles (out_n = obs dim padded to 16).  The MMA N drops from NC to out_n, the weight
