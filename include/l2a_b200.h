@@ -240,6 +240,12 @@ int l2a_shard_pack(l2a_ctx* ctx, const float* best_ret, const int32_t* best_idx,
 int l2a_shard_select(l2a_ctx* ctx, const float* gathered, int G, int m, int A, float* best_ret, int64_t* best_idx,
                      float* best_act, void* stream);
 
+/* Host-only (no device needed): the tensor-core tiling a model of this shape gets.  out8[0] = 1 if the tcgen05 rollout supports
+ * the shape (hidden widths multiples of 128 and <= 512, obs_dim <= 48, act_dim <= 16, pad8(obs_dim) + act_dim <= 64), then
+ * hidden_pairs (32 KB ring stages of the hidden layers), out_n (MMA N of the output layer), out_kcs (K chunks per output
+ * stage), out_stages, stages_per_set, set_bytes (low and high 32 bits).  Used by the CPU-side tests of the host logic. */
+int l2a_tc_plan_query(const l2a_mlp_desc* desc, int32_t* out8);
+
 /* ---- diagnostics -----------------------------------------------------------------------------------------
  * Single tcgen05 GEMM tile through the same descriptor / TMEM code as the rollout kernel:
  * C[128, n] = A[128, k] * B[n, k]^T with A, B fp32 split into bf16 hi/lo on the device. */

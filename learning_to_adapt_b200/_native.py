@@ -19,7 +19,7 @@ EXPORTS = [
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window",
-    "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_sample_uniform",
+    "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_sample_uniform", "l2a_tc_plan_query",
 ]
 
 
@@ -69,6 +69,7 @@ def load():
     lib.l2a_plan_destroy.argtypes = [vp, vp]
     lib.l2a_plan_uses_graph.argtypes = [vp]
     lib.l2a_plan_copy_candidates.argtypes = [vp, vp, vp]
+    lib.l2a_tc_plan_query.argtypes = [C.POINTER(MlpDesc), vp]
     lib.l2a_sample_uniform.argtypes = [vp, vp, vp, vp, i64, i32, C.c_uint64, C.c_uint64, vp]
     lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
     lib.l2a_adapt.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]

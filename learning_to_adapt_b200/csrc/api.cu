@@ -123,25 +123,15 @@ extern "C" int l2a_ctx_destroy(l2a_ctx* c) {
 
 extern "C" int64_t l2a_ctx_launch_count(const l2a_ctx* c) { return c ? c->launches : 0; }
 
-// --------------------------------------------------------------------------------------------- model
-extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** out) {
-  if (!c || !d || !out) return fail(L2A_ERR_INVALID, "NULL argument");
-  if (d->n_hidden < 1 || d->n_hidden > kMaxLayers - 1) return fail(L2A_ERR_INVALID, "n_hidden %d not in [1,%d]", d->n_hidden, kMaxLayers - 1);
-  if (d->obs_dim < 3 || d->act_dim < 1 || d->n_sets < 1) return fail(L2A_ERR_INVALID, "bad obs_dim/act_dim/n_sets");
-  CUDA_TRY(cudaSetDevice(c->device));
-  l2a_model* m = new (std::nothrow) l2a_model();
-  if (!m) return fail(L2A_ERR_INVALID, "out of host memory");
-  m->desc = *d;
-  MlpDims& md = m->dims;
+// dense-stack geometry + fp32 storage offsets of one weight set from the C descriptor (host only)
+static void fill_dims(const l2a_mlp_desc* d, MlpDims* out) {
+  MlpDims& md = *out;
   memset(&md, 0, sizeof(md));
   md.n_layers = d->n_hidden + 1;
   md.obs_dim = d->obs_dim;
   md.act_dim = d->act_dim;
   md.dims[0] = d->obs_dim + d->act_dim;
-  for (int i = 0; i < d->n_hidden; ++i) {
-    if (d->hidden[i] < 1) { delete m; return fail(L2A_ERR_INVALID, "hidden[%d] = %d", i, d->hidden[i]); }
-    md.dims[i + 1] = d->hidden[i];
-  }
+  for (int i = 0; i < d->n_hidden; ++i) md.dims[i + 1] = d->hidden[i];
   md.dims[md.n_layers] = d->obs_dim;
   int off = 0, maxw = 0;
   for (int l = 0; l < md.n_layers; ++l) {
@@ -154,6 +144,43 @@ extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** o
   for (int l = 0; l <= md.n_layers; ++l) maxw = std::max(maxw, md.dims[l]);
   md.set_stride = off;
   md.max_width = maxw;
+}
+
+// Host-only query of the tensor-core tiling a model of this shape would get (no device needed): out[0] = 1 if the tcgen05
+// rollout supports the shape, then hidden_pairs, out_n, out_kcs, out_stages, stages_per_set, set_bytes (low, high 32 bits).
+extern "C" int l2a_tc_plan_query(const l2a_mlp_desc* d, int32_t* out8) {
+  if (!d || !out8) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (d->n_hidden < 1 || d->n_hidden > kMaxLayers - 1) return fail(L2A_ERR_INVALID, "n_hidden %d not in [1,%d]", d->n_hidden, kMaxLayers - 1);
+  for (int i = 0; i < d->n_hidden; ++i)
+    if (d->hidden[i] < 1) return fail(L2A_ERR_INVALID, "hidden[%d] = %d", i, d->hidden[i]);
+  if (d->obs_dim < 3 || d->act_dim < 1) return fail(L2A_ERR_INVALID, "bad obs_dim/act_dim");
+  MlpDims md;
+  fill_dims(d, &md);
+  TcPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  const bool ok = tc_make_plan(md, &plan);
+  memset(out8, 0, 8 * sizeof(int32_t));
+  out8[0] = ok ? 1 : 0;
+  if (ok) {
+    out8[1] = plan.hidden_pairs; out8[2] = plan.out_n; out8[3] = plan.out_kcs; out8[4] = plan.out_stages;
+    out8[5] = plan.stages_per_set; out8[6] = (int32_t)(plan.set_bytes & 0xFFFFFFFFll); out8[7] = (int32_t)(plan.set_bytes >> 32);
+  }
+  return L2A_OK;
+}
+
+// --------------------------------------------------------------------------------------------- model
+extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** out) {
+  if (!c || !d || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (d->n_hidden < 1 || d->n_hidden > kMaxLayers - 1) return fail(L2A_ERR_INVALID, "n_hidden %d not in [1,%d]", d->n_hidden, kMaxLayers - 1);
+  if (d->obs_dim < 3 || d->act_dim < 1 || d->n_sets < 1) return fail(L2A_ERR_INVALID, "bad obs_dim/act_dim/n_sets");
+  for (int i = 0; i < d->n_hidden; ++i)
+    if (d->hidden[i] < 1) return fail(L2A_ERR_INVALID, "hidden[%d] = %d", i, d->hidden[i]);
+  CUDA_TRY(cudaSetDevice(c->device));
+  l2a_model* m = new (std::nothrow) l2a_model();
+  if (!m) return fail(L2A_ERR_INVALID, "out of host memory");
+  m->desc = *d;
+  MlpDims& md = m->dims;
+  fill_dims(d, &md);
   m->tc_ok = tc_make_plan(md, &m->plan);
   const size_t pbytes = (size_t)d->n_sets * md.set_stride * sizeof(float);
   if (cudaMalloc(&m->params, pbytes) != cudaSuccess) { delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(params, %zu)", pbytes); }

@@ -418,3 +418,44 @@ def rnn_rs_plan(observations, actions, hidden, params, norm, reward_kind, dt, di
     chosen = cand_a[range(m), best]
     _, new_hidden = rnn_predict(np.asarray(observations, np.float64), chosen, hidden, params, norm)
     return chosen, best, returns, new_hidden
+
+
+# --------------------------------------------------------------------------------------------------
+# device candidate sampler (throughput mode of get_random_action): Philox4x32-10 restated in numpy
+# --------------------------------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) on arrays of
+    counters [n, 4] uint32 with one key (k0, k1).  Returns [n, 4] uint32.  This is the published algorithm the CUDA kernel
+    learning_to_adapt_b200/csrc/sample.cuh implements; the reference itself draws with numpy's MT19937
+    (policies/mpc_controller.py:67-69), which the parity mode of the controller keeps."""
+    c = np.array(counter, dtype=np.uint64).reshape(-1, 4)
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    w0, w1 = np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+    mask = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = c[:, 0].copy(), c[:, 1].copy(), c[:, 2].copy(), c[:, 3].copy()
+    for _ in range(10):
+        p0, p1 = m0 * c0, m1 * c2                       # 32 x 32 -> 64 bit products
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & mask, lo1, (hi0 ^ c3 ^ k1) & mask, lo0
+        k0, k1 = (k0 + w0) & mask, (k1 + w1) & mask
+    return np.stack([c0, c1, c2, c3], axis=1).astype(np.uint32)
+
+
+def sample_rs_actions_device(seed, call_index, low, high, horizon, rows):
+    """The candidate tensor [H, rows, A] float32 that l2a_plan_run / l2a_sample_uniform draw for (seed, call_index):
+    element block b (4 consecutive elements of the flattened tensor) = Philox(counter = (b_lo, b_hi, call_lo, call_hi),
+    key = (seed_lo, seed_hi)); u = (word >> 8) * 2^-24 in [0, 1); value = fma(high - low, u, low) in float32."""
+    low32, high32 = np.asarray(low, np.float32), np.asarray(high, np.float32)
+    A = low32.shape[0]
+    total = horizon * rows * A
+    nblk = (total + 3) // 4
+    blk = np.arange(nblk, dtype=np.uint64)
+    ctr = np.stack([blk & np.uint64(0xFFFFFFFF), blk >> np.uint64(32),
+                    np.full(nblk, call_index & 0xFFFFFFFF, np.uint64), np.full(nblk, (call_index >> 32) & 0xFFFFFFFF, np.uint64)], axis=1)
+    words = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(-1)[:total]
+    u = (words >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
+    j = np.arange(total) % A
+    span = (high32 - low32).astype(np.float32)           # the kernel forms hi - lo in float32
+    val = span[j].astype(np.float64) * u + low32[j].astype(np.float64)   # exact product (24 x 24 bits), one rounding below = fma
+    return val.astype(np.float32).reshape(horizon, rows, A)

@@ -56,3 +56,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(root, f)
+
+
+def _plan(obs_dim, act_dim, hidden):
+    from learning_to_adapt_b200 import _native
+    lib = _native.load()
+    d = _native.MlpDesc()
+    d.obs_dim, d.act_dim, d.n_hidden, d.n_sets = obs_dim, act_dim, len(hidden), 1
+    for i, h in enumerate(hidden):
+        d.hidden[i] = h
+    out = (ctypes.c_int32 * 8)()
+    status = lib.l2a_tc_plan_query(ctypes.byref(d), out)
+    return status, list(out)
+
+
+def test_tensor_core_tiling_of_the_baseline_shapes():
+    """Host logic of the weight-tile plan (no GPU): ring stages per weight set, output-layer tile geometry, and which shapes
+    have a tcgen05 variant at all (the others run on the fp32 SIMT kernel -- or raise when tcgen05 is forced)."""
+    # HalfCheetah 26-512-512-512-20: layer 0 4 pairs + 2 x 32 pairs; output N = 32, 4 K chunks per 32 KB stage, 2 stages
+    st, p = _plan(20, 6, (512, 512, 512))
+    assert st == 0 and p[:6] == [1, 68, 32, 4, 2, 70] and p[6] == 70 * 32768 and p[7] == 0
+    # Ant 49-512-512-512-41: output N = 48 -> 2 chunks per stage, 4 stages
+    st, p = _plan(41, 8, (512, 512, 512))
+    assert st == 0 and p[:6] == [1, 68, 48, 2, 4, 72]
+    # BASELINE cfg1: two hidden layers
+    st, p = _plan(20, 6, (512, 512))
+    assert st == 0 and p[:6] == [1, 36, 32, 4, 2, 38]
+    # single 128-wide hidden layer (arm_7dof test shape): one pair + one output stage
+    st, p = _plan(17, 7, (128,))
+    assert st == 0 and p[:6] == [1, 1, 32, 4, 1, 2]
+    # no tensor-core variant: width not a multiple of 128, too wide, obs / act beyond the register-resident limits
+    for shape in [(20, 6, (100, 128)), (20, 6, (640,)), (49, 6, (128,)), (20, 17, (128,)), (48, 17, (128,))]:
+        st, p = _plan(*shape)
+        assert st == 0 and p[0] == 0, shape
+    st, _ = _plan(20, 6, ())
+    assert st == -1

@@ -311,6 +311,8 @@ def test_host_buffer_plan_call_matches_oracle_on_its_own_candidates(graph, monke
                                           discount=0.95, set_mode=2, first_set=0, n_sets=3, seed=7)
         cand = eng.last_plan_candidates()                       # [H, m*N, A] float32
         assert cand.shape == (h, 2 * n, prob["act_dim"])
+        # the draw is the oracle's Philox4x32-10 stream for (seed, call index), bit for bit
+        np.testing.assert_array_equal(cand, O.sample_rs_actions_device(7, call, prob["low"], prob["high"], h, 2 * n))
         assert np.all(cand >= prob["low"].astype(np.float32)) and np.all(cand < prob["high"].astype(np.float32))
         want = O.rollout_returns(obs.astype(np.float32).astype(np.float64), cand.astype(np.float64), prob["param_sets"],
                                  prob["norm"], prob["reward_kind"], prob["dt"], 0.95, "ensemble")

@@ -154,3 +154,18 @@ def test_rebal_recurrent_planner_matches_reference(golden):
         np.testing.assert_array_equal(hidden[1], golden["rebal_hidden_h"][step])
         obs_t = obs_t + 0.05 * np.random.RandomState(step).normal(size=obs_t.shape)
     assert tuple(golden["rebal_get_action_shape"]) == (1, 6)
+
+
+def test_philox_restatement_matches_the_published_known_answer_vectors():
+    """Random123's known-answer vectors for philox4x32-10 (the generator behind the device candidate sampler)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array([ctr]), key)[0]
+        assert tuple(int(v) for v in got) == want
+    a = O.sample_rs_actions_device(7, 3, -np.ones(6), np.ones(6), 4, 10)
+    assert a.shape == (4, 10, 6) and a.dtype == np.float32 and np.all(a >= -1) and np.all(a < 1)
+    b = O.sample_rs_actions_device(7, 4, -np.ones(6), np.ones(6), 4, 10)
+    assert not np.array_equal(a, b)
