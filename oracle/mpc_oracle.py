@@ -24,6 +24,8 @@ Pinning status (see DESIGN.md "Oracle"):
     against torch autograd in ``tests/test_oracle_golden.py``.
   * "ensemble = E" (BASELINE.json)         -- NO REFERENCE CODE exists; the aggregation
     rule (mean of the E predicted deltas) is this build's definition.
+  * device candidate sampler (Philox4x32-10, throughput mode only; the reference draws with numpy's MT19937,
+    which the parity mode keeps)             -- PINNED to Random123's published known-answer vectors.
 """
 from collections import OrderedDict
 
