@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   // ReLU -> bf16 hi/lo split -> the next layer's K-major B operand with transposed 8x8 stmatrix stores (16-byte rows of 8
   // features per candidate), in place; one readiness event per M-block (chunks 2mb, 2mb+1 of the next layer's input).
   constexpr int kCbAll = NC / 16, kCbMain = (kCbAll + 1) / 2;          // the epilogue warps take the lower blocks, the helpers the rest
+  static_assert(kCbMain < kCbAll, "the helper warps take part in every act_ready barrier: NC must be >= 32");
   auto hidden_epilogue = [&](auto cb0_tag, auto cb1_tag, int t, int l, int pair_a, int wq, bool stamps) {
     constexpr int CB0 = decltype(cb0_tag)::value, CB1 = decltype(cb1_tag)::value;
     const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   if (warp >= 6) {
     // ================================================================ epilogue helpers (warps 6-9; 10, 11 idle)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
-    if (warp < 10 && kCbMain < kCbAll) {
+    if (warp < 10) {
       const int wq = warp & 3;
       uint32_t lf_phase = 0;
       int pair_a = 0;
