@@ -55,6 +55,7 @@ struct TcPlan {
   int nkc[kMaxLayers];
   int nks_last[kMaxLayers];
   int tile_off[kMaxLayers];
+  int l0_packed;         // layer 0 uses <= 32 of a tile's 64 K columns: two M-blocks share one tile pair (K halves)
   int hidden_pairs;      // 32 KB ring stages (tile pairs) of the hidden layers
   int out_n;             // output layer: MMA N = obs dim padded to a multiple of 16
   int out_kcs;           // output layer: K chunks ([out_n x 64] hi + lo tiles) packed into one 32 KB ring stage
@@ -63,7 +64,11 @@ struct TcPlan {
   long long set_bytes;   // stages_per_set * 32 KB
 };
 
+__host__ __device__ inline int tc_layer_pairs(const TcPlan& p, int l) {
+  return (l == 0 && p.l0_packed) ? p.nmb[0] / 2 : p.nmb[l] * p.nkc[l];
+}
 __host__ __device__ inline int tc_tile_index(const TcPlan& p, int l, int mb, int kc, int part) {
+  if (l == 0 && p.l0_packed) return p.tile_off[0] + (mb / 2) * 2 + part;     // M-blocks 2j, 2j+1 = K halves of pair j
   const int nmb = p.nmb[l], nkc = p.nkc[l];
   const int nA = nmb < 2 ? nmb : 2, nB = nmb - nA;
   if (mb < nA) return p.tile_off[l] + ((kc * nA + mb) * 2 + part);
@@ -98,7 +103,8 @@ inline bool tc_make_plan(const MlpDims& md, TcPlan* p) {
     const int rem = din_eff - (p->nkc[l] - 1) * 64;
     p->nks_last[l] = (rem + 15) / 16;
     p->tile_off[l] = off;
-    if (l + 1 < md.n_layers) off += p->nmb[l] * p->nkc[l] * 2;
+    if (l == 0) p->l0_packed = (p->nkc[0] == 1 && p->nks_last[0] <= 2 && p->nmb[0] % 2 == 0) ? 1 : 0;
+    if (l + 1 < md.n_layers) off += tc_layer_pairs(*p, l) * 2;
   }
   p->hidden_pairs = off / 2;
   // output layer (roles swapped): per K chunk one [out_n x 64] hi tile followed by the lo tile, out_kcs chunks per stage
@@ -150,7 +156,29 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const PrepArgs a) {
     return;
   }
   int l = 0, rem = blockIdx.x;
-  while (l + 2 < a.plan.n_layers && rem >= a.plan.nmb[l] * a.plan.nkc[l]) { rem -= a.plan.nmb[l] * a.plan.nkc[l]; ++l; }
+  while (l + 2 < a.plan.n_layers && rem >= tc_layer_pairs(a.plan, l)) { rem -= tc_layer_pairs(a.plan, l); ++l; }
+  if (l == 0 && a.plan.l0_packed) {
+    // packed layer 0: tile pair `rem` holds M-block 2*rem in K columns [0, 32) and M-block 2*rem + 1 in [32, 64)
+    const int din = a.dims.dims[0], dout = a.dims.dims[1];
+    const float* W = a.params + (size_t)set * a.dims.set_stride + a.dims.w_off[0];
+    uint8_t* tile_hi = a.blobs + (size_t)set * a.plan.set_bytes + (size_t)tc_tile_index(a.plan, 0, 2 * rem, 0, 0) * kTcTileBytes;
+    uint8_t* tile_lo = tile_hi + kTcTileBytes;
+    for (int item = threadIdx.x; item < 128 * 8; item += blockDim.x) {
+      const int r = item & 127, ch = item >> 7;
+      const int f = (2 * rem + (ch >> 2)) * 128 + r;
+      uint16_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = tc_in0_of_col(a.dims.obs_dim, a.dims.act_dim, (ch & 3) * 8 + i);
+        const float w = (f < dout && k >= 0 && k < din) ? W[(size_t)k * dout + f] : 0.f;
+        umma::split_bf16(w, hi[i], lo[i]);
+      }
+      const uint32_t off = umma::sw128_offset(r, ch * 8);
+      *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+      *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+    }
+    return;
+  }
   const int mb = rem / a.plan.nkc[l], kc = rem % a.plan.nkc[l];
   const int din = a.dims.dims[l], dout = a.dims.dims[l + 1];
   const float* W = a.params + (size_t)set * a.dims.set_stride + a.dims.w_off[l];
@@ -434,6 +462,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         __syncwarp();
         if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
       };
+      // Packed layer 0 (its input is <= 32 wide): one stage holds TWO M-blocks, W[mb0] in K columns [0, 32) of the tile and
+      // W[mb1] in [32, 64); both multiply activation chunk 0, k-steps 0 .. nks-1, into the two accumulators of a slot pair.
+      // Halves the layer's weight stream and its stage handshakes.
+      auto packed_pair = [&](uint32_t d_tmem0, int nks) {
+        umma::mbar_wait(&full[stage], phase);
+        umma::tc_fence_after();
+        const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int mbsel = 0; mbsel < 2; ++mbsel) {
+            const uint32_t d = d_tmem0 + (uint32_t)(mbsel * NC);
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint32_t ka = (uint32_t)(2 * (2 * mbsel + ks)), kb = (uint32_t)(2 * ks);
+              umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d, a_hi + ka, hi_lo32 + kb, kIdesc, ks == 0 ? 0u : 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + ka, lo_lo32 + kb, kIdesc, 1u);
+              umma::mma_bf16_ss_lo(d, a_lo + ka, hi_lo32 + kb, kIdesc, 1u);
+            }
+          }
+          umma::mma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+      };
       // Accumulator slots: 3 pairs x 2 slots x NC TMEM columns.  Layer i accumulates its M-blocks {0,1} in pair a_i and
       // {2,3} in pair b_i = a_i + 1; a_{i+1} = a_i + 2 (mod 3) is the pair layer i does not touch, so phase A of layer i+1
       // can run while layer i's epilogue is still draining a_i / b_i, and b_{i+1} = a_i is drained by the time phase B starts.
@@ -462,6 +513,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             }
             umma::tc_fence_after();
             if (ev == 0) L2A_STAMP(4 * l + 3);
+            if (l == 0 && plan.l0_packed) {
+              packed_pair(tmem_base + (uint32_t)(2 * pair_a * NC), nks_last);       // M-blocks 0 and 1 from one stage
+              continue;
+            }
             const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * cpe);
             for (int kc = ev * cpe; kc < kc_end; ++kc) {
               const bool full_k = (kc != nkc - 1) || (nks_last == 4);
@@ -471,6 +526,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           }
           L2A_STAMP(4 * l + 1);
           // phase B: every chunk is there and the previous layer's accumulators (pair_b) are drained
+          if (l == 0 && plan.l0_packed) {
+            if (nmb > 2) packed_pair(tmem_base + (uint32_t)(2 * pair_b * NC), nks_last);   // M-blocks 2 and 3
+          } else
           for (int kc = 0; kc < nkc; ++kc) {
             const bool full_k = (kc != nkc - 1) || (nks_last == 4);
             for (int mb = nA; mb < nmb; ++mb)

@@ -73,15 +73,16 @@ def _plan(obs_dim, act_dim, hidden):
 def test_tensor_core_tiling_of_the_baseline_shapes():
     """Host logic of the weight-tile plan (no GPU): ring stages per weight set, output-layer tile geometry, and which shapes
     have a tcgen05 variant at all (the others run on the fp32 SIMT kernel -- or raise when tcgen05 is forced)."""
-    # HalfCheetah 26-512-512-512-20: layer 0 4 pairs + 2 x 32 pairs; output N = 32, 4 K chunks per 32 KB stage, 2 stages
+    # HalfCheetah 26-512-512-512-20: layer 0 (input 30 <= 32 wide: two M-blocks per tile pair) 2 pairs + 2 x 32 pairs;
+    # output N = 32, 4 K chunks per 32 KB stage, 2 stages
     st, p = _plan(20, 6, (512, 512, 512))
-    assert st == 0 and p[:6] == [1, 68, 32, 4, 2, 70] and p[6] == 70 * 32768 and p[7] == 0
-    # Ant 49-512-512-512-41: output N = 48 -> 2 chunks per stage, 4 stages
+    assert st == 0 and p[:6] == [1, 66, 32, 4, 2, 68] and p[6] == 68 * 32768 and p[7] == 0
+    # Ant 49-512-512-512-41: layer-0 input 56 wide -> unpacked (4 pairs); output N = 48 -> 2 chunks per stage, 4 stages
     st, p = _plan(41, 8, (512, 512, 512))
     assert st == 0 and p[:6] == [1, 68, 48, 2, 4, 72]
     # BASELINE cfg1: two hidden layers
     st, p = _plan(20, 6, (512, 512))
-    assert st == 0 and p[:6] == [1, 36, 32, 4, 2, 38]
+    assert st == 0 and p[:6] == [1, 34, 32, 4, 2, 36]
     # single 128-wide hidden layer (arm_7dof test shape): one pair + one output stage
     st, p = _plan(17, 7, (128,))
     assert st == 0 and p[:6] == [1, 1, 32, 4, 1, 2]
