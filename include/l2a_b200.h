@@ -263,6 +263,12 @@ int l2a_debug_stream(l2a_ctx* ctx, const void* blob, int n_tiles_per_pass, int p
  * shared memory (mode 0), from tensor memory (1), tcgen05.cp only (2), cp + TS-mode MMA pipelined (3). cycles_out: device int64[1]. */
 int l2a_debug_mma_rate(l2a_ctx* ctx, int nc, int mode, int iters, long long* cycles_out, void* stream);
 
+/* CTA-pair probes for the next step of K1, one cluster of 2 CTAs, NC = 80 candidates per CTA.
+ * mode 0: `iters` tile pairs of tcgen05.mma.cta_group::2 (M = 256, N = 160, 12 split-bf16 MMAs each): cycles_out[0] = total SM
+ * cycles, [1] = cycles until the last MMA was issued.  mode 1: `iters` DSMEM bulk copies of copy_bytes (16 .. 16384, multiple
+ * of 16) into the peer CTA in both directions: cycles_out[2], [3] = cycles each receiver waited.  cycles_out: device int64[4]. */
+int l2a_debug_pair(l2a_ctx* ctx, int mode, int iters, int copy_bytes, long long* cycles_out, void* stream);
+
 /* When set (device int64[128]), CTA 0 of the tcgen05 rollout records clock64() stamps of its pipeline events during
  * horizon step 1 (see L2A_STAMP slots in csrc/rollout_tc.cuh).  NULL switches it off. */
 int l2a_debug_set_timeline(l2a_ctx* ctx, long long* buf128);

@@ -15,7 +15,7 @@ EXPORTS = [
     "l2a_last_error", "l2a_version", "l2a_ctx_create", "l2a_ctx_destroy", "l2a_ctx_launch_count",
     "l2a_model_create", "l2a_model_destroy", "l2a_model_set_params", "l2a_model_get_params",
     "l2a_model_set_normalization", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
-    "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
+    "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_debug_pair", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window",
@@ -92,6 +92,7 @@ def load():
     lib.l2a_rnn_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_rnn_predict.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.l2a_debug_mma_rate.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.l2a_debug_pair.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.l2a_shard_pack.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.l2a_shard_select.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.l2a_debug_stream.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]

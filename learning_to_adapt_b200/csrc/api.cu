@@ -1012,6 +1012,32 @@ extern "C" int l2a_shard_select(l2a_ctx* c, const float* gathered, int G, int m,
   return L2A_OK;
 }
 
+extern "C" int l2a_debug_pair(l2a_ctx* c, int mode, int iters, int copy_bytes, long long* cycles_out, void* stream) {
+  if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (mode < 0 || mode > 1 || iters < 1 || copy_bytes < 16 || copy_bytes > 16384 || copy_bytes % 16 != 0)
+    return fail(L2A_ERR_INVALID, "bad mode/iters/copy_bytes");
+  if ((long long)iters * copy_bytes >= (1 << 20)) return fail(L2A_ERR_INVALID, "iters * copy_bytes must stay below the mbarrier tx-count range (1 MiB)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t smem = 4 * 16384 + 2 * 80 * 128 + 32768 + 64;
+  CUDA_TRY(cudaFuncSetAttribute(debug_pair_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, debug_pair_kernel<80>, mode, iters, copy_bytes, cycles_out));
+  c->launches++;
+  return L2A_OK;
+}
+
 extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long long* cycles_out, void* stream) {
   if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
   if (mode < 0 || mode > 8 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");

@@ -283,3 +283,89 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
   if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc<512>(tmem_base); }
 }
 }  // namespace l2a
+
+namespace l2a {
+// Diagnostics for the next step of K1: a CTA PAIR issuing tcgen05.mma.cta_group::2 (M = 256 across the two
+// CTAs, each CTA's shared memory supplies its 128 weight rows and its NC candidate rows of B; N = 2*NC), and the DSMEM bulk
+// copy the pair's epilogue all-to-all would use.
+//   mode 0: `iters` tile pairs (12 split-bf16 MMAs each, with the A-collector hints) -> cycles_out[0] = total, [1] = issue time
+//   mode 1: `iters` bulk copies of `copy_bytes` from this CTA's shared memory into the peer's (cp.async.bulk.shared::cluster,
+//           complete_tx on the peer's mbarrier), both directions at once -> cycles_out[2 + rank] = cycles seen by the receiver
+// Launch with a cluster of 2.  Operand contents are irrelevant (timing only).
+template <int NC>
+__global__ void __launch_bounds__(128, 1) debug_pair_kernel(int mode, int iters, int copy_bytes, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t pair_smem[];
+  uint8_t* a_tiles = pair_smem;                       // 2 stages x (hi 16 KB + lo 16 KB): this CTA's 128 rows of the 256-row tile
+  uint8_t* b_hi = pair_smem + 4 * 16384;              // [NC x 64] chunk: this CTA's half of the N = 2*NC columns
+  uint8_t* b_lo = b_hi + NC * 128;
+  uint8_t* xfer_src = b_lo + NC * 128;                // 16 KB source / 16 KB destination of the DSMEM copy test
+  uint8_t* xfer_dst = xfer_src + 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xfer_dst + 16384);   // [0] MMA completion, [1] incoming copy
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = umma::cluster_ctarank();
+  for (int i = tid; i < (4 * 16384 + 2 * NC * 128 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(pair_smem)[i] = 0x3c003c00u;
+  if (tid == 0) { umma::mbar_init(&bar[0], 1); umma::mbar_init(&bar[1], 1); umma::fence_barrier_init(); }
+  umma::cluster_sync_all();
+  if (warp == 0) {                                    // both CTAs of the pair take part in the 2-CTA allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  umma::cluster_sync_all();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (mode == 0) {
+    if (rank == 0 && warp == 1) {                     // only the leader CTA issues; descriptors are CTA-local offsets valid in both
+      constexpr uint32_t idesc = umma::make_idesc_bf16(256, 2 * NC);
+      const uint32_t a0 = umma::desc_lo32(umma::smem_u32(a_tiles)), bh = umma::desc_lo32(umma::smem_u32(b_hi)), bl = umma::desc_lo32(umma::smem_u32(b_lo));
+      const uint32_t stage_step = 32768u >> 4, lo_step = 16384u >> 4;
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t a_hi = a0 + (uint32_t)(it & 1) * stage_step, a_lo = a_hi + lo_step;
+        const uint32_t d = tmem_base + (uint32_t)((it & 1) * 2 * NC);
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                         "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], da, db, %3, p;\n\t}" ::"r"(d), "r"(a_hi + 2 * ks), "r"(bh + 2 * ks), "r"(idesc), "r"(umma::kDescHi32) : "memory");
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                         "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], da, db, %3, p;\n\t}" ::"r"(d), "r"(a_hi + 2 * ks), "r"(bl + 2 * ks), "r"(idesc), "r"(umma::kDescHi32) : "memory");
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d), "r"(a_lo + 2 * ks), "r"(bh + 2 * ks), "r"(idesc), "r"(umma::kDescHi32) : "memory");
+          }
+        }
+        __syncwarp();
+      }
+      const long long t_issued = clock64();
+      if (umma::elect_one())
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(umma::smem_u32(&bar[0])), "h"((uint16_t)1) : "memory");
+      __syncwarp();
+      umma::mbar_wait(&bar[0], 0);
+      if ((tid & 31) == 0) { cycles_out[0] = clock64() - t0; cycles_out[1] = t_issued - t0; }
+    }
+  } else {
+    // each CTA pushes `iters` copies into the peer's xfer_dst; the receiver waits on its own barrier
+    if (warp == 1 && (tid & 31) == 0) {
+      const uint32_t peer = rank ^ 1u;
+      const uint32_t dst = umma::map_to_cta(umma::smem_u32(xfer_dst), peer), rbar = umma::map_to_cta(umma::smem_u32(&bar[1]), peer);
+      for (int it = 0; it < iters; ++it)
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "r"(umma::smem_u32(xfer_src)), "r"((uint32_t)copy_bytes), "r"(rbar) : "memory");
+    }
+    if (warp == 2 && (tid & 31) == 0) {
+      const long long t0 = clock64();
+      umma::mbar_arrive_expect_tx(&bar[1], (uint32_t)copy_bytes * (uint32_t)iters);
+      umma::mbar_wait(&bar[1], 0);
+      cycles_out[2 + rank] = clock64() - t0;
+    }
+  }
+  umma::tc_fence_before();
+  umma::cluster_sync_all();
+  if (warp == 0) {
+    umma::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+}  // namespace l2a
