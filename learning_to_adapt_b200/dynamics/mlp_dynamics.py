@@ -140,8 +140,8 @@ class MLPDynamicsModel(Serializable):
         return np.asarray(obs, np.float64) + delta
 
     # ------------------------------------------------------------------ fit (host-side glue, off the hot path)
-    def fit(self, obs, act, obs_next, epochs=1000, compute_normalization=True, verbose=False, valid_split_ratio=None,
-            rolling_average_persitency=None, log_tabular=False):
+    def fit(self, obs, act, obs_next, epochs=1000, compute_normalization=True, valid_split_ratio=None,
+            rolling_average_persitency=None, verbose=False, log_tabular=False):
         """Adam on mean((delta_n - f(x_n))^2), validation-based early stop (mlp_dynamics.py:91-202).  Runs in torch on
         the engine's device and writes the result back into the engine's weight sets.  Off the planning hot path."""
         from learning_to_adapt_b200.dynamics.fit import fit_mlp
