@@ -27,6 +27,20 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
+def build_variant(name, defines, verbose=False):
+    """Development: a second build with extra -D flags at lib/variants/lib<name>.so (A/B runs on one box through the
+    L2A_B200_LIB environment variable).  Not used by the product."""
+    out_dir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "lib%s.so" % name)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "api.cu")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile csrc/api.cu (which includes every kernel) into lib/libl2a_b200.so."""
     if not force and not is_stale():

@@ -723,11 +723,13 @@ static int adapt_impl(l2a_ctx* c, l2a_model* m, const float* x, const float* tar
   memset(&aa, 0, sizeof(aa));
   aa.dims = md;
   int ao = 0, go = 0;
+  // every h_l / g_l block (and every task's block) starts on a 16-byte boundary: the kernels read them with float4 loads
+  // (an odd obs_dim such as Ant's 41 with M not a multiple of 4 would otherwise misalign task k >= 1)
   for (int l = 0; l < md.n_layers; ++l) {
     aa.act_off[l] = ao;
-    ao += md.dims[l] * M;
+    ao = (ao + md.dims[l] * M + 3) & ~3;
     aa.grad_off[l] = go;
-    go += md.dims[l + 1] * M;
+    go = (go + md.dims[l + 1] * M + 3) & ~3;
   }
   aa.act_off[md.n_layers] = ao;
   aa.grad_off[md.n_layers] = go;

@@ -44,6 +44,20 @@ constexpr int kTcThreads = 384;         // three warpgroups: 0 = epilogue + env 
 constexpr int kTcMaxAct = 16;           // action dim limit of this variant
 constexpr int kTcMaxObs = 48;           // obs dim limit of this variant (candidate state lives in registers)
 
+// Schedule options of the rollout kernel (compile-time; see DESIGN.md "K1 schedule"):
+//  L2A_TC_EARLY_EPI  the epilogue of M-blocks 0 and 1 of a hidden layer starts while the layer's phase B is still running, as
+//                    soon as phase B has consumed the activation chunks that epilogue overwrites in place (chunks 0,1 / 2,3);
+//                    the layer-0 input then lives in the LAST chunk so that layer 0 can do the same.
+//  L2A_TC_PIPE_WAIT  the MMA issuer tests the next ring stage's full barrier (non-blocking) in the middle of the current
+//                    stage's MMA burst, so a stage that has already landed costs no handshake bubble.
+#ifndef L2A_TC_EARLY_EPI
+#define L2A_TC_EARLY_EPI 1
+#endif
+#ifndef L2A_TC_PIPE_WAIT
+#define L2A_TC_PIPE_WAIT 1
+#endif
+constexpr int kTcXChunk = L2A_TC_EARLY_EPI ? (kTcMaxChunks - 1) : 0;   // activation chunk that holds the layer-0 input
+
 // Tile enumeration of one weight set's blob; consumed in exactly this order by the kernel.  Within a layer the M-blocks
 // are split into phase A (the first min(2, nmb) blocks) and phase B (the rest); each phase is K-OUTER:
 //   A: for kc: for mb in A: (hi, lo)      B: for kc: for mb in B: (hi, lo)
@@ -282,7 +296,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
                                               // MMA issuer can lag several events behind without mbarrier parity aliasing
   uint64_t* peer_ready = layer_full + 5;
   uint64_t* x_ready = layer_full + 6;         // the layer-0 input of the next step is written (the 128 env-step threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 7);
+  uint64_t* early = layer_full + 7;           // [2]: M-block 0 / 1 of a hidden layer may be drained (L2A_TC_EARLY_EPI)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 9);
   float* red_v = reinterpret_cast<float*>(tmem_slot + 2);   // [4]
   int* red_i = reinterpret_cast<int*>(red_v + 4);           // [4]
   int* s_flag = red_i + 4;
@@ -308,6 +323,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     umma::mbar_init(layer_full, 1);
     for (int j = 0; j < 4; ++j) umma::mbar_init(&act_ready[j], 256);   // epilogue warps + helper warps
     umma::mbar_init(x_ready, 128);
+    umma::mbar_init(&early[0], 1);
+    umma::mbar_init(&early[1], 1);
     umma::mbar_init(peer_ready, csize);
     umma::fence_barrier_init();
   }
@@ -336,12 +353,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   // features per candidate), in place; one readiness event per M-block (chunks 2mb, 2mb+1 of the next layer's input).
   constexpr int kCbAll = NC / 16, kCbMain = (kCbAll + 1) / 2;          // the epilogue warps take the lower blocks, the helpers the rest
   static_assert(kCbMain < kCbAll, "the helper warps take part in every act_ready barrier: NC must be >= 32");
-  auto hidden_epilogue = [&](auto cb0_tag, auto cb1_tag, int t, int l, int pair_a, int wq, bool stamps) {
+  auto hidden_epilogue = [&](auto cb0_tag, auto cb1_tag, int t, int l, int pair_a, int wq, bool stamps, uint32_t& lf_phase,
+                             uint32_t& early_phase) {
     constexpr int CB0 = decltype(cb0_tag)::value, CB1 = decltype(cb1_tag)::value;
     const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
     const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;          // stmatrix row owned by this lane (within 16 candidates)
     const int fsel = ((lane >> 3) & 1) * 8;                         // ... of the feature-group matrix 0 / +8
+#if !L2A_TC_EARLY_EPI
+    umma::mbar_wait(layer_full, lf_phase);
+    umma::tc_fence_after();
+    if (stamps) L2A_STAMP(32 + 4 * l + 0);
+#endif
     for (int mb = 0; mb < plan.nmb[l]; ++mb) {
+#if L2A_TC_EARLY_EPI
+      // M-blocks 0, 1 (phase A accumulators): drained as soon as the issuer says phase B no longer reads the chunks they
+      // overwrite; M-blocks 2, 3 after the whole layer
+      if (mb < 2) {
+        umma::mbar_wait(&early[mb], (early_phase >> mb) & 1u);
+        umma::tc_fence_after();
+        if (stamps && mb == 0) L2A_STAMP(32 + 4 * l + 0);
+      } else if (mb == 2) {
+        umma::mbar_wait(layer_full, lf_phase);
+        umma::tc_fence_after();
+      }
+#endif
       const int slot = (mb < 2) ? (2 * pair_a + mb) : (2 * ((pair_a + 1) % 3) + (mb - 2));
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -376,6 +411,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       umma::mbar_arrive(&act_ready[mb]);
       if (stamps && mb == 0) L2A_STAMP(32 + 4 * l + 1);
     }
+#if L2A_TC_EARLY_EPI
+    if (plan.nmb[l] <= 2) umma::mbar_wait(layer_full, lf_phase);      // keeps the layer_full phase in step
+    early_phase ^= 3u;
+#endif
+    lf_phase ^= 1u;
   };
 
   // Register re-partitioning between the warpgroups (see the header): the env-step warps need ~240, everything else < 128.
@@ -385,14 +425,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
     if (warp < 10) {
       const int wq = warp & 3;
-      uint32_t lf_phase = 0;
+      uint32_t lf_phase = 0, early_phase = 0;
       int pair_a = 0;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l + 1 < L; ++l) {
-          umma::mbar_wait(layer_full, lf_phase);
-          lf_phase ^= 1u;
-          umma::tc_fence_after();
-          hidden_epilogue(IntTag<kCbMain>{}, IntTag<kCbAll>{}, t, l, pair_a, wq, false);
+          hidden_epilogue(IntTag<kCbMain>{}, IntTag<kCbAll>{}, t, l, pair_a, wq, false, lf_phase, early_phase);
           pair_a = (pair_a + 2) % 3;
         }
         umma::mbar_wait(layer_full, lf_phase);                       // the output layer's completion: keeps the phase in step
@@ -428,62 +465,99 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     {
       int stage = 0;
       uint32_t phase = 0, act_phase = 0, xr_phase = 0;
+      bool ready = false;        // full[stage] was already seen complete for `phase` by a mid-burst probe (L2A_TC_PIPE_WAIT)
       const uint32_t hi_lo32 = umma::desc_lo32(umma::smem_u32(act_hi)), lo_lo32 = umma::desc_lo32(umma::smem_u32(act_lo));
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)S::kStageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
-      // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block
-      auto tile_pair = [&](uint32_t d_tmem, int kc, bool first, bool full_k, int nks_last) {
-        const uint32_t bh = hi_lo32 + (uint32_t)kc * kChunkStep, bl = lo_lo32 + (uint32_t)kc * kChunkStep;
-        umma::mbar_wait(&full[stage], phase);
+      // ring protocol of the consumer side: acquire (wait unless a probe already saw the stage full) -> MMAs -> commit -> advance
+      auto acquire = [&]() {
+        if (!ready) umma::mbar_wait(&full[stage], phase);
         umma::tc_fence_after();
+      };
+      auto probe_next = [&]() {
+#if L2A_TC_PIPE_WAIT
+        const int ns = (stage + 1 == kTcStages) ? 0 : stage + 1;
+        ready = umma::mbar_test_wait(&full[ns], (ns == 0) ? (phase ^ 1u) : phase);
+#endif
+      };
+      auto advance = [&](bool probed) {
+        if (!probed) ready = false;
+        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+      };
+      // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block against activation chunk `ch`
+      auto tile_pair = [&](uint32_t d_tmem, int ch, bool first, bool full_k, int nks_last) {
+        const uint32_t bh = hi_lo32 + (uint32_t)ch * kChunkStep, bl = lo_lo32 + (uint32_t)ch * kChunkStep;
+        acquire();
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
-        if (umma::elect_one()) {
-          // per 16-wide k-step: W_hi * x_hi, W_hi * x_lo (the W_hi slice is fetched from shared memory once for the two:
-          // A-collector keep / reuse), W_lo * x_hi
-          if (full_k) {
+        // per 16-wide k-step: W_hi * x_hi, W_hi * x_lo (the W_hi slice is fetched from shared memory once for the two:
+        // A-collector keep / reuse), W_lo * x_hi
+        if (full_k) {
+          if (umma::elect_one()) {
             umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi, bh, kIdesc, first ? 0u : 1u);
             umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi, bl, kIdesc, 1u);
             umma::mma_bf16_ss_lo(d_tmem, a_lo, bh, kIdesc, 1u);
+            umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2, bh + 2, kIdesc, 1u);
+            umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2, bl + 2, kIdesc, 1u);
+            umma::mma_bf16_ss_lo(d_tmem, a_lo + 2, bh + 2, kIdesc, 1u);
+          }
+          __syncwarp();
+          probe_next();            // its latency hides behind the MMAs already queued on the tensor pipe
+          if (umma::elect_one()) {
 #pragma unroll
-            for (int ks = 1; ks < 4; ++ks) {
+            for (int ks = 2; ks < 4; ++ks) {
               umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
             }
-          } else {
+            umma::mma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          advance(true);
+        } else {
+          if (umma::elect_one()) {
             for (int ks = 0; ks < nks_last; ++ks) {
               umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
               umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
               umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
             }
+            umma::mma_commit(&empty[stage]);
           }
-          umma::mma_commit(&empty[stage]);
+          __syncwarp();
+          advance(false);
         }
-        __syncwarp();
-        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
       };
       // Packed layer 0 (its input is <= 32 wide): one stage holds TWO M-blocks, W[mb0] in K columns [0, 32) of the tile and
-      // W[mb1] in [32, 64); both multiply activation chunk 0, k-steps 0 .. nks-1, into the two accumulators of a slot pair.
+      // W[mb1] in [32, 64); both multiply the input chunk, k-steps 0 .. nks-1, into the two accumulators of a slot pair.
       // Halves the layer's weight stream and its stage handshakes.
       auto packed_pair = [&](uint32_t d_tmem0, int nks) {
-        umma::mbar_wait(&full[stage], phase);
-        umma::tc_fence_after();
+        acquire();
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
+        const uint32_t xh = hi_lo32 + (uint32_t)kTcXChunk * kChunkStep, xl = lo_lo32 + (uint32_t)kTcXChunk * kChunkStep;
         if (umma::elect_one()) {
 #pragma unroll
           for (int mbsel = 0; mbsel < 2; ++mbsel) {
             const uint32_t d = d_tmem0 + (uint32_t)(mbsel * NC);
             for (int ks = 0; ks < nks; ++ks) {
               const uint32_t ka = (uint32_t)(2 * (2 * mbsel + ks)), kb = (uint32_t)(2 * ks);
-              umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d, a_hi + ka, hi_lo32 + kb, kIdesc, ks == 0 ? 0u : 1u);
-              umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + ka, lo_lo32 + kb, kIdesc, 1u);
-              umma::mma_bf16_ss_lo(d, a_lo + ka, hi_lo32 + kb, kIdesc, 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d, a_hi + ka, xh + kb, kIdesc, ks == 0 ? 0u : 1u);
+              umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + ka, xl + kb, kIdesc, 1u);
+              umma::mma_bf16_ss_lo(d, a_lo + ka, xh + kb, kIdesc, 1u);
             }
           }
           umma::mma_commit(&empty[stage]);
         }
         __syncwarp();
-        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        advance(false);
+      };
+      // "M-blocks 0 / 1 of this layer may be drained": all MMAs issued so far (phase A entirely, phase B up to the chunks those
+      // epilogues overwrite) are complete when the commit arrives
+      auto commit_early = [&](int which) {
+#if L2A_TC_EARLY_EPI
+        if (umma::elect_one()) umma::mma_commit(&early[which]);
+        __syncwarp();
+#else
+        (void)which;
+#endif
       };
       // Accumulator slots: 3 pairs x 2 slots x NC TMEM columns.  Layer i accumulates its M-blocks {0,1} in pair a_i and
       // {2,3} in pair b_i = a_i + 1; a_{i+1} = a_i + 2 (mod 3) is the pair layer i does not touch, so phase A of layer i+1
@@ -500,6 +574,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           const int pair_b = (pair_a + 1) % 3;
           const int nsrc = (l == 0) ? 1 : plan.nmb[l - 1];          // readiness events of this layer's input
           const int cpe = (l == 0) ? nkc : 2;                       // activation chunks published per event
+          const int ch0 = (l == 0) ? kTcXChunk : 0;                 // layer 0 reads its single input chunk from kTcXChunk
           L2A_STAMP(4 * l + 0);
           if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64();   // step length
           // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
@@ -521,18 +596,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             for (int kc = ev * cpe; kc < kc_end; ++kc) {
               const bool full_k = (kc != nkc - 1) || (nks_last == 4);
               for (int mb = 0; mb < nA; ++mb)
-                tile_pair(tmem_base + (uint32_t)((2 * pair_a + mb) * NC), kc, kc == 0, full_k, nks_last);
+                tile_pair(tmem_base + (uint32_t)((2 * pair_a + mb) * NC), ch0 + kc, kc == 0, full_k, nks_last);
             }
           }
           L2A_STAMP(4 * l + 1);
-          // phase B: every chunk is there and the previous layer's accumulators (pair_b) are drained
+          // phase B: every chunk is there and the previous layer's accumulators (pair_b) are drained.
+          // Early drain of M-blocks 0 / 1: layer 0 keeps its input in chunk kTcXChunk, which those epilogues do not write ->
+          // right after phase A; wider inputs -> once phase B is past chunks {0,1} / {2,3}; no phase B -> now.
+          const bool early_now = (l == 0) || (nmb <= nA);
+          if (early_now) { commit_early(0); commit_early(1); }
           if (l == 0 && plan.l0_packed) {
             if (nmb > 2) packed_pair(tmem_base + (uint32_t)(2 * pair_b * NC), nks_last);   // M-blocks 2 and 3
           } else
           for (int kc = 0; kc < nkc; ++kc) {
             const bool full_k = (kc != nkc - 1) || (nks_last == 4);
             for (int mb = nA; mb < nmb; ++mb)
-              tile_pair(tmem_base + (uint32_t)((2 * pair_b + (mb - nA)) * NC), kc, kc == 0, full_k, nks_last);
+              tile_pair(tmem_base + (uint32_t)((2 * pair_b + (mb - nA)) * NC), ch0 + kc, kc == 0, full_k, nks_last);
+            if (!early_now) {
+              if (kc == min(nkc - 1, 1)) commit_early(0);
+              if (kc == min(nkc - 1, 3)) commit_early(1);
+            }
           }
           if (umma::elect_one()) umma::mma_commit(layer_full);
           __syncwarp();
@@ -555,10 +638,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
             if (ev == 0) L2A_STAMP(4 * l + 3);
             const int kc_end = (ev == nsrc - 1) ? nkc : min(nkc, (ev + 1) * 2);
             for (int kc = ev * 2; kc < kc_end; ++kc) {
-              if (j == 0) {
-                umma::mbar_wait(&full[stage], phase);
-                umma::tc_fence_after();
-              }
+              if (j == 0) acquire();
               const uint32_t xh = hi_lo32 + (uint32_t)kc * kChunkStep, xl = lo_lo32 + (uint32_t)kc * kChunkStep;
               const uint32_t wh = st_lo32 + (uint32_t)stage * kStageStep + (uint32_t)j * 2u * out_part, wl = wh + out_part;
               const bool last_in_stage = (j + 1 == plan.out_kcs) || (kc == nkc - 1);
@@ -582,7 +662,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
               __syncwarp();
               if (last_in_stage) {
                 j = 0;
-                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+                advance(false);
               } else {
                 ++j;
               }
@@ -603,7 +683,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
     const bool valid = n < nvalid;
     const long long row = (long long)env * a.n_candidates + c0 + (valid ? n : 0);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    uint32_t lf_phase = 0, pr_phase = 0;
+    uint32_t lf_phase = 0, pr_phase = 0, early_phase = 0;
     int pair_a = 0;                                     // same accumulator-pair rotation as the MMA issuer
     float ret = 0.f, asq = 0.f;
     constexpr int AMAX = (DMAX <= 24) ? 8 : kTcMaxAct;    // the small instance serves act_dim <= 8 (see launch dispatch)
@@ -631,7 +711,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) umma::split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-          const uint32_t off = umma::sw128_offset((uint32_t)n, (uint32_t)g * 8u);
+          const uint32_t off = (uint32_t)kTcXChunk * (uint32_t)kChunkBytes + umma::sw128_offset((uint32_t)n, (uint32_t)g * 8u);
           *reinterpret_cast<uint4*>(act_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(act_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         };
@@ -688,11 +768,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       const float disc_t = __ldg(a.discount_pow + t);       // discount**t, fetched a whole step before its use
       // ---------------- hidden layers: TMEM -> bias + ReLU -> split -> next layer's B operand (in place)
       for (int l = 0; l + 1 < L; ++l) {
-        umma::mbar_wait(layer_full, lf_phase);
-        lf_phase ^= 1u;
-        umma::tc_fence_after();
-        if (warp == 0) L2A_STAMP(32 + 4 * l + 0);
-        hidden_epilogue(IntTag<0>{}, IntTag<kCbMain>{}, t, l, pair_a, warp, warp == 0);
+        hidden_epilogue(IntTag<0>{}, IntTag<kCbMain>{}, t, l, pair_a, warp, warp == 0, lf_phase, early_phase);
         if (warp == 0) L2A_STAMP(32 + 4 * l + 2);
         pair_a = (pair_a + 2) % 3;
       }

@@ -17,13 +17,28 @@ def make_engine(prob, n_sets=None, extra_sets=0):
     return eng
 
 
-def assert_returns_close(got, want, rtol=RTOL):
+def error_report(got, want):
+    """Error figures of a batch of returns: `scaled` = max |err| / max(1, max |want|) (the round-1 figure), `rel` = max
+    per-element |err| / max(|want|, median |want|) (north_star's "1e-4 rel", with the batch median as the floor that keeps
+    near-zero returns meaningful), `rel_raw_p99` = 99th percentile of the unfloored per-element relative error."""
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
-    scale = max(1.0, float(np.max(np.abs(want))))
     err = np.abs(got - want)
-    tol = rtol * np.maximum(np.abs(want), scale)
-    assert np.all(err <= tol), "max err %.3e (tol %.3e, scale %.3e)" % (err.max(), tol.min(), scale)
+    scale = max(1.0, float(np.max(np.abs(want))))
+    floor = max(float(np.median(np.abs(want))), 1e-30)
+    rel = err / np.maximum(np.abs(want), floor)
+    raw = err / np.maximum(np.abs(want), 1e-30)
+    return dict(scaled=float(err.max() / scale), rel=float(rel.max()), rel_raw_p99=float(np.percentile(raw, 99)),
+                floor=floor, scale=scale)
+
+
+def assert_returns_close(got, want, rtol=RTOL):
+    """Per-element relative check: |got - want| <= rtol * max(|want|, median |want| of the batch)."""
+    rep = error_report(got, want)
+    assert np.all(np.isfinite(np.asarray(got, np.float64)) | ~np.isfinite(np.asarray(want, np.float64))), "non-finite returns"
+    assert rep["rel"] <= rtol, "max per-element relative error %.3e > %.1e (scaled %.3e, floor %.3e)" % (
+        rep["rel"], rtol, rep["scaled"], rep["floor"])
+    return rep
 
 
 def assert_argmax_consistent(best_idx, want_returns, rtol=RTOL):

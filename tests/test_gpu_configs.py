@@ -1,0 +1,223 @@
+"""GPU parity at the BASELINE.json configurations, at their FULL sizes, through the C ABI.
+
+The CUDA path always runs the whole configuration; the CPU oracle runs either the whole configuration too (cfg1, cfg4)
+or a strided sample of the candidates (candidates are independent given (obs, weight sets), so the oracle return of
+candidate c does not depend on which other candidates are rolled out) -- sized so the host side stays within seconds.
+Every test prints the error figures (`tests.helpers.error_report`: max-scaled AND per-element relative) and appends them
+to gpurun_out/parity_configs.jsonl when that directory exists.
+
+Tolerance: 1e-4 relative per element on returns (north_star), floor = batch median |return|.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpc_oracle as O
+from tests.helpers import RTOL, assert_argmax_consistent, assert_returns_close, dev, error_report, make_engine
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(tag, rep, **extra):
+    row = dict(config=tag, **rep, **extra)
+    print("PARITY", json.dumps(row))
+    out = os.path.join(REPO, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_configs.jsonl"), "a") as f:
+            f.write(json.dumps(row) + "\n")
+
+
+def _rollout(eng, prob, actions, n, h, discount, set_mode, first_set, n_sets, kernel=2):
+    res = eng.rollout(dev(prob["obs0"]), dev(actions), n, h, prob["reward_kind"], prob["dt"], discount=discount,
+                      set_mode=set_mode, first_set=first_set, n_sets=n_sets, kernel=kernel)
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if v is not None else None) for k, v in res.items()}
+
+
+def _oracle_on_stride(prob, actions, n, m, sub, sets, mode, discount):
+    """Oracle returns [m, len(sub)] of the candidates `sub` of every env (row r of `actions` is env r // n)."""
+    rows = np.concatenate([e * n + sub for e in range(m)])
+    return O.rollout_returns(prob["obs0"], actions[:, rows], sets, prob["norm"], prob["reward_kind"], prob["dt"], discount, mode)
+
+
+# ------------------------------------------------------------------------------------------------ cfg1 / cfg1'
+def test_cfg1_half_cheetah_rs_full():
+    """configs[0]: HalfCheetah random shooting N=500 H=10, single MLP (512,512), m=1 -- oracle on ALL candidates."""
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=1, seed=11)
+    eng = make_engine(prob)
+    n, h = 500, 10
+    actions = O.sample_rs_actions(21, prob["low"], prob["high"], h, n)
+    want = O.rollout_returns(prob["obs0"], actions, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "shared")
+    for kernel in (2, 1):
+        res = _rollout(eng, prob, actions, n, h, 1.0, 0, 0, 1, kernel)
+        rep = assert_returns_close(res["returns"], want)
+        assert_argmax_consistent(res["best_idx"], want)
+        _record("cfg1 kernel=%d" % kernel, rep, n=n, h=h)
+
+
+def test_cfg1p_half_cheetah_rs_script_defaults():
+    """run_mb_mpc.py defaults: N=2000, H=20, m=10 envs (512,512): 20 000 rows; oracle on every 20th candidate of every env."""
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=10, seed=12)
+    eng = make_engine(prob)
+    n, h, m = 2000, 20, 10
+    actions = O.sample_rs_actions(22, prob["low"], prob["high"], h, n * m)
+    res = _rollout(eng, prob, actions, n, h, 1.0, 0, 0, 1)
+    sub = np.arange(0, n, 20)
+    want = _oracle_on_stride(prob, actions, n, m, sub, prob["param_sets"], "shared", 1.0)
+    rep = assert_returns_close(res["returns"][:, sub], want)
+    _record("cfg1p", rep, n=n, h=h, m=m, oracle_candidates=len(sub) * m)
+    best = res["best_idx"]
+    np.testing.assert_array_equal(res["best_ret"], res["returns"][range(m), best])
+    np.testing.assert_array_equal(best, np.argmax(res["returns"], axis=1))
+
+
+# ------------------------------------------------------------------------------------------------ cfg2
+def test_cfg2_half_cheetah_grbal_full():
+    """configs[1]: HalfCheetah GrBAL N=1000 H=15, 5 envs with their own K2-adapted weight sets (reading (i)), M=16, lr=1e-3,
+    MLP (512,512,512): adapt on the device, plan with the adapted sets; oracle adapts and plans on every 8th candidate."""
+    m, n, h, M, lr = 5, 1000, 15, 16, 1e-3
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512, 512), n_sets=1, m=m, seed=13)
+    eng = make_engine(prob, n_sets=1 + m)
+    theta = prob["param_sets"][0]
+    ctx = O.make_adapt_context(23, prob, m, M)
+    adapted = O.adapt(*ctx, theta, prob["norm"], lr)
+    xs, ts = [], []
+    for o, a, nx in zip(*ctx):
+        xs.append(np.concatenate([O.normalize(o, *prob["norm"]["obs"]), O.normalize(a, *prob["norm"]["act"])], axis=1))
+        ts.append(O.normalize(nx - o, *prob["norm"]["delta"]))
+    eng.adapt(dev(np.stack(xs)), dev(np.stack(ts)), lr, 0, 1)
+    actions = O.sample_rs_actions(24, prob["low"], prob["high"], h, n * m)
+    res = _rollout(eng, prob, actions, n, h, 1.0, 1, 1, m)
+    sub = np.arange(0, n, 8)
+    want = _oracle_on_stride(prob, actions, n, m, sub, adapted, "per_env", 1.0)
+    rep = assert_returns_close(res["returns"][:, sub], want)
+    _record("cfg2 reading (i)", rep, n=n, h=h, m=m, oracle_candidates=len(sub) * m)
+    np.testing.assert_array_equal(res["best_idx"], np.argmax(res["returns"], axis=1))
+    # reading (ii): the 5 adapted sets as an ensemble for ONE env
+    prob1 = dict(prob, obs0=prob["obs0"][:1])
+    act1 = actions[:, :n]
+    res2 = _rollout(eng, prob1, act1, n, h, 1.0, 2, 1, m)
+    want2 = O.rollout_returns(prob1["obs0"], act1[:, sub], adapted, prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
+    rep2 = assert_returns_close(res2["returns"][:, sub], want2)
+    _record("cfg2 reading (ii)", rep2, n=n, h=h, e=m, oracle_candidates=len(sub))
+
+
+# ------------------------------------------------------------------------------------------------ cfg3 / cfg5 (Ant)
+@pytest.mark.parametrize("tag,n,h", [("cfg3", 2000, 20), ("cfg5 per-GPU share", 4096, 25)])
+def test_cfg3_cfg5_ant_ensemble_full(tag, n, h):
+    """configs[2] Ant N=2000 H=20 E=5 and configs[4]'s per-GPU share N=4096 H=25 E=5, MLP 49-512-512-512-41, ctrl +-150:
+    the fp32 device state against the oracle's float64 state over the full horizon, on >= 125 strided candidates."""
+    E = 5
+    prob = O.make_problem("ant", hidden_sizes=(512, 512, 512), n_sets=E, m=1, seed=14)
+    eng = make_engine(prob)
+    actions = O.sample_rs_actions(25, prob["low"], prob["high"], h, n)
+    res = _rollout(eng, prob, actions, n, h, 1.0, 2, 0, E)
+    sub = np.arange(0, n, 16 if n <= 2000 else 32)
+    want = O.rollout_returns(prob["obs0"], actions[:, sub], prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
+    rep = assert_returns_close(res["returns"][:, sub], want)
+    _record(tag, rep, n=n, h=h, e=E, oracle_candidates=len(sub))
+    np.testing.assert_array_equal(res["best_idx"], np.argmax(res["returns"], axis=1))
+    # the SIMT fp32 kernel on the same sample of candidates (second implementation)
+    res_s = _rollout(eng, prob, actions[:, sub], len(sub), h, 1.0, 2, 0, E, kernel=1)
+    assert_returns_close(res_s["returns"], want)
+
+
+def test_cfg3_ant_grbal_per_env_full():
+    """configs[2] read as GrBAL (reading (i)): 5 crippled-Ant envs x N=2000, H=20, each with its adapted set."""
+    m, n, h, M, lr = 5, 2000, 20, 16, 1e-3
+    prob = O.make_problem("ant", hidden_sizes=(512, 512, 512), n_sets=1, m=m, seed=15)
+    eng = make_engine(prob, n_sets=1 + m)
+    theta = prob["param_sets"][0]
+    ctx = O.make_adapt_context(26, prob, m, M)
+    adapted = O.adapt(*ctx, theta, prob["norm"], lr)
+    xs, ts = [], []
+    for o, a, nx in zip(*ctx):
+        xs.append(np.concatenate([O.normalize(o, *prob["norm"]["obs"]), O.normalize(a, *prob["norm"]["act"])], axis=1))
+        ts.append(O.normalize(nx - o, *prob["norm"]["delta"]))
+    eng.adapt(dev(np.stack(xs)), dev(np.stack(ts)), lr, 0, 1)
+    actions = O.sample_rs_actions(27, prob["low"], prob["high"], h, n * m)
+    res = _rollout(eng, prob, actions, n, h, 1.0, 1, 1, m)
+    sub = np.arange(0, n, 40)
+    want = _oracle_on_stride(prob, actions, n, m, sub, adapted, "per_env", 1.0)
+    rep = assert_returns_close(res["returns"][:, sub], want)
+    _record("cfg3 reading (i)", rep, n=n, h=h, m=m, oracle_candidates=len(sub) * m)
+
+
+# ------------------------------------------------------------------------------------------------ cfg4 (CEM)
+def test_cfg4_half_cheetah_cem_full_compat():
+    """configs[3]: HalfCheetah CEM, 5000 candidates, 500 elites, 3 iterations, H=30, MLP (512,512), m=1, bug-compatible mode,
+    numpy draws.  Every iteration is checked at full size against ONE oracle iteration started from the device's own (mean, std)
+    (teacher forcing: the compat elite mask is a function of the rank ORDER, so an end-to-end comparison over 3 refits would
+    amplify a single near-tie rank swap into different samples): returns of all 5000 candidates, then the refit (mean, std) from
+    the device's returns."""
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    n, h, iters, pct, alpha = 5000, 30, 3, 0.1, 0.1
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=1, seed=16)
+    eng = make_engine(prob)
+    A = prob["act_dim"]
+    ha = h * A
+    k = max(int(n * pct), 1)
+    rng = np.random.RandomState(28)
+    zs = [rng.normal(size=(n, 1, ha)) for _ in range(iters)]
+    d_mean = torch.zeros((1, ha), device="cuda", dtype=torch.float64)
+    d_std = torch.ones((1, ha), device="cuda", dtype=torch.float64)
+    lo, hi = dev(np.concatenate([prob["low"]] * h)), dev(np.concatenate([prob["high"]] * h))
+    clip_low, clip_high = np.concatenate([prob["low"]] * h), np.concatenate([prob["high"]] * h)
+    for it, z in enumerate(zs):
+        mean0, std0 = d_mean.cpu().numpy().copy(), d_std.cpu().numpy().copy()
+        samples, clipped = eng.cem_sample(dev(z), d_mean, d_std, lo, hi)
+        res = eng.rollout(dev(prob["obs0"]), samples, n, h, prob["reward_kind"], prob["dt"], layout="nmha")
+        eng.cem_refit(res["returns"], clipped, k, alpha, d_mean, d_std, compat=True)
+        torch.cuda.synchronize()
+        # oracle iteration from the same state (mpc_controller.py:85-104); the device rolls out fp32-rounded samples
+        a = mean0 + z.astype(np.float32).astype(np.float64) * std0
+        a32 = a.astype(np.float32).astype(np.float64)
+        a_roll = np.transpose(a32.reshape(n, h, A), (1, 0, 2))
+        want = O.rollout_returns(prob["obs0"], a_roll, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "shared")
+        got = res["returns"].cpu().numpy()
+        rep = assert_returns_close(got, want)
+        _record("cfg4 iter %d returns" % it, rep, n=n, h=h)
+        assert int(res["best_idx"][0]) == int(np.argmax(got[0]))
+        # refit from the device's own returns: elite mask ((-returns).argsort() < k).T (:101), pooled mean / std (:102-104)
+        order = np.argsort(-got.astype(np.float64), axis=-1, kind="stable")
+        mask = (order < k).T
+        a_stacked = np.clip(a, clip_low, clip_high).astype(np.float32).astype(np.float64)      # the clipped copy is stored as fp32
+        elites = a_stacked[mask]
+        mean1 = mean0 * alpha + (1 - alpha) * elites.mean(axis=0)
+        std1 = elites.std(axis=0)
+        np.testing.assert_allclose(d_mean.cpu().numpy(), mean1, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(d_std.cpu().numpy()[0], std1, rtol=1e-6, atol=1e-6)
+    # and the controller end to end (same draws through np.random): chosen action = first action of its own best row
+    env = SyntheticEnv("half_cheetah")
+    model = MLPDynamicsModel("dyn", env, hidden_sizes=(512, 512))
+    model.set_params(prob["param_sets"][0])
+    model.set_normalization(prob["norm"])
+    ctrl = MPCController("policy", env, model, use_cem=True, n_candidates=n, horizon=h, num_cem_iters=iters,
+                         percent_elites=pct, alpha=alpha)
+    np.random.seed(28)
+    acts, _ = ctrl.get_actions(prob["obs0"])
+    assert acts.shape == (1, A) and acts.dtype == np.float64
+    np.testing.assert_allclose(ctrl.last_cem_state[0].cpu().numpy(), d_mean.cpu().numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ctrl.last_cem_state[1].cpu().numpy(), d_std.cpu().numpy(), rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ headline at full size
+def test_headline_full_size_vs_oracle_and_report():
+    """north_star target: HalfCheetah N=2000, H=20, ensemble=5 (512,512,512) -- every 10th candidate against the oracle."""
+    E, n, h = 5, 2000, 20
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512, 512), n_sets=E, m=1, seed=0)
+    eng = make_engine(prob)
+    actions = O.sample_rs_actions(3, prob["low"], prob["high"], h, n)
+    res = _rollout(eng, prob, actions, n, h, 1.0, 2, 0, E)
+    sub = np.arange(0, n, 10)
+    want = O.rollout_returns(prob["obs0"], actions[:, sub], prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
+    rep = assert_returns_close(res["returns"][:, sub], want)
+    _record("headline", rep, n=n, h=h, e=E, oracle_candidates=len(sub))
+    np.testing.assert_array_equal(res["best_idx"], np.argmax(res["returns"], axis=1))

@@ -330,6 +330,30 @@ def test_adapt_full_size_matches_oracle():
     assert_returns_close(res["returns"], ref)
 
 
+@pytest.mark.parametrize("env,hidden,K,M", [("ant", (128, 128), 2, 6), ("ant", (128, 128), 3, 5), ("arm_7dof", (64, 200), 4, 10),
+                                            ("ant", (512, 512, 512), 2, 6), ("half_cheetah", (128,), 3, 7)])
+def test_adapt_odd_dims_and_context_lengths(env, hidden, K, M):
+    """obs dims that are not multiples of 4 (Ant 41, Arm 17) with M not a multiple of 4 and K >= 2: the per-task workspace
+    blocks must stay 16-byte aligned for the vectorised loads of the backward chain (a misaligned float4 load faults)."""
+    prob = O.make_problem(env, hidden_sizes=hidden, n_sets=1, m=K, seed=19, out_scale=1.0)
+    eng = make_engine(prob, n_sets=1 + K)
+    theta = prob["param_sets"][0]
+    ctx = O.make_adapt_context(8, prob, K, M)
+    lr = 1e-2
+    want = O.adapt(*ctx, theta, prob["norm"], lr)
+    xs, ts = [], []
+    for o, a, nx in zip(*ctx):
+        xs.append(np.concatenate([O.normalize(o, *prob["norm"]["obs"]), O.normalize(a, *prob["norm"]["act"])], axis=1))
+        ts.append(O.normalize(nx - o, *prob["norm"]["delta"]))
+    eng.adapt(dev(np.stack(xs)), dev(np.stack(ts)), lr, 0, 1)
+    torch.cuda.synchronize()
+    for k in range(K):
+        got = eng.get_params(1 + k)
+        for key in theta.keys():
+            upd = np.abs(want[k][key] - theta[key]).max()
+            np.testing.assert_allclose(got[key], want[k][key], rtol=1e-5, atol=2e-4 * upd + 1e-9)
+
+
 # ------------------------------------------------------------------------------------------------ K1c CEM
 @pytest.mark.parametrize("tag", ["cem_m1", "cem_m2"])
 def test_cem_bug_compatible_matches_reference_golden(golden, tag):
