@@ -145,6 +145,49 @@ int l2a_plan_uses_graph(const l2a_plan* plan);   /* 1 once the call sequence has
 /* the candidate tensor the most recent l2a_plan_run drew, [H, m*N, A] float32, to a HOST buffer (tests / diagnostics) */
 int l2a_plan_copy_candidates(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
 
+/* ---- the general host-buffer planning call ------------------------------------------------------------------------------
+ * l2a_plan_create_ex / l2a_plan_run_ex extend the call above along two axes, still ONE C call and one CUDA-graph replay per
+ * MPCController.get_actions:
+ *  sampler  L2A_SAMPLER_PHILOX   device Philox stream (throughput mode, as l2a_plan_create).
+ *           L2A_SAMPLER_MT19937  the reference's OWN draw (policies/mpc_controller.py:67-69,114: np.random.uniform(low, high,
+ *                                (H*N*m, A)) from numpy's global MT19937 stream), regenerated bit-exactly on the device from the
+ *                                generator state the caller passes in (np.random.get_state(): 624 key words + position);
+ *                                the advanced state is returned for np.random.set_state().  No host RNG, no candidate upload;
+ *                                act_out carries the float64 candidate values the reference would return.
+ *  shard    shard_world > 1: this process rolls candidates [shard_offset, shard_offset + p->n_candidates) of every env's
+ *           n_candidates_total (one process per GPU); the per-env (return, global index, action) records are
+ *           exchanged over peer memory (NVLink) inside the same graph: every rank writes its record into every peer's exchange
+ *           buffer and raises a sequence flag, waits for all flags in its own buffer and selects with np.argmax semantics over
+ *           the concatenated candidates.  With MT19937 every rank regenerates the reference's full stream and materialises
+ *           only its slice, so a seeded G-GPU run returns exactly the single-GPU / reference actions.
+ *           Peer plumbing: l2a_plan_exchange_buffer -> l2a_ipc_get_handle -> (host exchanges the 64-byte handles, e.g.
+ *           torch.distributed.all_gather_object) -> l2a_ipc_open_handle -> l2a_plan_attach_peers.  Every rank must make the
+ *           same sequence of l2a_plan_run_ex calls (collective semantics). */
+enum { L2A_SAMPLER_PHILOX = 0, L2A_SAMPLER_MT19937 = 1 };
+typedef struct {
+  int32_t sampler;              /* L2A_SAMPLER_* */
+  int32_t shard_rank;           /* 0 .. shard_world-1 */
+  int32_t shard_world;          /* <= 1: not sharded */
+  int32_t n_candidates_total;   /* N of the whole job (0 = p->n_candidates) */
+  int64_t shard_offset;         /* global index of this rank's first candidate of every env */
+  uint64_t seed;                /* Philox key (each rank's stream is offset by its rank) */
+} l2a_plan_opts;
+typedef struct {
+  uint32_t* mt_key;             /* in/out HOST uint32[624]: MT19937 key (np.random.get_state()[1])          -- MT19937 only */
+  int32_t* mt_pos;              /* in/out HOST int32:       position in [0, 624] (np.random.get_state()[2]) -- MT19937 only */
+  double* act_out;              /* out HOST float64 [m, A]: chosen first actions */
+  float* ret_out;               /* out HOST float32 [m] or NULL: return of the winner */
+  int64_t* idx_out;             /* out HOST int64 [m] or NULL: global candidate index of the winner */
+} l2a_plan_io;
+int l2a_plan_create_ex(l2a_ctx* ctx, l2a_model* model, const l2a_rollout_params* p, double discount, const double* low,
+                       const double* high, const l2a_plan_opts* opts, l2a_plan** out);
+int l2a_plan_run_ex(l2a_ctx* ctx, l2a_plan* plan, const double* obs, l2a_plan_io* io, void* stream);
+int l2a_plan_exchange_buffer(l2a_plan* plan, void** ptr_out, uint64_t* bytes_out);
+int l2a_plan_attach_peers(l2a_ctx* ctx, l2a_plan* plan, void* const* peer_bufs /* HOST array [shard_world] of device pointers */);
+int l2a_ipc_get_handle(l2a_ctx* ctx, void* dev_ptr, void* handle64_out);
+int l2a_ipc_open_handle(l2a_ctx* ctx, const void* handle64, void** dev_ptr_out);
+int l2a_ipc_close_handle(l2a_ctx* ctx, void* dev_ptr);
+
 /* Candidate sampling alone (DEVICE pointers): out[rows, A] = U[low, high) from Philox4x32-10 keyed by seed, counter =
  * (element block, call_index).  What l2a_plan_run uses internally; the multi-GPU candidate shard calls it with a per-rank seed.
  * Replaces MPCController.get_random_action (policies/mpc_controller.py:67-69) in throughput mode. */

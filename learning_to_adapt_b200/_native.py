@@ -19,7 +19,8 @@ EXPORTS = [
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window",
-    "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_sample_uniform", "l2a_tc_plan_query",
+    "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_create_ex", "l2a_plan_run_ex", "l2a_plan_exchange_buffer",
+    "l2a_plan_attach_peers", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_sample_uniform", "l2a_tc_plan_query",
 ]
 
 
@@ -33,6 +34,19 @@ class RolloutParams(C.Structure):
                 ("first_set", C.c_int32), ("n_sets", C.c_int32), ("reward_kind", C.c_int32), ("dt", C.c_float),
                 ("act_stride_t", C.c_int64), ("act_stride_row", C.c_int64), ("kernel", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+SAMPLER_PHILOX, SAMPLER_MT19937 = 0, 1
+
+
+class PlanOpts(C.Structure):
+    _fields_ = [("sampler", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("n_candidates_total", C.c_int32),
+                ("shard_offset", C.c_int64), ("seed", C.c_uint64)]
+
+
+class PlanIO(C.Structure):
+    _fields_ = [("mt_key", C.c_void_p), ("mt_pos", C.c_void_p), ("act_out", C.c_void_p), ("ret_out", C.c_void_p),
+                ("idx_out", C.c_void_p)]
 
 
 _lib = None
@@ -67,6 +81,13 @@ def load():
     lib.l2a_plan_create.argtypes = [vp, vp, C.POINTER(RolloutParams), f32, vp, vp, C.c_uint64, pp]
     lib.l2a_plan_run.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_plan_destroy.argtypes = [vp, vp]
+    lib.l2a_plan_create_ex.argtypes = [vp, vp, C.POINTER(RolloutParams), f64, vp, vp, C.POINTER(PlanOpts), pp]
+    lib.l2a_plan_run_ex.argtypes = [vp, vp, vp, C.POINTER(PlanIO), vp]
+    lib.l2a_plan_exchange_buffer.argtypes = [vp, pp, C.POINTER(C.c_uint64)]
+    lib.l2a_plan_attach_peers.argtypes = [vp, vp, vp]
+    lib.l2a_ipc_get_handle.argtypes = [vp, vp, vp]
+    lib.l2a_ipc_open_handle.argtypes = [vp, vp, pp]
+    lib.l2a_ipc_close_handle.argtypes = [vp, vp]
     lib.l2a_plan_uses_graph.argtypes = [vp]
     lib.l2a_plan_copy_candidates.argtypes = [vp, vp, vp]
     lib.l2a_tc_plan_query.argtypes = [C.POINTER(MlpDesc), vp]

@@ -14,6 +14,7 @@
 #include "cem.cuh"
 #include "common.cuh"
 #include "debug_tile.cuh"
+#include "mt19937.cuh"
 #include "rollout_simt.cuh"
 #include "rollout_rnn_simt.cuh"
 #include "rollout_rnn_tc.cuh"
@@ -479,28 +480,137 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
 
 
 // --------------------------------------------------------------------------------------------- host-buffer planning call
-// One random-shooting planning call with HOST buffers on both sides (what MPCController.get_actions is to its caller,
-// policies/mpc_controller.py:59-65 + 108-129): H2D(obs, call index) -> Philox candidate sampling -> K1 -> D2H(result).
-// The four stream operations are captured once into a CUDA graph and replayed (one cudaGraphLaunch per call); the pinned
-// input block carries the call index so that every replay draws fresh candidates.
+// One planning call with HOST buffers on both sides (what MPCController.get_actions is to its caller,
+// policies/mpc_controller.py:59-65 + 108-129): H2D(obs, call index, [numpy generator state]) -> candidate sampling (Philox, or
+// numpy's MT19937 stream regenerated on the device) -> K1 -> [candidate-shard exchange with the peer GPUs] -> D2H(result,
+// [advanced generator state]).  The stream operations are captured once into a CUDA graph and replayed (one cudaGraphLaunch
+// per call); everything that changes from call to call travels in the pinned input block.
 struct l2a_plan {
   l2a_model* model = nullptr;
-  l2a_rollout_params p;
-  int D = 0, A = 0;
-  uint64_t seed = 0, calls = 0;
+  l2a_rollout_params p;          // p.n_candidates = this rank's candidates per env
+  l2a_plan_opts o;
+  int D = 0, A = 0, rec = 0;     // rec = doubles per result record: (return, global index, action[A])
+  uint64_t calls = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr;
-  float* in_host = nullptr;        // pinned: obs [m, D] fp32, then the 64-bit call index
-  float* in_dev = nullptr;
-  float* out_host = nullptr;       // pinned: best_ret [m], best_idx [m] (int32), best_act [m, A]
-  float* out_dev = nullptr;
-  float* actions = nullptr;        // [H, m*N, A]
-  float* low = nullptr;            // [A], high [A], discount_pow [H]
+  uint8_t* in_host = nullptr;    // pinned input block (layout: in_* offsets)
+  uint8_t* in_dev = nullptr;
+  uint8_t* out_host = nullptr;   // pinned output block (layout: out_* offsets)
+  uint8_t* out_dev = nullptr;
   size_t in_bytes = 0, out_bytes = 0;
+  size_t in_call = 0, in_key = 0, in_pos = 0;                               // byte offsets inside the input block
+  size_t out_ret = 0, out_idx = 0, out_act = 0, out_rec = 0, out_final = 0, out_key = 0, out_pos = 0;
+  float* actions = nullptr;      // [H, m*N, A]
+  double* act64_t0 = nullptr;    // MT19937: float64 candidates of time step 0, [m*N, A]
+  uint32_t* mt_raw = nullptr;    // MT19937: raw generator blocks
+  long long mt_words = 0;
+  float* consts = nullptr;       // low [A], high [A], discount_pow [H]
+  double* consts64 = nullptr;    // low [A], high - low [A]
+  // candidate shard (o.shard_world > 1): exchange buffer of THIS rank (peers write into it) and the peers' buffers
+  uint8_t* xbuf = nullptr;
+  size_t xbuf_bytes = 0;
+  void** peers_dev = nullptr;    // device array [world] of peer xbuf pointers
+  bool peers_attached = false;
   cudaGraphExec_t exec = nullptr;
   long long graph_epoch = -1;
   bool use_graph = true;
 };
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- candidate-shard exchange over peer memory (NVLink): every rank writes its per-env record into every peer's buffer,
+// raises a sequence flag there (release at system scope), waits for all ranks' flags in its own buffer and selects the winner
+// with np.argmax semantics over the concatenated candidates (max return, NaN wins, ties -> lowest global index).  One CTA.
+// Buffer layout per rank: flags uint64[world] (padded to 256 B) | data [2 parities][world][m][rec] doubles.
+struct ShardXArgs {
+  void* const* peers;            // [world] device pointers to the ranks' exchange buffers (own included)
+  int rank, world, m, rec;
+  const uint32_t* call_index;    // 64-bit call counter in the input block (low word first)
+  const double* mine;            // [m][rec] this rank's records
+  double* final_rec;             // [m][rec] winner per env
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(128) shard_exchange_kernel(const ShardXArgs a) {
+  const int tid = threadIdx.x;
+  const unsigned long long seq = ((unsigned long long)a.call_index[0] | ((unsigned long long)a.call_index[1] << 32)) + 1ull;
+  const int par = (int)(seq & 1ull);
+  const size_t flag_bytes = ((size_t)a.world * 8 + 255) / 256 * 256;
+  const size_t blk = (size_t)a.m * a.rec;                                   // doubles per (parity, rank) block
+  for (int g = 0; g < a.world; ++g) {
+    double* dst = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(a.peers[g]) + flag_bytes) + ((size_t)par * a.world + a.rank) * blk;
+    for (size_t i = tid; i < blk; i += blockDim.x) dst[i] = a.mine[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.world) st_release_sys_u64(reinterpret_cast<unsigned long long*>(a.peers[tid]) + a.rank, seq);
+  if (tid < a.world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(a.peers[a.rank]) + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(f) < seq) {
+      if (clock64() - t0 > 200000000000ll) __trap();                        // ~100 s: a peer never made this call
+    }
+  }
+  __syncthreads();
+  const double* data = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(a.peers[a.rank]) + flag_bytes) + (size_t)par * a.world * blk;
+  for (int e = tid; e < a.m; e += blockDim.x) {
+    int win = 0;
+    double bv = 0.0, bi = 0.0;
+    for (int g = 0; g < a.world; ++g) {
+      const double* r = data + ((size_t)g * a.m + e) * a.rec;
+      const double v = __ldcv(r), idx = __ldcv(r + 1);
+      bool take = (g == 0);
+      if (!take) {
+        const bool nv = (v != v), nb = (bv != bv);
+        if (nv != nb) take = nv;
+        else if (nv) take = idx < bi;
+        else take = (v > bv) || (v == bv && idx < bi);
+      }
+      if (take) { win = g; bv = v; bi = idx; }
+    }
+    const double* r = data + ((size_t)win * a.m + e) * a.rec;
+    for (int j = 0; j < a.rec; ++j) a.final_rec[(size_t)e * a.rec + j] = __ldcv(r + j);
+  }
+}
+
+// per-env result record of this rank: (return, global candidate index, chosen first action in float64)
+__global__ void plan_record_kernel(const float* __restrict__ best_ret, const int* __restrict__ best_idx, const float* __restrict__ best_act,
+                                   const double* __restrict__ act64_t0, long long idx_offset, int n_loc, int m, int A, double* __restrict__ rec_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  double* r = rec_out + (size_t)e * (2 + A);
+  const int bi = best_idx[e];
+  r[0] = (double)best_ret[e];
+  r[1] = (double)((long long)bi + idx_offset);
+  for (int j = 0; j < A; ++j)
+    r[2 + j] = act64_t0 ? act64_t0[((size_t)e * n_loc + bi) * A + j] : (double)best_act[e * A + j];
+}
+
+// MT19937 uniform draw restricted to this rank's slice of the reference tensor [H, m, N_total, A] -> [H, m * n_loc, A]
+__global__ void __launch_bounds__(256) mt19937_uniform_slice_kernel(const uint32_t* __restrict__ raw, const int* __restrict__ pos_in,
+                                                                    const double* __restrict__ low, const double* __restrict__ range,
+                                                                    long long total_loc, int n_total, int lo, int n_loc, int m, int A,
+                                                                    float* __restrict__ actions, double* __restrict__ act64_t0) {
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // destination element
+  if (d >= total_loc) return;
+  const int j = (int)(d % A);
+  const long long row = d / A;                                               // t * (m * n_loc) + env * n_loc + c
+  const int c = (int)(row % n_loc);
+  const long long te = row / n_loc;                                          // t * m + env
+  const long long e = ((te * n_total) + lo + c) * A + j;                     // element of the reference's full tensor
+  const uint32_t* w = raw + pos_in[0] + 2 * e;
+  const double v = __dadd_rn(low[j], __dmul_rn(range[j], mt_double(w[0], w[1])));
+  actions[d] = __double2float_rn(v);
+  if (te < m) act64_t0[d] = v;
+}
 
 extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   if (!pl) return L2A_OK;
@@ -514,34 +624,70 @@ extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   cudaFree(pl->in_dev);
   cudaFree(pl->out_dev);
   cudaFree(pl->actions);
-  cudaFree(pl->low);
+  cudaFree(pl->act64_t0);
+  cudaFree(pl->mt_raw);
+  cudaFree(pl->consts);
+  cudaFree(pl->consts64);
+  cudaFree(pl->xbuf);
+  cudaFree(pl->peers_dev);
   delete pl;
   return L2A_OK;
 }
 
-extern "C" int l2a_plan_create(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p, float discount, const float* low,
-                               const float* high, uint64_t seed, l2a_plan** out) {
-  if (!c || !m || !p || !low || !high || !out) return fail(L2A_ERR_INVALID, "NULL argument");
+extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p, double discount, const double* low,
+                                  const double* high, const l2a_plan_opts* opts, l2a_plan** out) {
+  if (!c || !m || !p || !low || !high || !opts || !out) return fail(L2A_ERR_INVALID, "NULL argument");
   if (p->n_candidates < 1 || p->n_envs < 1 || p->horizon < 1) return fail(L2A_ERR_INVALID, "n_candidates/n_envs/horizon must be >= 1");
+  if (opts->sampler != L2A_SAMPLER_PHILOX && opts->sampler != L2A_SAMPLER_MT19937) return fail(L2A_ERR_INVALID, "sampler %d", opts->sampler);
+  const int world = opts->shard_world < 1 ? 1 : opts->shard_world;
+  if (opts->shard_rank < 0 || opts->shard_rank >= world || world > 64) return fail(L2A_ERR_INVALID, "shard rank %d / world %d", opts->shard_rank, world);
+  const int n_total = opts->n_candidates_total > 0 ? opts->n_candidates_total : p->n_candidates;
+  if (opts->shard_offset < 0 || opts->shard_offset + p->n_candidates > n_total)
+    return fail(L2A_ERR_INVALID, "shard [%lld, %lld) outside the %d candidates", (long long)opts->shard_offset,
+                (long long)opts->shard_offset + p->n_candidates, n_total);
   CUDA_TRY(cudaSetDevice(c->device));
   l2a_plan* pl = new (std::nothrow) l2a_plan();
   if (!pl) return fail(L2A_ERR_INVALID, "out of host memory");
   pl->model = m;
   pl->p = *p;
+  pl->o = *opts;
+  pl->o.shard_world = world;
+  pl->o.n_candidates_total = n_total;
   pl->D = m->dims.obs_dim;
   pl->A = m->dims.act_dim;
-  pl->seed = seed;
-  const int mm = p->n_envs, A = pl->A, H = p->horizon;
+  pl->rec = 2 + pl->A;
+  const int mm = p->n_envs, A = pl->A, H = p->horizon, D = pl->D;
   const long long rows = (long long)p->n_candidates * mm;
   pl->p.act_stride_t = rows * A;                       // the plan owns the candidate tensor: [H, m*N, A] (mpc_controller.py:114)
   pl->p.act_stride_row = A;
-  pl->in_bytes = sizeof(float) * (size_t)mm * pl->D + 8;
-  pl->out_bytes = sizeof(float) * (size_t)mm * (2 + A);
+  const bool mt = opts->sampler == L2A_SAMPLER_MT19937;
+  // input block: obs f32 [m, D] | call index u64 | MT key u32 [624] | MT pos i32
+  size_t off = sizeof(float) * (size_t)mm * D;
+  off = align_up(off, 8);  pl->in_call = off;  off += 8;
+  pl->in_key = off;  off += mt ? sizeof(uint32_t) * kMtN : 0;
+  pl->in_pos = off;  off += mt ? 8 : 0;
+  pl->in_bytes = align_up(off, 16);
+  // output block: best_ret f32 [m] | best_idx i32 [m] | best_act f32 [m, A] | local record f64 [m, rec] | final record f64 [m, rec] |
+  //               MT key u32 [624] | MT pos i32
+  off = 0;
+  pl->out_ret = off;  off += sizeof(float) * mm;
+  pl->out_idx = off;  off += sizeof(int32_t) * mm;
+  pl->out_act = off;  off += sizeof(float) * (size_t)mm * A;
+  off = align_up(off, 8);
+  pl->out_rec = off;  off += sizeof(double) * (size_t)mm * pl->rec;
+  pl->out_final = off;  off += sizeof(double) * (size_t)mm * pl->rec;
+  pl->out_key = off;  off += mt ? sizeof(uint32_t) * kMtN : 0;
+  pl->out_pos = off;  off += mt ? 8 : 0;
+  pl->out_bytes = align_up(off, 16);
   pl->use_graph = getenv("L2A_NO_GRAPH") == nullptr;
   std::vector<float> consts((size_t)2 * A + H);
-  for (int j = 0; j < A; ++j) { consts[j] = low[j]; consts[A + j] = high[j]; }
+  std::vector<double> consts64((size_t)2 * A);
+  for (int j = 0; j < A; ++j) {
+    consts[j] = (float)low[j]; consts[A + j] = (float)high[j];
+    consts64[j] = low[j]; consts64[A + j] = high[j] - low[j];      // numpy: range = high - low in float64 (RandomState.uniform)
+  }
   double pw = 1.0;
-  for (int t = 0; t < H; ++t) { consts[2 * A + t] = (float)pw; pw *= (double)discount; }   // discount**t (mpc_controller.py:126)
+  for (int t = 0; t < H; ++t) { consts[2 * A + t] = (float)pw; pw *= discount; }   // discount**t (mpc_controller.py:126)
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
@@ -550,13 +696,87 @@ extern "C" int l2a_plan_create(l2a_ctx* c, l2a_model* m, const l2a_rollout_param
   if (e == cudaSuccess) e = cudaMalloc(&pl->in_dev, pl->in_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&pl->out_dev, pl->out_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&pl->actions, sizeof(float) * (size_t)H * rows * A);
-  if (e == cudaSuccess) e = cudaMalloc(&pl->low, sizeof(float) * consts.size());
-  if (e == cudaSuccess) e = cudaMemcpy(pl->low, consts.data(), sizeof(float) * consts.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->consts, sizeof(float) * consts.size());
+  if (e == cudaSuccess) e = cudaMemcpy(pl->consts, consts.data(), sizeof(float) * consts.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->consts64, sizeof(double) * consts64.size());
+  if (e == cudaSuccess) e = cudaMemcpy(pl->consts64, consts64.data(), sizeof(double) * consts64.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { memset(pl->in_host, 0, pl->in_bytes); memset(pl->out_host, 0, pl->out_bytes); }
+  if (mt && e == cudaSuccess) {
+    pl->mt_words = 2ll * H * mm * (long long)n_total * A;                 // two 32-bit words per double, the reference's FULL tensor
+    const long long blocks = (pl->mt_words + kMtN) / kMtN + 2;
+    e = cudaMalloc(&pl->mt_raw, sizeof(uint32_t) * (size_t)blocks * kMtN);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->act64_t0, sizeof(double) * (size_t)rows * A);
+  }
+  if (world > 1 && e == cudaSuccess) {
+    pl->xbuf_bytes = align_up((size_t)world * 8, 256) + sizeof(double) * 2 * (size_t)world * mm * pl->rec;
+    e = cudaMalloc(&pl->xbuf, pl->xbuf_bytes);
+    if (e == cudaSuccess) e = cudaMemset(pl->xbuf, 0, pl->xbuf_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->peers_dev, sizeof(void*) * world);
+  }
   if (e != cudaSuccess) {
     l2a_plan_destroy(c, pl);
     return fail(L2A_ERR_CUDA, "l2a_plan_create: %s", cudaGetErrorString(e));
   }
   *out = pl;
+  return L2A_OK;
+}
+
+extern "C" int l2a_plan_create(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p, float discount, const float* low,
+                               const float* high, uint64_t seed, l2a_plan** out) {
+  if (!m || !low || !high) return fail(L2A_ERR_INVALID, "NULL argument");
+  std::vector<double> lo(m->dims.act_dim), hi(m->dims.act_dim);
+  for (int j = 0; j < m->dims.act_dim; ++j) { lo[j] = low[j]; hi[j] = high[j]; }
+  l2a_plan_opts o;
+  memset(&o, 0, sizeof(o));
+  o.sampler = L2A_SAMPLER_PHILOX;
+  o.seed = seed;
+  o.shard_world = 1;
+  return l2a_plan_create_ex(c, m, p, (double)discount, lo.data(), hi.data(), &o, out);
+}
+
+// ---- peer memory plumbing for the candidate shard: the host side exchanges the 64-byte IPC handles of the ranks' exchange
+// buffers (e.g. with torch.distributed.all_gather_object), opens the peers' and hands the pointers to the plan.
+extern "C" int l2a_plan_exchange_buffer(l2a_plan* pl, void** ptr_out, uint64_t* bytes_out) {
+  if (!pl || !ptr_out || !bytes_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  *ptr_out = pl->xbuf;
+  *bytes_out = pl->xbuf_bytes;
+  return L2A_OK;
+}
+extern "C" int l2a_ipc_get_handle(l2a_ctx* c, void* dev_ptr, void* handle64_out) {
+  if (!c || !dev_ptr || !handle64_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64_out, &h, 64);
+  return L2A_OK;
+}
+extern "C" int l2a_ipc_open_handle(l2a_ctx* c, const void* handle64, void** dev_ptr_out) {
+  if (!c || !handle64 || !dev_ptr_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return L2A_OK;
+}
+extern "C" int l2a_ipc_close_handle(l2a_ctx* c, void* dev_ptr) {
+  if (!c || !dev_ptr) return fail(L2A_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return L2A_OK;
+}
+extern "C" int l2a_plan_attach_peers(l2a_ctx* c, l2a_plan* pl, void* const* peer_bufs) {
+  if (!c || !pl || !peer_bufs) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (pl->o.shard_world < 2) return fail(L2A_ERR_INVALID, "the plan is not sharded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<void*> ptrs(pl->o.shard_world);
+  for (int g = 0; g < pl->o.shard_world; ++g) {
+    ptrs[g] = (g == pl->o.shard_rank) ? (void*)pl->xbuf : peer_bufs[g];
+    if (!ptrs[g]) return fail(L2A_ERR_INVALID, "peer buffer %d is NULL", g);
+  }
+  CUDA_TRY(cudaMemcpy(pl->peers_dev, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice));
+  pl->peers_attached = true;
+  if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
   return L2A_OK;
 }
 
@@ -579,27 +799,79 @@ static int plan_enqueue(l2a_ctx* c, l2a_plan* pl) {
   const long long total = (long long)H * pl->p.n_candidates * mm * A;
   cudaStream_t st = pl->stream;
   CUDA_TRY(cudaMemcpyAsync(pl->in_dev, pl->in_host, pl->in_bytes, cudaMemcpyHostToDevice, st));
-  const long long blocks = (total + 4 * 256 - 1) / (4 * 256);
-  sample_uniform_kernel<<<(unsigned)blocks, 256, 0, st>>>(pl->low, pl->low + A, pl->actions, total, A, pl->seed,
-                                                          reinterpret_cast<const uint32_t*>(pl->in_dev + (size_t)mm * pl->D), 0ull);
-  c->launches++;
+  const uint32_t* call_dev = reinterpret_cast<const uint32_t*>(pl->in_dev + pl->in_call);
+  const bool mt = pl->o.sampler == L2A_SAMPLER_MT19937;
+  if (mt) {
+    const uint32_t* key = reinterpret_cast<const uint32_t*>(pl->in_dev + pl->in_key);
+    const int* pos = reinterpret_cast<const int*>(pl->in_dev + pl->in_pos);
+    mt19937_raw_kernel<<<1, 256, 0, st>>>(key, pos, pl->mt_words, pl->mt_raw);
+    c->launches++;
+    const long long blocks = (total + 255) / 256;
+    mt19937_uniform_slice_kernel<<<(unsigned)blocks, 256, 0, st>>>(pl->mt_raw, pos, pl->consts64, pl->consts64 + A, total,
+                                                                  pl->o.n_candidates_total, (int)pl->o.shard_offset, pl->p.n_candidates,
+                                                                  mm, A, pl->actions, pl->act64_t0);
+    c->launches++;
+  } else {
+    const long long blocks = (total + 4 * 256 - 1) / (4 * 256);
+    sample_uniform_kernel<<<(unsigned)blocks, 256, 0, st>>>(pl->consts, pl->consts + A, pl->actions, total, A,
+                                                            pl->o.seed + 0x9E3779B97F4A7C15ull * (uint64_t)pl->o.shard_rank, call_dev, 0ull);
+    c->launches++;
+  }
   CUDA_TRY(cudaGetLastError());
-  float* best_ret = pl->out_dev;
-  int32_t* best_idx = reinterpret_cast<int32_t*>(pl->out_dev + mm);
-  float* best_act = pl->out_dev + 2 * mm;
-  int rc = l2a_rollout(c, pl->model, &pl->p, pl->in_dev, pl->actions, pl->low + 2 * A, nullptr, best_ret, best_idx, best_act, st);
+  float* best_ret = reinterpret_cast<float*>(pl->out_dev + pl->out_ret);
+  int32_t* best_idx = reinterpret_cast<int32_t*>(pl->out_dev + pl->out_idx);
+  float* best_act = reinterpret_cast<float*>(pl->out_dev + pl->out_act);
+  int rc = l2a_rollout(c, pl->model, &pl->p, reinterpret_cast<const float*>(pl->in_dev), pl->actions, pl->consts + 2 * A, nullptr,
+                       best_ret, best_idx, best_act, st);
   if (rc) return rc;
+  double* rec = reinterpret_cast<double*>(pl->out_dev + pl->out_rec);
+  double* fin = reinterpret_cast<double*>(pl->out_dev + pl->out_final);
+  plan_record_kernel<<<(mm + 127) / 128, 128, 0, st>>>(best_ret, best_idx, best_act, mt ? pl->act64_t0 : nullptr, pl->o.shard_offset,
+                                                       pl->p.n_candidates, mm, A, pl->o.shard_world > 1 ? rec : fin);
+  c->launches++;
+  if (pl->o.shard_world > 1) {
+    ShardXArgs xa;
+    xa.peers = pl->peers_dev;
+    xa.rank = pl->o.shard_rank;
+    xa.world = pl->o.shard_world;
+    xa.m = mm;
+    xa.rec = pl->rec;
+    xa.call_index = call_dev;
+    xa.mine = rec;
+    xa.final_rec = fin;
+    shard_exchange_kernel<<<1, 128, 0, st>>>(xa);
+    c->launches++;
+  }
+  if (mt) {
+    mt19937_state_out_kernel<<<1, 256, 0, st>>>(pl->mt_raw, reinterpret_cast<const int*>(pl->in_dev + pl->in_pos), pl->mt_words, nullptr,
+                                                reinterpret_cast<uint32_t*>(pl->out_dev + pl->out_key),
+                                                reinterpret_cast<int*>(pl->out_dev + pl->out_pos));
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(pl->out_host, pl->out_dev, pl->out_bytes, cudaMemcpyDeviceToHost, st));
   return L2A_OK;
 }
 
-extern "C" int l2a_plan_run(l2a_ctx* c, l2a_plan* pl, const double* obs, double* act_out, float* ret_out, int32_t* idx_out,
-                            void* stream) {
-  if (!c || !pl || !obs || !act_out) return fail(L2A_ERR_INVALID, "NULL argument");
+static int plan_launches_per_call(const l2a_plan* pl) {
+  return (pl->o.sampler == L2A_SAMPLER_MT19937 ? 3 : 1) + 2 + (pl->o.shard_world > 1 ? 1 : 0);
+}
+
+extern "C" int l2a_plan_run_ex(l2a_ctx* c, l2a_plan* pl, const double* obs, l2a_plan_io* io, void* stream) {
+  if (!c || !pl || !obs || !io || !io->act_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  const bool mt = pl->o.sampler == L2A_SAMPLER_MT19937;
+  if (mt && (!io->mt_key || !io->mt_pos)) return fail(L2A_ERR_INVALID, "the MT19937 sampler needs the generator state (mt_key, mt_pos)");
+  if (mt && (*io->mt_pos < 0 || *io->mt_pos > kMtN)) return fail(L2A_ERR_INVALID, "mt_pos %d not in [0, 624]", *io->mt_pos);
+  if (pl->o.shard_world > 1 && !pl->peers_attached) return fail(L2A_ERR_INVALID, "sharded plan without peers (l2a_plan_attach_peers)");
   CUDA_TRY(cudaSetDevice(c->device));
   const int mm = pl->p.n_envs, A = pl->A, D = pl->D;
-  for (int i = 0; i < mm * D; ++i) pl->in_host[i] = (float)obs[i];                    // the float32 feed of mlp_dynamics.py:212-214
-  memcpy(pl->in_host + (size_t)mm * D, &pl->calls, 8);
+  float* obs32 = reinterpret_cast<float*>(pl->in_host);
+  for (int i = 0; i < mm * D; ++i) obs32[i] = (float)obs[i];                          // the float32 feed of mlp_dynamics.py:212-214
+  memcpy(pl->in_host + pl->in_call, &pl->calls, 8);
+  if (mt) {
+    memcpy(pl->in_host + pl->in_key, io->mt_key, sizeof(uint32_t) * kMtN);
+    memcpy(pl->in_host + pl->in_pos, io->mt_pos, sizeof(int32_t));
+  }
   // everything the caller queued on its stream (weight uploads, adapt) happens before this call
   CUDA_TRY(cudaEventRecord(pl->ev_in, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->ev_in, 0));
@@ -632,7 +904,7 @@ extern "C" int l2a_plan_run(l2a_ctx* c, l2a_plan* pl, const double* obs, double*
     }
     if (pl->exec) {
       CUDA_TRY(cudaGraphLaunch(pl->exec, pl->stream));
-      c->launches += 2;                                           // sample + K1 per replay
+      c->launches += plan_launches_per_call(pl);
       done = true;
     }
   }
@@ -642,11 +914,33 @@ extern "C" int l2a_plan_run(l2a_ctx* c, l2a_plan* pl, const double* obs, double*
   }
   CUDA_TRY(cudaStreamSynchronize(pl->stream));
   pl->calls++;
-  const float* o = pl->out_host;
-  if (ret_out) memcpy(ret_out, o, sizeof(float) * mm);
-  if (idx_out) memcpy(idx_out, o + mm, sizeof(int32_t) * mm);
-  for (int i = 0; i < mm * A; ++i) act_out[i] = (double)o[2 * mm + i];
+  const double* fin = reinterpret_cast<const double*>(pl->out_host + pl->out_final);
+  for (int e = 0; e < mm; ++e) {
+    if (io->ret_out) io->ret_out[e] = (float)fin[(size_t)e * pl->rec];
+    if (io->idx_out) io->idx_out[e] = (int64_t)fin[(size_t)e * pl->rec + 1];
+    for (int j = 0; j < A; ++j) io->act_out[e * A + j] = fin[(size_t)e * pl->rec + 2 + j];
+  }
+  if (mt) {
+    memcpy(io->mt_key, pl->out_host + pl->out_key, sizeof(uint32_t) * kMtN);
+    memcpy(io->mt_pos, pl->out_host + pl->out_pos, sizeof(int32_t));
+  }
   return L2A_OK;
+}
+
+extern "C" int l2a_plan_run(l2a_ctx* c, l2a_plan* pl, const double* obs, double* act_out, float* ret_out, int32_t* idx_out,
+                            void* stream) {
+  if (!pl || !act_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (pl->o.sampler != L2A_SAMPLER_PHILOX) return fail(L2A_ERR_INVALID, "l2a_plan_run serves Philox plans; use l2a_plan_run_ex");
+  std::vector<int64_t> idx64(pl->p.n_envs);
+  l2a_plan_io io;
+  memset(&io, 0, sizeof(io));
+  io.act_out = act_out;
+  io.ret_out = ret_out;
+  io.idx_out = idx64.data();
+  const int rc = l2a_plan_run_ex(c, pl, obs, &io, stream);
+  if (rc == L2A_OK && idx_out)
+    for (int e = 0; e < pl->p.n_envs; ++e) idx_out[e] = (int32_t)idx64[e];
+  return rc;
 }
 
 extern "C" int l2a_plan_uses_graph(const l2a_plan* pl) { return (pl && pl->exec) ? 1 : 0; }
@@ -1042,9 +1336,9 @@ extern "C" int l2a_debug_pair(l2a_ctx* c, int mode, int iters, int copy_bytes, l
 
 extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long long* cycles_out, void* stream) {
   if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
-  if (mode < 0 || mode > 8 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
+  if (mode < 0 || mode > 10 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
   CUDA_TRY(cudaSetDevice(c->device));
-  const size_t smem = 4 * 16384 + 2 * (size_t)nc * 128 + 64;
+  const size_t smem = 4 * 16384 + 2 * (size_t)nc * 128 + 64 + (mode >= 9 ? 2 * 32768 + 2048 : 0);
   if (nc == 80) {
     CUDA_TRY(cudaFuncSetAttribute(debug_mma_rate_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     debug_mma_rate_kernel<80><<<1, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_out);

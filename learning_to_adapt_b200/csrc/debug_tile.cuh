@@ -179,6 +179,8 @@ namespace l2a {
 //   mode 4: SS with the A-collector keep / reuse hints on the two W_hi passes           -- rollout_tc_kernel, hidden layers
 //   mode 5-8: the output layer's swapped-role shape (M = 128 candidates, N = 32 / 48 features) with / without the hints
 // cycles_out[0] = SM cycles for `iters` pairs.
+__device__ uint8_t g_rate_stream_src[65536];        // source of the concurrent TMA stream of modes 9, 10
+
 template <int NC>
 __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int iters, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t rate_smem[];
@@ -197,6 +199,39 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t idesc = umma::make_idesc_bf16(128, NC);
+  // modes 9 / 10 = mode 4 / mode 0 with a concurrent bulk-copy stream into two further 32 KB stages of this CTA's shared memory
+  // (what the weight ring of the rollout kernel does beside the MMAs): shows whether the MMA operand reads and the TMA fill
+  // writes compete for the shared-memory bandwidth.  cycles_out[2] = 32 KB copies completed while the MMAs ran.
+  __shared__ uint64_t s_bars[2];
+  __shared__ volatile int s_stop;
+  const bool streaming = (mode == 9 || mode == 10);
+  if (streaming) {
+    if (tid == 0) { umma::mbar_init(&s_bars[0], 1); umma::mbar_init(&s_bars[1], 1); umma::fence_barrier_init(); s_stop = 0; }
+    __syncthreads();
+    if (mode == 9) mode = 4; else mode = 0;
+  }
+  if (streaming && warp == 2 && (tid & 31) == 0) {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(bar) + 1024;       // 64 KB behind the probe's own buffers (1024-byte aligned below)
+    dst = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dst) + 1023) & ~(uintptr_t)1023);
+    long long copies = 0;
+    uint32_t ph[2] = {0, 0};
+    umma::mbar_arrive_expect_tx(&s_bars[0], 32768);
+    umma::bulk_g2s(dst, g_rate_stream_src, 32768, &s_bars[0]);
+    umma::mbar_arrive_expect_tx(&s_bars[1], 32768);
+    umma::bulk_g2s(dst + 32768, g_rate_stream_src + 32768, 32768, &s_bars[1]);
+    int sidx = 0;
+    while (!s_stop) {
+      umma::mbar_wait(&s_bars[sidx], ph[sidx]);
+      ph[sidx] ^= 1u;
+      ++copies;
+      umma::mbar_arrive_expect_tx(&s_bars[sidx], 32768);
+      umma::bulk_g2s(dst + sidx * 32768, g_rate_stream_src + sidx * 32768, 32768, &s_bars[sidx]);
+      sidx ^= 1;
+    }
+    umma::mbar_wait(&s_bars[0], ph[0]);
+    umma::mbar_wait(&s_bars[1], ph[1]);
+    cycles_out[2] = copies;
+  }
   if (warp == 1) {
     const uint32_t a0 = umma::desc_lo32(umma::smem_u32(a_tiles)), bh = umma::desc_lo32(umma::smem_u32(b_hi)), bl = umma::desc_lo32(umma::smem_u32(b_lo));
     const uint32_t stage_step = 32768u >> 4, lo_step = 16384u >> 4;
@@ -276,7 +311,7 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
     if (umma::elect_one()) umma::mma_commit(bar);
     __syncwarp();
     umma::mbar_wait(bar, 0);
-    if ((tid & 31) == 0) { cycles_out[0] = clock64() - t0; cycles_out[1] = t_issued - t0; }
+    if ((tid & 31) == 0) { cycles_out[0] = clock64() - t0; cycles_out[1] = t_issued - t0; s_stop = 1; }
   }
   umma::tc_fence_before();
   __syncthreads();

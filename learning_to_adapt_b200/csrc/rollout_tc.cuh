@@ -54,7 +54,15 @@ constexpr int kTcMaxObs = 48;           // obs dim limit of this variant (candid
 #define L2A_TC_EARLY_EPI 1
 #endif
 #ifndef L2A_TC_PIPE_WAIT
-#define L2A_TC_PIPE_WAIT 1
+#define L2A_TC_PIPE_WAIT 0
+#endif
+//  L2A_TC_SPLIT_RING the W_hi and W_lo halves of a ring stage travel separately: two producer threads (warps 4 and 10), one 16 KB
+//                    bulk copy each, own full / empty barriers.  The issuer runs the 8 W_hi MMAs of a pair first and releases
+//                    the W_hi half right after them, so its refill is requested 4 MMAs earlier and has to cover only 16 KB of
+//                    transfer before the next use: the 2-deep ring's refill latency (~860 cycles for 32 KB against 563 of MMA
+//                    time per pair) drops below the MMA time of the stages in between.
+#ifndef L2A_TC_SPLIT_RING
+#define L2A_TC_SPLIT_RING 1
 #endif
 constexpr int kTcXChunk = L2A_TC_EARLY_EPI ? (kTcMaxChunks - 1) : 0;   // activation chunk that holds the layer-0 input
 
@@ -251,7 +259,7 @@ struct TcSmem {
   static constexpr size_t misc_off = stage_off + (size_t)kStages * kStageBytes;
   static size_t total(int D, int A) {
     (void)D; (void)A;
-    size_t misc = sizeof(float) * (5 * (size_t)kTcMaxObs + 2 * (size_t)kTcMaxAct) + 64 /*pad*/ + 32 * sizeof(uint64_t) + 64;
+    size_t misc = sizeof(float) * (5 * (size_t)kTcMaxObs + 2 * (size_t)kTcMaxAct) + 64 /*pad*/ + 40 * sizeof(uint64_t) + 64;
     return misc_off + misc;       // the dynamic shared window is 1024-byte aligned (checked in the kernel)
   }
 };
@@ -291,7 +299,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(n_act_den + kTcMaxAct) + 15) & ~(uintptr_t)15);
   uint64_t* full = bars;                      // [kTcStages]
   uint64_t* empty = bars + kTcStages;         // [kTcStages]
-  uint64_t* layer_full = bars + 2 * kTcStages;
+  uint64_t* full2 = bars + 2 * kTcStages;     // [kTcStages]  W_lo halves (L2A_TC_SPLIT_RING)
+  uint64_t* empty2 = bars + 3 * kTcStages;    // [kTcStages]
+  uint64_t* layer_full = bars + 4 * kTcStages;
   uint64_t* act_ready = layer_full + 1;       // [4]: one barrier per readiness event (source M-block) of a layer's input, so the
                                               // MMA issuer can lag several events behind without mbarrier parity aliasing
   uint64_t* peer_ready = layer_full + 5;
@@ -319,7 +329,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
 
   // ------------------------------------------------------------------ setup
   if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kTcStages; ++s) {
+      umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1);
+      umma::mbar_init(&full2[s], 1); umma::mbar_init(&empty2[s], 1);
+    }
     umma::mbar_init(layer_full, 1);
     for (int j = 0; j < 4; ++j) umma::mbar_init(&act_ready[j], 256);   // epilogue warps + helper warps
     umma::mbar_init(x_ready, 128);
@@ -437,6 +450,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         pair_a = (pair_a + 2) % 3;
       }
     }
+#if L2A_TC_SPLIT_RING
+    else if (warp == 10 && lane == 0) {
+      // ============================================================== second TMA producer: the W_lo half of every ring stage
+      int stage = 0;
+      uint32_t phase = 0;
+      const int out_part2 = 2 * plan.out_n * 128;
+      const int out_nkc = plan.nkc[L - 1];
+      for (int t = 0; t < H; ++t) {
+        for (int pr = 0; pr < plan.stages_per_set; ++pr) {
+          uint32_t bytes = S::kStageBytes;
+          if (pr >= plan.hidden_pairs) bytes = (uint32_t)(min(plan.out_kcs, out_nkc - (pr - plan.hidden_pairs) * plan.out_kcs) * out_part2);
+          const uint32_t bytes_l = bytes > (uint32_t)kTcTileBytes ? bytes - (uint32_t)kTcTileBytes : 0u;
+          umma::mbar_wait(&empty2[stage], phase ^ 1u);
+          if (bytes_l) {
+            umma::mbar_arrive_expect_tx(&full2[stage], bytes_l);
+            umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes + kTcTileBytes, blob + (size_t)pr * S::kStageBytes + kTcTileBytes, bytes_l, &full2[stage]);
+          } else {
+            umma::mbar_arrive(&full2[stage]);
+          }
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+#endif
   } else if (warp == 4) {
     // ================================================================ TMA producer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
@@ -449,6 +486,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         for (int pr = 0; pr < plan.stages_per_set; ++pr) {
           uint32_t bytes = S::kStageBytes;
           if (pr >= plan.hidden_pairs) bytes = (uint32_t)(min(plan.out_kcs, out_nkc - (pr - plan.hidden_pairs) * plan.out_kcs) * out_part2);
+#if L2A_TC_SPLIT_RING
+          if (bytes > (uint32_t)kTcTileBytes) bytes = (uint32_t)kTcTileBytes;       // the W_hi half; warp 10 streams the rest
+#endif
           umma::mbar_wait(&empty[stage], phase ^ 1u);
           umma::mbar_arrive_expect_tx(&full[stage], bytes);
           umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes, blob + (size_t)pr * S::kStageBytes, bytes, &full[stage]);
@@ -472,7 +512,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       // ring protocol of the consumer side: acquire (wait unless a probe already saw the stage full) -> MMAs -> commit -> advance
       auto acquire = [&]() {
         if (!ready) umma::mbar_wait(&full[stage], phase);
+#if L2A_TC_SPLIT_RING
+        umma::mbar_wait(&full2[stage], phase);
+#endif
         umma::tc_fence_after();
+      };
+      // whole stage consumed (elected lane only)
+      auto release = [&]() {
+        umma::mma_commit(&empty[stage]);
+#if L2A_TC_SPLIT_RING
+        umma::mma_commit(&empty2[stage]);
+#endif
       };
       auto probe_next = [&]() {
 #if L2A_TC_PIPE_WAIT
@@ -487,6 +537,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block against activation chunk `ch`
       auto tile_pair = [&](uint32_t d_tmem, int ch, bool first, bool full_k, int nks_last) {
         const uint32_t bh = hi_lo32 + (uint32_t)ch * kChunkStep, bl = lo_lo32 + (uint32_t)ch * kChunkStep;
+#if L2A_TC_SPLIT_RING
+        {
+          const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
+          const int nks = full_k ? 4 : nks_last;
+          // the two W_hi passes of every k-step (W_hi slice read from shared memory once: A-collector keep / reuse) ...
+          umma::mbar_wait(&full[stage], phase);
+          umma::tc_fence_after();
+          if (umma::elect_one()) {
+            if (full_k) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
+                umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              }
+            } else {
+              for (int ks = 0; ks < nks; ++ks) {
+                umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
+                umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              }
+            }
+            umma::mma_commit(&empty[stage]);                 // the W_hi half may be refilled
+          }
+          __syncwarp();
+          // ... then the W_lo * x_hi pass
+          umma::mbar_wait(&full2[stage], phase);
+          umma::tc_fence_after();
+          if (umma::elect_one()) {
+            if (full_k) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+            } else {
+              for (int ks = 0; ks < nks; ++ks) umma::mma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+            }
+            umma::mma_commit(&empty2[stage]);
+          }
+          __syncwarp();
+          advance(false);
+          return;
+        }
+#endif
         acquire();
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         // per 16-wide k-step: W_hi * x_hi, W_hi * x_lo (the W_hi slice is fetched from shared memory once for the two:
@@ -544,7 +634,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
               umma::mma_bf16_ss_lo(d, a_lo + ka, xh + kb, kIdesc, 1u);
             }
           }
-          umma::mma_commit(&empty[stage]);
+          release();
         }
         __syncwarp();
         advance(false);
@@ -657,7 +747,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
                   }
                   umma::mma_bf16_ss_lo(d_out, xl + 2 * ks, wh + 2 * ks, idesc_out, 1u);                             // x_lo * W_hi
                 }
-                if (last_in_stage) umma::mma_commit(&empty[stage]);
+                if (last_in_stage) release();
               }
               __syncwarp();
               if (last_in_stage) {

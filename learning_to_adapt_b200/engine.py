@@ -61,6 +61,8 @@ class PlanningEngine(object):
     # ------------------------------------------------------------------ lifetime
     def close(self):
         for plan in getattr(self, "_plans", {}).values():
+            for peer in plan.get("peers", []):
+                self.lib.l2a_ipc_close_handle(self._ctx, peer)
             self.lib.l2a_plan_destroy(self._ctx, plan["handle"])
         self._plans = {}
         if getattr(self, "_model", None) is not None and self._model:
@@ -170,37 +172,81 @@ class PlanningEngine(object):
 
     # ------------------------------------------------------------------ host-buffer planning call (l2a_plan_*)
     def plan_rs_host(self, observations, n_candidates, horizon, reward_kind, dt, low, high, discount=1.0,
-                     set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO, seed=0):
+                     set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO, seed=0, sampler="philox", shard=None):
         """One random-shooting planning call with HOST arrays on both sides (policies/mpc_controller.py:59-65, 108-129):
-        observations float64 [m, D] -> (actions float64 [m, A], best_ret float32 [m], best_idx int32 [m]).  The candidates
-        are drawn on the device (Philox); after the first call the whole sequence H2D -> sample -> K1 -> D2H is one CUDA
-        graph replay inside libl2a_b200."""
+        observations float64 [m, D] -> (actions float64 [m, A], best_ret float32 [m], best_idx int64 [m]).  ONE C call; after the
+        first call the whole sequence H2D -> sample -> K1 [-> peer exchange] -> D2H is one CUDA graph replay inside libl2a_b200.
+
+        sampler "philox": candidates from the device Philox stream (throughput mode).
+        sampler "mt19937": the reference's own draw, np.random.uniform(low, high, (H*N*m, A)) (:67-69, 114), regenerated on the
+            device from np.random.get_state(); np.random.set_state() then leaves the global stream exactly where the reference
+            would have left it, and the returned actions are the float64 candidates the reference returns.
+        shard: None, or dict(rank, world, all_gather) -- this process rolls its slice of the `n_candidates` of every env and the
+            ranks' winners are exchanged over peer memory inside the call (`all_gather(bytes) -> list of bytes` is only used once,
+            to exchange the IPC handles of the exchange buffers)."""
         obs = np.ascontiguousarray(observations, dtype=np.float64)
         m = obs.shape[0]
         assert obs.shape == (m, self.obs_dim)
-        low32 = np.ascontiguousarray(low, dtype=np.float32)
-        high32 = np.ascontiguousarray(high, dtype=np.float32)
-        assert low32.shape == (self.act_dim,) and high32.shape == (self.act_dim,)
+        low64 = np.ascontiguousarray(low, dtype=np.float64)
+        high64 = np.ascontiguousarray(high, dtype=np.float64)
+        assert low64.shape == (self.act_dim,) and high64.shape == (self.act_dim,)
+        rank, world = (int(shard["rank"]), int(shard["world"])) if shard else (0, 1)
         key = (m, int(n_candidates), int(horizon), int(reward_kind), float(dt), float(discount), int(set_mode), int(first_set),
-               int(n_sets), int(kernel), low32.tobytes(), high32.tobytes(), int(seed))
+               int(n_sets), int(kernel), low64.tobytes(), high64.tobytes(), int(seed), sampler, rank, world)
         plan = self._plans.get(key)
         if plan is None:
+            from .parallel import shard_bounds
+            lo, hi = shard_bounds(n_candidates, rank, world)
             p = N.RolloutParams()
-            p.n_candidates, p.n_envs, p.horizon = int(n_candidates), int(m), int(horizon)
+            p.n_candidates, p.n_envs, p.horizon = int(hi - lo), int(m), int(horizon)
             p.set_mode, p.first_set, p.n_sets = int(set_mode), int(first_set), int(n_sets)
             p.reward_kind, p.dt, p.kernel = int(reward_kind), float(dt), int(kernel)
+            o = N.PlanOpts()
+            o.sampler = {"philox": N.SAMPLER_PHILOX, "mt19937": N.SAMPLER_MT19937}[sampler]
+            o.shard_rank, o.shard_world, o.n_candidates_total, o.shard_offset = rank, world, int(n_candidates), int(lo)
+            o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
             handle = C.c_void_p()
-            N.check(self.lib.l2a_plan_create(self._ctx, self._model, C.byref(p), float(discount),
-                                             low32.ctypes.data_as(C.c_void_p), high32.ctypes.data_as(C.c_void_p),
-                                             C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.byref(handle)))
+            N.check(self.lib.l2a_plan_create_ex(self._ctx, self._model, C.byref(p), float(discount),
+                                                low64.ctypes.data_as(C.c_void_p), high64.ctypes.data_as(C.c_void_p),
+                                                C.byref(o), C.byref(handle)))
             plan = dict(handle=handle, act=np.empty((m, self.act_dim), np.float64), ret=np.empty(m, np.float32),
-                        idx=np.empty(m, np.int32), shape=(int(horizon), int(n_candidates) * m, self.act_dim))
+                        idx=np.empty(m, np.int64), shape=(int(horizon), int(hi - lo) * m, self.act_dim),
+                        key=np.empty(624, np.uint32), pos=C.c_int32(0), io=N.PlanIO(), peers=[])
+            io = plan["io"]
+            io.act_out, io.ret_out, io.idx_out = plan["act"].ctypes.data, plan["ret"].ctypes.data, plan["idx"].ctypes.data
+            io.mt_key, io.mt_pos = plan["key"].ctypes.data, C.addressof(plan["pos"])
+            if world > 1:
+                self._attach_peers(plan, rank, world, shard["all_gather"])
             self._plans[key] = plan
-        N.check(self.lib.l2a_plan_run(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p),
-                                      plan["act"].ctypes.data_as(C.c_void_p), plan["ret"].ctypes.data_as(C.c_void_p),
-                                      plan["idx"].ctypes.data_as(C.c_void_p), _stream()))
+        if sampler == "mt19937":
+            st = np.random.get_state()
+            assert st[0] == "MT19937"
+            plan["key"][:] = st[1]
+            plan["pos"].value = int(st[2])
+        N.check(self.lib.l2a_plan_run_ex(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p), C.byref(plan["io"]), _stream()))
+        if sampler == "mt19937":
+            np.random.set_state(("MT19937", plan["key"], int(plan["pos"].value), st[3], st[4]))
         self._last_plan = plan
         return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy()
+
+    def _attach_peers(self, plan, rank, world, all_gather):
+        """Exchange the CUDA IPC handles of the ranks' exchange buffers once and hand the peers' pointers to the plan."""
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        N.check(self.lib.l2a_plan_exchange_buffer(plan["handle"], C.byref(ptr), C.byref(nbytes)))
+        mine = C.create_string_buffer(64)
+        N.check(self.lib.l2a_ipc_get_handle(self._ctx, ptr, mine))
+        handles = all_gather(mine.raw)
+        assert len(handles) == world
+        ptrs = (C.c_void_p * world)()
+        for g, h in enumerate(handles):
+            if g == rank:
+                ptrs[g] = ptr.value
+                continue
+            peer = C.c_void_p()
+            N.check(self.lib.l2a_ipc_open_handle(self._ctx, C.create_string_buffer(bytes(h), 64), C.byref(peer)))
+            ptrs[g] = peer.value
+            plan["peers"].append(peer)
+        N.check(self.lib.l2a_plan_attach_peers(self._ctx, plan["handle"], ptrs))
 
     def sample_uniform(self, low, high, rows, seed=0, call_index=0, out=None):
         """[rows, A] float32 device tensor of U[low, high) draws (Philox4x32-10, this library's kernel)."""

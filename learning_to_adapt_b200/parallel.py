@@ -60,6 +60,12 @@ class CandidateShard(object):
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
 
+    def all_gather_bytes(self, payload):
+        """Host-side exchange of a small bytes object (the CUDA IPC handles of the plans' exchange buffers; once per plan)."""
+        out = [None] * self.world_size
+        dist.all_gather_object(out, bytes(payload), group=self.group)
+        return out
+
     def all_gather_best(self, packed):
         out = torch.empty((self.world_size * packed.shape[0],) + tuple(packed.shape[1:]), device=packed.device,
                           dtype=packed.dtype)
@@ -86,7 +92,7 @@ class CandidateShard(object):
         act_dim = ctrl.action_space.shape[0]
         lo, hi = shard_bounds(n, self.rank, self.world_size)
         n_loc = hi - lo
-        if ctrl.sampler == "numpy":
+        if ctrl.sampler in ("numpy", "numpy_host"):
             a_full = ctrl.get_random_action(h * n * m).reshape((h, m, n, act_dim))
             a_dev = eng._f32(np.ascontiguousarray(a_full[:, :, lo:hi]).reshape(h, m * n_loc, act_dim))
         else:
@@ -99,7 +105,7 @@ class CandidateShard(object):
                           kernel=ctrl.kernel)
         best_ret, best_idx, best_act = self.combine(res["best_ret"], res["best_idx"], res["best_act"], lo, engine=eng)
         ctrl.last_plan = dict(best_ret=best_ret, best_idx=best_idx, best_act=best_act, returns=None)
-        if ctrl.sampler == "numpy":
+        if ctrl.sampler in ("numpy", "numpy_host"):
             idx = best_idx.cpu().numpy()
             return a_full[0][range(m), idx]
         return best_act.cpu().numpy().astype(np.float64)

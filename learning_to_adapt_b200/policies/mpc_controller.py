@@ -7,12 +7,15 @@ fused kernel call per planning step (random shooting) or per CEM iteration: samp
 fallback.
 
 Candidate sampling
-  sampler="numpy" (default): the reference's own draw from the global numpy MT19937 stream
-      (``np.random.uniform`` :67-69,114 / ``np.random.normal`` :85), uploaded as fp32 -> identical candidates,
-      hence identical chosen actions for a fixed ``np.random.seed`` (parity mode).
-  sampler="device": Philox draws on the GPU -> no host RNG, no H2D of candidates (throughput mode; env var
-      L2A_B200_SAMPLER=device selects it without touching the run scripts).  Random shooting then is ONE host-buffer C call
-      (l2a_plan_run: H2D obs -> sample -> K1 -> D2H action, replayed as a CUDA graph); CEM draws with torch.randn.
+  sampler="numpy" (default): the reference's own draw from the global numpy MT19937 stream (``np.random.uniform`` :67-69,114),
+      regenerated bit-exactly ON THE DEVICE from ``np.random.get_state()`` inside the one host-buffer C call (l2a_plan_run_ex:
+      H2D obs + generator state -> MT19937 -> K1 -> D2H action + advanced state, replayed as a CUDA graph);
+      ``np.random.set_state()`` leaves the global stream where the reference would have left it -> identical candidates, hence
+      identical chosen actions for a fixed ``np.random.seed``, at device speed.  CEM draws ``np.random.normal`` (:85) on the host.
+  sampler="numpy_host": the same stream drawn by numpy on the host and uploaded as fp32 (the round-1 parity path; kept as the
+      cross-check of the device generator).
+  sampler="device": Philox draws on the GPU (throughput mode; env var L2A_B200_SAMPLER=device selects it without touching
+      the run scripts); CEM draws with torch.randn.
 """
 import os
 
@@ -23,6 +26,20 @@ from learning_to_adapt_b200 import _native as N
 from learning_to_adapt_b200.envs.synthetic import reward_kind_of
 from learning_to_adapt_b200.policies.base import Policy
 from learning_to_adapt_b200.utils.serializable import Serializable
+
+
+class _HostArray(np.ndarray):
+    """Host result that also answers the tensor-style accessors of the device-tensor results (``.cpu().numpy()``)."""
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+def _host(a):
+    return np.asarray(a).view(_HostArray)
 
 
 class MPCController(Policy, Serializable):
@@ -41,7 +58,7 @@ class MPCController(Policy, Serializable):
         self.use_reward_model = use_reward_model
         self.alpha = alpha
         self.sampler = sampler or os.environ.get("L2A_B200_SAMPLER", "numpy")
-        assert self.sampler in ("numpy", "device")
+        assert self.sampler in ("numpy", "numpy_host", "device")
         self.cem_compat = cem_compat
         self.kernel = kernel
         self.parallel = parallel          # optional learning_to_adapt_b200.parallel.CandidateShard
@@ -94,11 +111,15 @@ class MPCController(Policy, Serializable):
         eng = self.dynamics_model._engine
         act_dim = self.action_space.shape[0]
         set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
-        if self.sampler == "device" and self.parallel is None:
+        if self.sampler in ("device", "numpy"):
+            shard = None
+            if self.parallel is not None:
+                shard = dict(rank=self.parallel.rank, world=self.parallel.world_size, all_gather=self.parallel.all_gather_bytes)
             acts, ret, idx = eng.plan_rs_host(observations, n, h, self._reward_kind, self._dt, self.action_space.low,
                                               self.action_space.high, discount=self.discount, set_mode=set_mode,
-                                              first_set=first_set, n_sets=n_sets, kernel=self.kernel, seed=self.seed)
-            self.last_plan = dict(best_ret=ret, best_idx=idx, best_act=acts, returns=None)      # host arrays
+                                              first_set=first_set, n_sets=n_sets, kernel=self.kernel, seed=self.seed,
+                                              sampler="philox" if self.sampler == "device" else "mt19937", shard=shard)
+            self.last_plan = dict(best_ret=_host(ret), best_idx=_host(idx), best_act=_host(acts), returns=None)    # host arrays
             return acts
         obs_dev = eng._f32(observations)
         if self.parallel is not None:
@@ -129,7 +150,7 @@ class MPCController(Policy, Serializable):
         obs_dev = eng._f32(observations)
         res = None
         for _ in range(self.num_cem_iters):                                               # :84
-            if self.sampler == "numpy":
+            if self.sampler in ("numpy", "numpy_host"):
                 z = eng._f32(np.random.normal(size=(n, m, ha)))                           # :85
             else:
                 z = torch.randn((n, m, ha), device=eng.device, dtype=torch.float32)

@@ -11,7 +11,7 @@ from learning_to_adapt_b200 import _native as N  # noqa: E402
 lib = N.load()
 ctx = C.c_void_p()
 N.check(lib.l2a_ctx_create(0, C.byref(ctx)))
-out = torch.zeros(2, dtype=torch.int64, device="cuda")
+out = torch.zeros(4, dtype=torch.int64, device="cuda")
 names = {0: "SS (A,B smem)", 1: "TS (A tmem)", 2: "cp only", 3: "cp + TS pipelined", 4: "SS + A keep/reuse",
          5: "out M128 N32 hints", 6: "out M128 N32 plain", 7: "out M128 N48 hints", 8: "out M128 N48 plain"}
 for nc in (64, 80, 128):
@@ -25,3 +25,12 @@ for iters in (1, 2, 3, 4, 8):
     N.check(lib.l2a_debug_mma_rate(ctx, 80, 4, iters, C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     print("NC= 80 SS + hints, %d pair(s) = %2d MMAs: issued after %5d cycles, complete after %5d" % (iters, 12 * iters, out[1].item(), out[0].item()))
+
+# shared-memory bandwidth: the same MMA stream with a concurrent TMA fill of 32 KB stages into the same CTA's shared memory
+for mode, base in ((9, 4), (10, 0)):
+    for _ in range(2):
+        N.check(lib.l2a_debug_mma_rate(ctx, 80, mode, 2000, C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+    cyc, copies = out[0].item(), out[2].item()
+    print("NC= 80 %-20s + concurrent bulk-copy stream: %7.1f cycles / tile pair; %d x 32 KB landed in %d cycles = %.1f B/clk of fill writes"
+          % (names[base], cyc / 2000.0, copies, cyc, copies * 32768.0 / cyc))

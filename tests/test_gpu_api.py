@@ -146,30 +146,47 @@ def _nccl_worker(rank, world, port, q):
         model.set_params(prob["param_sets"][0])
         model.set_normalization(prob["norm"])
         n, h = 301, 5
-        ctrl = MPCController("policy", env, model, n_candidates=n, horizon=h, parallel=CandidateShard())
-        np.random.seed(9)
-        acts, _ = ctrl.get_actions(prob["obs0"])
         cand = O.sample_rs_actions(9, prob["low"], prob["high"], h, n * 2)
         want, best, returns = O.rs_plan(prob["obs0"], cand, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"])
-        ok = np.array_equal(ctrl.last_plan["best_idx"].cpu().numpy(), best) and np.array_equal(acts, want)
+        ok = True
+        # (1) default sampler: the reference stream regenerated on every rank's device, slice rolled per rank, winners exchanged
+        #     over peer memory inside the one C call  (2) the round-1 path: host draw + torch.distributed all-gather
+        for sampler in ("numpy", "numpy_host"):
+            ctrl = MPCController("policy", env, model, n_candidates=n, horizon=h, parallel=CandidateShard(), sampler=sampler)
+            for rep in range(3):                                     # direct call, graph capture, graph replay
+                np.random.seed(9)
+                acts, _ = ctrl.get_actions(prob["obs0"])
+                ok = ok and np.array_equal(np.asarray(ctrl.last_plan["best_idx"].cpu().numpy()), best) and np.array_equal(acts, want)
+        # (3) throughput mode: every rank draws its own Philox slice; all ranks must agree on the (global) winner, and that
+        #     winner's return must be what the oracle computes for its action sequence... checked through rank agreement + bounds
+        ctrl = MPCController("policy", env, model, n_candidates=n, horizon=h, parallel=CandidateShard(), sampler="device", seed=11)
+        for rep in range(3):
+            acts, _ = ctrl.get_actions(prob["obs0"])
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (acts.tobytes(), np.asarray(ctrl.last_plan["best_idx"]).tobytes(),
+                                              np.asarray(ctrl.last_plan["best_ret"]).tobytes()))
+            ok = ok and all(g == gathered[0] for g in gathered)
+            ok = ok and bool(np.all(np.abs(acts) <= 1.0)) and bool(np.all(np.asarray(ctrl.last_plan["best_idx"]) < n))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_nccl_shard_equals_single_gpu_and_reference():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_shard_equals_single_gpu_and_reference(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 1000) + world
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted(q.get(timeout=180) for _ in procs)
+    results = sorted(q.get(timeout=300) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    assert results == [(0, True), (1, True)]
+    assert results == [(r, True) for r in range(world)]
 
 
 # ------------------------------------------------------------------------------------------------ ReBAL
