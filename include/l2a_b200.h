@@ -144,6 +144,8 @@ int l2a_plan_destroy(l2a_ctx* ctx, l2a_plan* plan);
 int l2a_plan_uses_graph(const l2a_plan* plan);   /* 1 once the call sequence has been captured and is being replayed */
 /* the candidate tensor the most recent l2a_plan_run drew, [H, m*N, A] float32, to a HOST buffer (tests / diagnostics) */
 int l2a_plan_copy_candidates(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
+/* CEM plans: the returns [m, N] float32 of the LAST iteration's rollout (what mpc_controller.py:100 holds), to a HOST buffer */
+int l2a_plan_copy_returns(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
 
 /* ---- the general host-buffer planning call ------------------------------------------------------------------------------
  * l2a_plan_create_ex / l2a_plan_run_ex extend the call above along two axes, still ONE C call and one CUDA-graph replay per
@@ -164,6 +166,16 @@ int l2a_plan_copy_candidates(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
  *           torch.distributed.all_gather_object) -> l2a_ipc_open_handle -> l2a_plan_attach_peers.  Every rank must make the
  *           same sequence of l2a_plan_run_ex calls (collective semantics). */
 enum { L2A_SAMPLER_PHILOX = 0, L2A_SAMPLER_MT19937 = 1 };
+/*  planner  L2A_PLANNER_RS   random shooting (policies/mpc_controller.py:108-129).
+ *           L2A_PLANNER_CEM  the cross-entropy planner (:71-106), ALL cem_iters iterations inside the one call / one graph:
+ *                            per iteration  normal draw z [N, m, H*A] (MT19937: numpy's legacy polar Box-Muller stream incl. its
+ *                            cached second value, float64; PHILOX: Box-Muller on the device stream) -> a = mean + z*std, clipped
+ *                            copy (:86-87) -> K1 on the UNclipped samples viewed as (N*m, H, A) (:88-99) -> rank -> elite refit
+ *                            (:101-104; cem_compat != 0 reproduces the reference's rank-mask defect, 0 = true top-k).  mean = 0,
+ *                            std = 1 at the start of every call (:79-80).  act_out = float64 first action of the last iteration's
+ *                            best row (:106).  cem_alpha = 0 gives the RNN controller's variant (rnn_mpc_controller.py:107-108).
+ *                            Not combinable with shard_world > 1. */
+enum { L2A_PLANNER_RS = 0, L2A_PLANNER_CEM = 1 };
 typedef struct {
   int32_t sampler;              /* L2A_SAMPLER_* */
   int32_t shard_rank;           /* 0 .. shard_world-1 */
@@ -171,6 +183,11 @@ typedef struct {
   int32_t n_candidates_total;   /* N of the whole job (0 = p->n_candidates) */
   int64_t shard_offset;         /* global index of this rank's first candidate of every env */
   uint64_t seed;                /* Philox key (each rank's stream is offset by its rank) */
+  int32_t planner;              /* L2A_PLANNER_* */
+  int32_t cem_iters;            /* num_cem_iters */
+  int32_t cem_num_elites;       /* max(int(N * percent_elites), 1) (:78) */
+  int32_t cem_compat;           /* 1 = the reference's elite mask */
+  double cem_alpha;             /* mean' = alpha*mean + (1-alpha)*mean(elites) (:103) */
 } l2a_plan_opts;
 typedef struct {
   uint32_t* mt_key;             /* in/out HOST uint32[624]: MT19937 key (np.random.get_state()[1])          -- MT19937 only */
@@ -178,7 +195,20 @@ typedef struct {
   double* act_out;              /* out HOST float64 [m, A]: chosen first actions */
   float* ret_out;               /* out HOST float32 [m] or NULL: return of the winner */
   int64_t* idx_out;             /* out HOST int64 [m] or NULL: global candidate index of the winner */
+  int32_t* mt_has_gauss;        /* in/out HOST int32:  np.random.get_state()[3] -- MT19937 + CEM only */
+  double* mt_cached;            /* in/out HOST float64: np.random.get_state()[4] -- MT19937 + CEM only */
+  double* cem_mean_out;         /* out HOST float64 [m, H*A] or NULL: CEM mean after the last refit */
+  double* cem_std_out;          /* out HOST float64 [m, H*A] or NULL */
+  int32_t flags;                /* L2A_PLAN_* bits of THIS call (need l2a_plan_attach_window) */
+  int32_t reserved;
 } l2a_plan_io;
+/*  GrBAL env step (samplers/sampler.py:81-91) inside the same call / graph, for a plan with an attached adaptation window:
+ *   L2A_PLAN_ADAPT  before planning: gather the envs' last M transitions from the device window, K2 adapt from weight set
+ *                   src_set into sets dst_first_set.. (= dynamics_model.switch_to_pre_adapt(); dynamics_model.adapt(...)) and
+ *                   re-tile them; the plan's own p->set_mode / first_set say which sets the planner then uses.
+ *   L2A_PLAN_PUSH   after planning: append (observation, chosen action) of every env to the window in float64
+ *                   (running_paths[idx]["observations"/"actions"].append, :109-110); the window's host length mirror follows. */
+enum { L2A_PLAN_ADAPT = 1, L2A_PLAN_PUSH = 2 };
 int l2a_plan_create_ex(l2a_ctx* ctx, l2a_model* model, const l2a_rollout_params* p, double discount, const double* low,
                        const double* high, const l2a_plan_opts* opts, l2a_plan** out);
 int l2a_plan_run_ex(l2a_ctx* ctx, l2a_plan* plan, const double* obs, l2a_plan_io* io, void* stream);
@@ -238,6 +268,8 @@ int l2a_window_length(l2a_ctx* ctx, const l2a_window* w, int env);
 int l2a_window_gather(l2a_ctx* ctx, l2a_window* w, float* x, float* target, void* stream);
 int l2a_adapt_from_window(l2a_ctx* ctx, l2a_model* model, l2a_window* w, float inner_lr, int src_set, int dst_first_set,
                           void* stream);
+/* attach the window to a host-buffer plan (see L2A_PLAN_ADAPT / L2A_PLAN_PUSH): window envs / dims must match the plan's */
+int l2a_plan_attach_window(l2a_ctx* ctx, l2a_plan* plan, l2a_window* w, float inner_lr, int src_set, int dst_first_set);
 
 /* ---- K1c: CEM sampling / refit (policies/mpc_controller.py:84-104) -------------------------------------
  * l2a_cem_sample: a = mean + z*std (:86) -> samples [n, m, H*A] fp32 (rolled out UNclipped, :88-89) and

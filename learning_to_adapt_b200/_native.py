@@ -18,9 +18,9 @@ EXPORTS = [
     "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_debug_pair", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
-    "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window",
+    "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window", "l2a_plan_attach_window",
     "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_create_ex", "l2a_plan_run_ex", "l2a_plan_exchange_buffer",
-    "l2a_plan_attach_peers", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_sample_uniform", "l2a_tc_plan_query",
+    "l2a_plan_attach_peers", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_plan_copy_returns", "l2a_sample_uniform", "l2a_tc_plan_query",
 ]
 
 
@@ -37,16 +37,20 @@ class RolloutParams(C.Structure):
 
 
 SAMPLER_PHILOX, SAMPLER_MT19937 = 0, 1
+PLANNER_RS, PLANNER_CEM = 0, 1
+PLAN_ADAPT, PLAN_PUSH = 1, 2
 
 
 class PlanOpts(C.Structure):
     _fields_ = [("sampler", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("n_candidates_total", C.c_int32),
-                ("shard_offset", C.c_int64), ("seed", C.c_uint64)]
+                ("shard_offset", C.c_int64), ("seed", C.c_uint64), ("planner", C.c_int32), ("cem_iters", C.c_int32),
+                ("cem_num_elites", C.c_int32), ("cem_compat", C.c_int32), ("cem_alpha", C.c_double)]
 
 
 class PlanIO(C.Structure):
     _fields_ = [("mt_key", C.c_void_p), ("mt_pos", C.c_void_p), ("act_out", C.c_void_p), ("ret_out", C.c_void_p),
-                ("idx_out", C.c_void_p)]
+                ("idx_out", C.c_void_p), ("mt_has_gauss", C.c_void_p), ("mt_cached", C.c_void_p), ("cem_mean_out", C.c_void_p),
+                ("cem_std_out", C.c_void_p), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -90,6 +94,7 @@ def load():
     lib.l2a_ipc_close_handle.argtypes = [vp, vp]
     lib.l2a_plan_uses_graph.argtypes = [vp]
     lib.l2a_plan_copy_candidates.argtypes = [vp, vp, vp]
+    lib.l2a_plan_copy_returns.argtypes = [vp, vp, vp]
     lib.l2a_tc_plan_query.argtypes = [C.POINTER(MlpDesc), vp]
     lib.l2a_sample_uniform.argtypes = [vp, vp, vp, vp, i64, i32, C.c_uint64, C.c_uint64, vp]
     lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
@@ -102,6 +107,7 @@ def load():
     lib.l2a_window_length.argtypes = [vp, vp, i32]
     lib.l2a_window_gather.argtypes = [vp, vp, vp, vp, vp]
     lib.l2a_adapt_from_window.argtypes = [vp, vp, vp, f32, i32, i32, vp]
+    lib.l2a_plan_attach_window.argtypes = [vp, vp, vp, f32, i32, i32]
     lib.l2a_cem_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.l2a_cem_refit.argtypes = [vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp]
     lib.l2a_debug_umma_tile.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]

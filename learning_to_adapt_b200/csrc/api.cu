@@ -485,6 +485,14 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
 // numpy's MT19937 stream regenerated on the device) -> K1 -> [candidate-shard exchange with the peer GPUs] -> D2H(result,
 // [advanced generator state]).  The stream operations are captured once into a CUDA graph and replayed (one cudaGraphLaunch
 // per call); everything that changes from call to call travels in the pinned input block.
+struct l2a_window;
+static int adapt_impl(l2a_ctx* c, l2a_model* m, const float* x, const float* target, int K, int M, float inner_lr, int src_set,
+                      int dst_first_set, void* stream);
+static int window_gather_own(l2a_ctx* c, l2a_window* w, const float** x_out, const float** target_out, int* K_out, int* M_out, cudaStream_t st);
+static int window_push_strided(l2a_ctx* c, l2a_window* w, const double* obs, const double* act, int act_stride, bool count_on_host, cudaStream_t st);
+static bool window_matches(const l2a_window* w, int n_envs, int D, int A);
+static void window_count_push(l2a_window* w);
+
 struct l2a_plan {
   l2a_model* model = nullptr;
   l2a_rollout_params p;          // p.n_candidates = this rank's candidates per env
@@ -504,19 +512,48 @@ struct l2a_plan {
   double* act64_t0 = nullptr;    // MT19937: float64 candidates of time step 0, [m*N, A]
   uint32_t* mt_raw = nullptr;    // MT19937: raw generator blocks
   long long mt_words = 0;
-  float* consts = nullptr;       // low [A], high [A], discount_pow [H]
+  float* consts = nullptr;       // low [A], high [A], discount_pow [H], then (CEM) clip_low [H*A], clip_high [H*A]
   double* consts64 = nullptr;    // low [A], high - low [A]
+  // CEM planner state (o.planner == L2A_PLANNER_CEM); `actions` then holds the samples [N, m, H*A]
+  double* z64 = nullptr;         // [N, m, H*A] standard normals
+  double* clipped = nullptr;     // [N, m, H*A] float64 like the reference's a_stacked
+  float* returns = nullptr;      // [m, N]
+  int32_t* rank = nullptr;       // [m, N]
+  double* mean = nullptr;        // [m, H*A], std right behind it
+  double* first64 = nullptr;     // [N*m, A] float64 first actions of the rows
+  uint8_t* gflags = nullptr;     // MT19937 gauss attempts: accept flags, values
+  double* gvals = nullptr;
+  long long attempts = 0;        // attempt budget per iteration
+  uint8_t* mt_scratch = nullptr; // two generator-state blocks (MtStateBlock) + per-iteration meta int[2 * iters]
+  size_t out_mean = 0, out_meta = 0;
+  // GrBAL: adaptation window attached to the plan (l2a_plan_attach_window)
+  l2a_window* window = nullptr;
+  float win_lr = 0.f;
+  int win_src_set = 0, win_dst_first_set = 1;
+  size_t in_obs64 = 0;           // float64 copy of the observations (the window keeps float64 pairs)
+  int cur_flags = 0;             // L2A_PLAN_* flags of the call being enqueued
+  cudaGraphExec_t exec_flags[4] = {nullptr, nullptr, nullptr, nullptr};   // one captured graph per flag combination
   // candidate shard (o.shard_world > 1): exchange buffer of THIS rank (peers write into it) and the peers' buffers
   uint8_t* xbuf = nullptr;
   size_t xbuf_bytes = 0;
   void** peers_dev = nullptr;    // device array [world] of peer xbuf pointers
   bool peers_attached = false;
-  cudaGraphExec_t exec = nullptr;
+  long long calls_flags[4] = {0, 0, 0, 0};
+  int launches_flags[4] = {0, 0, 0, 0};
   long long graph_epoch = -1;
   bool use_graph = true;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// numpy generator state as it travels in the pinned blocks / between CEM iterations on the device
+struct MtStateBlock {
+  uint32_t key[kMtN];
+  int32_t pos;
+  int32_t has_gauss;
+  double cached;
+};
+static_assert(sizeof(MtStateBlock) == 2512, "MtStateBlock layout");
 
 // ---- candidate-shard exchange over peer memory (NVLink): every rank writes its per-env record into every peer's buffer,
 // raises a sequence flag there (release at system scope), waits for all ranks' flags in its own buffer and selects the winner
@@ -616,7 +653,8 @@ extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   if (!pl) return L2A_OK;
   if (c) cudaSetDevice(c->device);
   if (pl->stream) cudaStreamSynchronize(pl->stream);
-  if (pl->exec) cudaGraphExecDestroy(pl->exec);
+  for (int f = 0; f < 4; ++f)
+    if (pl->exec_flags[f]) cudaGraphExecDestroy(pl->exec_flags[f]);
   if (pl->ev_in) cudaEventDestroy(pl->ev_in);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   cudaFreeHost(pl->in_host);
@@ -630,6 +668,15 @@ extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   cudaFree(pl->consts64);
   cudaFree(pl->xbuf);
   cudaFree(pl->peers_dev);
+  cudaFree(pl->z64);
+  cudaFree(pl->clipped);
+  cudaFree(pl->returns);
+  cudaFree(pl->rank);
+  cudaFree(pl->mean);
+  cudaFree(pl->first64);
+  cudaFree(pl->gflags);
+  cudaFree(pl->gvals);
+  cudaFree(pl->mt_scratch);
   delete pl;
   return L2A_OK;
 }
@@ -641,6 +688,12 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
   if (opts->sampler != L2A_SAMPLER_PHILOX && opts->sampler != L2A_SAMPLER_MT19937) return fail(L2A_ERR_INVALID, "sampler %d", opts->sampler);
   const int world = opts->shard_world < 1 ? 1 : opts->shard_world;
   if (opts->shard_rank < 0 || opts->shard_rank >= world || world > 64) return fail(L2A_ERR_INVALID, "shard rank %d / world %d", opts->shard_rank, world);
+  if (opts->planner != L2A_PLANNER_RS && opts->planner != L2A_PLANNER_CEM) return fail(L2A_ERR_INVALID, "planner %d", opts->planner);
+  if (opts->planner == L2A_PLANNER_CEM) {
+    if (world > 1) return fail(L2A_ERR_UNSUPPORTED, "the CEM planner is not sharded across GPUs");
+    if (opts->cem_iters < 1 || opts->cem_num_elites < 1 || opts->cem_num_elites > p->n_candidates)
+      return fail(L2A_ERR_INVALID, "cem_iters %d / cem_num_elites %d", opts->cem_iters, opts->cem_num_elites);
+  }
   const int n_total = opts->n_candidates_total > 0 ? opts->n_candidates_total : p->n_candidates;
   if (opts->shard_offset < 0 || opts->shard_offset + p->n_candidates > n_total)
     return fail(L2A_ERR_INVALID, "shard [%lld, %lld) outside the %d candidates", (long long)opts->shard_offset,
@@ -660,12 +713,16 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
   const long long rows = (long long)p->n_candidates * mm;
   pl->p.act_stride_t = rows * A;                       // the plan owns the candidate tensor: [H, m*N, A] (mpc_controller.py:114)
   pl->p.act_stride_row = A;
+  if (opts->planner == L2A_PLANNER_CEM) {              // CEM: [N, m, H*A] viewed as (N*m, H, A) (:85-89)
+    pl->p.act_stride_t = A;
+    pl->p.act_stride_row = (long long)H * A;
+  }
   const bool mt = opts->sampler == L2A_SAMPLER_MT19937;
   // input block: obs f32 [m, D] | call index u64 | MT key u32 [624] | MT pos i32
   size_t off = sizeof(float) * (size_t)mm * D;
   off = align_up(off, 8);  pl->in_call = off;  off += 8;
-  pl->in_key = off;  off += mt ? sizeof(uint32_t) * kMtN : 0;
-  pl->in_pos = off;  off += mt ? 8 : 0;
+  pl->in_key = off;  pl->in_pos = off + offsetof(MtStateBlock, pos);  off += mt ? sizeof(MtStateBlock) : 0;
+  pl->in_obs64 = off;  off += sizeof(double) * (size_t)mm * D;
   pl->in_bytes = align_up(off, 16);
   // output block: best_ret f32 [m] | best_idx i32 [m] | best_act f32 [m, A] | local record f64 [m, rec] | final record f64 [m, rec] |
   //               MT key u32 [624] | MT pos i32
@@ -676,12 +733,21 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
   off = align_up(off, 8);
   pl->out_rec = off;  off += sizeof(double) * (size_t)mm * pl->rec;
   pl->out_final = off;  off += sizeof(double) * (size_t)mm * pl->rec;
-  pl->out_key = off;  off += mt ? sizeof(uint32_t) * kMtN : 0;
-  pl->out_pos = off;  off += mt ? 8 : 0;
+  pl->out_key = off;  pl->out_pos = off + offsetof(MtStateBlock, pos);  off += mt ? sizeof(MtStateBlock) : 0;
+  const bool cem = opts->planner == L2A_PLANNER_CEM;
+  const int ha = H * A;
+  pl->out_mean = off;  off += cem ? sizeof(double) * 2 * (size_t)mm * ha : 0;
+  pl->out_meta = off;  off += cem ? sizeof(int32_t) * 2 * (size_t)std::max(1, opts->cem_iters) : 0;
   pl->out_bytes = align_up(off, 16);
   pl->use_graph = getenv("L2A_NO_GRAPH") == nullptr;
-  std::vector<float> consts((size_t)2 * A + H);
+  std::vector<float> consts((size_t)2 * A + H + (cem ? 2 * (size_t)ha : 0));
   std::vector<double> consts64((size_t)2 * A);
+  if (cem)
+    for (int t = 0; t < H; ++t)
+      for (int j = 0; j < A; ++j) {                                      // np.concatenate([low] * h) (:81-82)
+        consts[(size_t)2 * A + H + t * A + j] = (float)low[j];
+        consts[(size_t)2 * A + H + ha + t * A + j] = (float)high[j];
+      }
   for (int j = 0; j < A; ++j) {
     consts[j] = (float)low[j]; consts[A + j] = (float)high[j];
     consts64[j] = low[j]; consts64[A + j] = high[j] - low[j];      // numpy: range = high - low in float64 (RandomState.uniform)
@@ -701,7 +767,26 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
   if (e == cudaSuccess) e = cudaMalloc(&pl->consts64, sizeof(double) * consts64.size());
   if (e == cudaSuccess) e = cudaMemcpy(pl->consts64, consts64.data(), sizeof(double) * consts64.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) { memset(pl->in_host, 0, pl->in_bytes); memset(pl->out_host, 0, pl->out_bytes); }
-  if (mt && e == cudaSuccess) {
+  if (cem && e == cudaSuccess) {
+    const size_t tot = (size_t)rows * ha;
+    e = cudaMalloc(&pl->z64, sizeof(double) * tot);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->clipped, sizeof(double) * tot);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->returns, sizeof(float) * (size_t)rows);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->rank, sizeof(int32_t) * (size_t)rows);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->mean, sizeof(double) * 2 * (size_t)mm * ha);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->first64, sizeof(double) * (size_t)rows * A);
+    if (mt && e == cudaSuccess) {
+      const long long pairs = ((long long)tot + 1) / 2;
+      pl->attempts = pairs + pairs * 3 / 10 + 1024;                       // acceptance pi/4: mean 1.273 x pairs, >= 30 sigma of margin
+      pl->mt_words = 4ll * pl->attempts;
+      const long long blocks = (pl->mt_words + kMtN) / kMtN + 2;
+      e = cudaMalloc(&pl->mt_raw, sizeof(uint32_t) * (size_t)blocks * kMtN);
+      if (e == cudaSuccess) e = cudaMalloc(&pl->gflags, (size_t)pl->attempts);
+      if (e == cudaSuccess) e = cudaMalloc(&pl->gvals, sizeof(double) * 2 * (size_t)pl->attempts);
+      if (e == cudaSuccess) e = cudaMalloc(&pl->mt_scratch, 2 * sizeof(MtStateBlock) + 64);
+    }
+  }
+  if (mt && !cem && e == cudaSuccess) {
     pl->mt_words = 2ll * H * mm * (long long)n_total * A;                 // two 32-bit words per double, the reference's FULL tensor
     const long long blocks = (pl->mt_words + kMtN) / kMtN + 2;
     e = cudaMalloc(&pl->mt_raw, sizeof(uint32_t) * (size_t)blocks * kMtN);
@@ -776,7 +861,8 @@ extern "C" int l2a_plan_attach_peers(l2a_ctx* c, l2a_plan* pl, void* const* peer
   }
   CUDA_TRY(cudaMemcpy(pl->peers_dev, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice));
   pl->peers_attached = true;
-  if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+  for (int f = 0; f < 4; ++f)
+    if (pl->exec_flags[f]) { cudaGraphExecDestroy(pl->exec_flags[f]); pl->exec_flags[f] = nullptr; }
   return L2A_OK;
 }
 
@@ -793,12 +879,108 @@ extern "C" int l2a_sample_uniform(l2a_ctx* c, const float* low, const float* hig
   return L2A_OK;
 }
 
-// the stream-ordered body of one planning call (captured into the graph, or issued directly)
+// CEM winner record: (return, candidate index, float64 first action of the winning row of the (N*m, H, A) view)
+__global__ void plan_record_cem_kernel(const float* __restrict__ best_ret, const int* __restrict__ best_idx, const double* __restrict__ first64,
+                                       int n, int m, int A, double* __restrict__ rec_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  double* r = rec_out + (size_t)e * (2 + A);
+  const int bi = best_idx[e];
+  r[0] = (double)best_ret[e];
+  r[1] = (double)bi;
+  for (int j = 0; j < A; ++j) r[2 + j] = first64[((size_t)e * n + bi) * A + j];
+}
+
+static int plan_enqueue_cem(l2a_ctx* c, l2a_plan* pl) {
+  const int mm = pl->p.n_envs, A = pl->A, H = pl->p.horizon, n = pl->p.n_candidates, ha = H * A;
+  const long long tot = (long long)n * mm * ha;
+  cudaStream_t st = pl->stream;
+  const bool mt = pl->o.sampler == L2A_SAMPLER_MT19937;
+  const uint32_t* call_dev = reinterpret_cast<const uint32_t*>(pl->in_dev + pl->in_call);
+  double* mean = pl->mean;
+  double* std_ = pl->mean + (size_t)mm * ha;
+  cem_init_kernel<<<(mm * ha + 255) / 256, 256, 0, st>>>(mean, std_, mm * ha);                       // :79-80
+  c->launches++;
+  float* best_ret = reinterpret_cast<float*>(pl->out_dev + pl->out_ret);
+  int32_t* best_idx = reinterpret_cast<int32_t*>(pl->out_dev + pl->out_idx);
+  float* best_act = reinterpret_cast<float*>(pl->out_dev + pl->out_act);
+  const float* clip_low = pl->consts + 2 * A + H;
+  const float* clip_high = clip_low + ha;
+  const MtStateBlock* state_in = reinterpret_cast<const MtStateBlock*>(pl->in_dev + pl->in_key);
+  MtStateBlock* scratch = reinterpret_cast<MtStateBlock*>(pl->mt_scratch);
+  int32_t* meta_out = reinterpret_cast<int32_t*>(pl->out_dev + pl->out_meta);
+  for (int it = 0; it < pl->o.cem_iters; ++it) {
+    const bool last = (it + 1 == pl->o.cem_iters);
+    if (mt) {
+      // np.random.normal(size=(n, m, h*A)) (:85) continued from where the previous iteration left the generator
+      MtStateBlock* state_out = last ? reinterpret_cast<MtStateBlock*>(pl->out_dev + pl->out_key) : &scratch[it & 1];
+      mt19937_raw_kernel<<<1, 256, 0, st>>>(state_in->key, &state_in->pos, pl->mt_words, pl->mt_raw);
+      mt19937_gauss_kernel<<<(unsigned)((pl->attempts + 255) / 256), 256, 0, st>>>(pl->mt_raw, &state_in->pos, pl->attempts, pl->gflags, pl->gvals);
+      mt19937_gauss_scatter_kernel<<<1, 1024, 0, st>>>(pl->gflags, pl->gvals, pl->attempts, tot, &state_in->has_gauss, &state_in->cached,
+                                                       pl->z64, meta_out + 2 * it, &state_out->cached);
+      mt19937_state_out_kernel<<<1, 256, 0, st>>>(pl->mt_raw, &state_in->pos, 0, meta_out + 2 * it, state_out->key, &state_out->pos);
+      CUDA_TRY(cudaMemcpyAsync(&state_out->has_gauss, meta_out + 2 * it + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      c->launches += 4;
+      state_in = state_out;
+    } else {
+      sample_normal_kernel<<<(unsigned)((tot + 4 * 256 - 1) / (4 * 256)), 256, 0, st>>>(pl->z64, tot, pl->o.seed, call_dev, (uint32_t)it);
+      c->launches++;
+    }
+    const int blocks = (int)std::min<long long>((tot + 255) / 256, (long long)c->num_sms * 8);
+    cem_sample64_kernel<<<blocks, 256, 0, st>>>(pl->z64, mean, std_, clip_low, clip_high, n, mm, ha, A, pl->actions, pl->clipped, pl->first64);   // :86-87
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int rc = l2a_rollout(c, pl->model, &pl->p, reinterpret_cast<const float*>(pl->in_dev), pl->actions, pl->consts + 2 * A, pl->returns,
+                         best_ret, best_idx, best_act, st);                                          // :88-100
+    if (rc) return rc;
+    if (last) {
+      plan_record_cem_kernel<<<(mm + 127) / 128, 128, 0, st>>>(best_ret, best_idx, pl->first64, n, mm, A,
+                                                               reinterpret_cast<double*>(pl->out_dev + pl->out_final));   // :106
+      c->launches++;
+    }
+    dim3 g1((n + 255) / 256, mm);
+    cem_rank_kernel<<<g1, 256, 0, st>>>(pl->returns, n, pl->rank);                                   // :101
+    cem_refit_kernel<double><<<ha, 256, 0, st>>>(pl->rank, pl->clipped, n, mm, ha, pl->o.cem_num_elites, pl->o.cem_alpha, pl->o.cem_compat, mean, std_);   // :102-104
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaMemcpyAsync(pl->out_dev + pl->out_mean, mean, sizeof(double) * 2 * (size_t)mm * ha, cudaMemcpyDeviceToDevice, st));
+  return L2A_OK;
+}
+
+static int plan_enqueue_rs(l2a_ctx* c, l2a_plan* pl);
+
+// the stream-ordered body of one planning call (captured into the graph, or issued directly):
+//   H2D -> [GrBAL: window gather -> K2 adapt -> re-tile]  -> planner (sampling, K1, records)  -> [window push of (obs, action)] -> D2H
 static int plan_enqueue(l2a_ctx* c, l2a_plan* pl) {
+  cudaStream_t st = pl->stream;
+  CUDA_TRY(cudaMemcpyAsync(pl->in_dev, pl->in_host, pl->in_bytes, cudaMemcpyHostToDevice, st));
+  if (pl->cur_flags & L2A_PLAN_ADAPT) {
+    // dynamics_model.switch_to_pre_adapt(); dynamics_model.adapt(obs[-M-1:-1], act[-M-1:-1], obs[-M:])   (samplers/sampler.py:82-90)
+    const float *x = nullptr, *target = nullptr;
+    int K = 0, M = 0;
+    int rc = window_gather_own(c, pl->window, &x, &target, &K, &M, st);
+    if (rc) return rc;
+    rc = adapt_impl(c, pl->model, x, target, K, M, pl->win_lr, pl->win_src_set, pl->win_dst_first_set, st);
+    if (rc) return rc;
+  }
+  int rc = (pl->o.planner == L2A_PLANNER_CEM) ? plan_enqueue_cem(c, pl) : plan_enqueue_rs(c, pl);
+  if (rc) return rc;
+  if (pl->cur_flags & L2A_PLAN_PUSH) {
+    // running_paths[idx]["observations"].append(obs); ["actions"].append(action)   (sampler.py:109-110), float64 like the host lists
+    const double* fin = reinterpret_cast<const double*>(pl->out_dev + pl->out_final);
+    rc = window_push_strided(c, pl->window, reinterpret_cast<const double*>(pl->in_dev + pl->in_obs64), fin + 2, pl->rec,
+                             /*count_on_host=*/false, st);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(pl->out_host, pl->out_dev, pl->out_bytes, cudaMemcpyDeviceToHost, st));
+  return L2A_OK;
+}
+
+static int plan_enqueue_rs(l2a_ctx* c, l2a_plan* pl) {
   const int mm = pl->p.n_envs, A = pl->A, H = pl->p.horizon;
   const long long total = (long long)H * pl->p.n_candidates * mm * A;
   cudaStream_t st = pl->stream;
-  CUDA_TRY(cudaMemcpyAsync(pl->in_dev, pl->in_host, pl->in_bytes, cudaMemcpyHostToDevice, st));
   const uint32_t* call_dev = reinterpret_cast<const uint32_t*>(pl->in_dev + pl->in_call);
   const bool mt = pl->o.sampler == L2A_SAMPLER_MT19937;
   if (mt) {
@@ -849,12 +1031,7 @@ static int plan_enqueue(l2a_ctx* c, l2a_plan* pl) {
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(pl->out_host, pl->out_dev, pl->out_bytes, cudaMemcpyDeviceToHost, st));
   return L2A_OK;
-}
-
-static int plan_launches_per_call(const l2a_plan* pl) {
-  return (pl->o.sampler == L2A_SAMPLER_MT19937 ? 3 : 1) + 2 + (pl->o.shard_world > 1 ? 1 : 0);
 }
 
 extern "C" int l2a_plan_run_ex(l2a_ctx* c, l2a_plan* pl, const double* obs, l2a_plan_io* io, void* stream) {
@@ -868,21 +1045,35 @@ extern "C" int l2a_plan_run_ex(l2a_ctx* c, l2a_plan* pl, const double* obs, l2a_
   float* obs32 = reinterpret_cast<float*>(pl->in_host);
   for (int i = 0; i < mm * D; ++i) obs32[i] = (float)obs[i];                          // the float32 feed of mlp_dynamics.py:212-214
   memcpy(pl->in_host + pl->in_call, &pl->calls, 8);
+  const bool cem = pl->o.planner == L2A_PLANNER_CEM;
+  if (mt && cem && (!io->mt_has_gauss || !io->mt_cached)) return fail(L2A_ERR_INVALID, "MT19937 + CEM needs mt_has_gauss / mt_cached");
   if (mt) {
-    memcpy(pl->in_host + pl->in_key, io->mt_key, sizeof(uint32_t) * kMtN);
-    memcpy(pl->in_host + pl->in_pos, io->mt_pos, sizeof(int32_t));
+    MtStateBlock* sb = reinterpret_cast<MtStateBlock*>(pl->in_host + pl->in_key);
+    memcpy(sb->key, io->mt_key, sizeof(uint32_t) * kMtN);
+    sb->pos = *io->mt_pos;
+    sb->has_gauss = cem ? *io->mt_has_gauss : 0;
+    sb->cached = cem ? *io->mt_cached : 0.0;
   }
+  const int flags = io->flags & 3;
+  if (flags && !pl->window) return fail(L2A_ERR_INVALID, "flags %d need an attached adaptation window (l2a_plan_attach_window)", flags);
+  if (flags) {
+    double* o64 = reinterpret_cast<double*>(pl->in_host + pl->in_obs64);
+    for (int i = 0; i < mm * D; ++i) o64[i] = obs[i];
+  }
+  pl->cur_flags = flags;
   // everything the caller queued on its stream (weight uploads, adapt) happens before this call
   CUDA_TRY(cudaEventRecord(pl->ev_in, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->ev_in, 0));
   bool done = false;
-  if (pl->use_graph && pl->calls > 0) {
-    if (pl->exec && pl->graph_epoch != c->ws_epoch) {             // a workspace the graph points into was reallocated
-      cudaGraphExecDestroy(pl->exec);
-      pl->exec = nullptr;
-    }
-    if (!pl->exec) {
-      // (the first call ran uncaptured and sized every workspace, so no allocation happens inside the capture)
+  cudaGraphExec_t& exec = pl->exec_flags[flags];
+  if (pl->graph_epoch != c->ws_epoch) {                           // a workspace the graphs point into was reallocated
+    for (int f = 0; f < 4; ++f)
+      if (pl->exec_flags[f]) { cudaGraphExecDestroy(pl->exec_flags[f]); pl->exec_flags[f] = nullptr; }
+    pl->graph_epoch = c->ws_epoch;
+  }
+  if (pl->use_graph && pl->calls_flags[flags] > 0) {
+    if (!exec) {
+      // (the first call with these flags ran uncaptured and sized every workspace, so no allocation happens inside the capture)
       cudaGraph_t g = nullptr;
       const long long launches0 = c->launches, epoch0 = c->ws_epoch;
       cudaError_t e = cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal);
@@ -891,27 +1082,29 @@ extern "C" int l2a_plan_run_ex(l2a_ctx* c, l2a_plan* pl, const double* obs, l2a_
         rc = plan_enqueue(c, pl);
         e = cudaStreamEndCapture(pl->stream, &g);
       }
+      pl->launches_flags[flags] = (int)(c->launches - launches0);
       c->launches = launches0;
-      if (e == cudaSuccess && rc == L2A_OK && g && c->ws_epoch == epoch0) e = cudaGraphInstantiate(&pl->exec, g, 0);
+      if (e == cudaSuccess && rc == L2A_OK && g && c->ws_epoch == epoch0) e = cudaGraphInstantiate(&exec, g, 0);
       if (g) cudaGraphDestroy(g);
-      if (e != cudaSuccess || rc != L2A_OK || !pl->exec || c->ws_epoch != epoch0) {
-        if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+      if (e != cudaSuccess || rc != L2A_OK || !exec || c->ws_epoch != epoch0) {
+        if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
         cudaGetLastError();
         pl->use_graph = false;                                    // direct launches from now on (same kernels)
-      } else {
-        pl->graph_epoch = c->ws_epoch;
       }
     }
-    if (pl->exec) {
-      CUDA_TRY(cudaGraphLaunch(pl->exec, pl->stream));
-      c->launches += plan_launches_per_call(pl);
+    if (exec) {
+      CUDA_TRY(cudaGraphLaunch(exec, pl->stream));
+      c->launches += pl->launches_flags[flags];
       done = true;
     }
   }
   if (!done) {
     int rc = plan_enqueue(c, pl);
     if (rc) return rc;
+    pl->graph_epoch = c->ws_epoch;
   }
+  pl->calls_flags[flags]++;
+  if (flags & L2A_PLAN_PUSH) window_count_push(pl->window);
   CUDA_TRY(cudaStreamSynchronize(pl->stream));
   pl->calls++;
   const double* fin = reinterpret_cast<const double*>(pl->out_host + pl->out_final);
@@ -920,9 +1113,23 @@ extern "C" int l2a_plan_run_ex(l2a_ctx* c, l2a_plan* pl, const double* obs, l2a_
     if (io->idx_out) io->idx_out[e] = (int64_t)fin[(size_t)e * pl->rec + 1];
     for (int j = 0; j < A; ++j) io->act_out[e * A + j] = fin[(size_t)e * pl->rec + 2 + j];
   }
+  if (cem && mt) {
+    const int32_t* meta = reinterpret_cast<const int32_t*>(pl->out_host + pl->out_meta);
+    for (int it = 0; it < pl->o.cem_iters; ++it)
+      if (meta[2 * it] < 0)
+        return fail(L2A_ERR_UNSUPPORTED, "CEM iteration %d: the normal draw needed more than %lld polar-method attempts", it, pl->attempts);
+  }
   if (mt) {
-    memcpy(io->mt_key, pl->out_host + pl->out_key, sizeof(uint32_t) * kMtN);
-    memcpy(io->mt_pos, pl->out_host + pl->out_pos, sizeof(int32_t));
+    const MtStateBlock* sb = reinterpret_cast<const MtStateBlock*>(pl->out_host + pl->out_key);
+    memcpy(io->mt_key, sb->key, sizeof(uint32_t) * kMtN);
+    *io->mt_pos = sb->pos;
+    if (cem) { *io->mt_has_gauss = sb->has_gauss; *io->mt_cached = sb->cached; }
+  }
+  if (cem) {
+    const size_t cnt = (size_t)mm * pl->p.horizon * A;
+    const double* ms = reinterpret_cast<const double*>(pl->out_host + pl->out_mean);
+    if (io->cem_mean_out) memcpy(io->cem_mean_out, ms, sizeof(double) * cnt);
+    if (io->cem_std_out) memcpy(io->cem_std_out, ms + cnt, sizeof(double) * cnt);
   }
   return L2A_OK;
 }
@@ -943,7 +1150,21 @@ extern "C" int l2a_plan_run(l2a_ctx* c, l2a_plan* pl, const double* obs, double*
   return rc;
 }
 
-extern "C" int l2a_plan_uses_graph(const l2a_plan* pl) { return (pl && pl->exec) ? 1 : 0; }
+extern "C" int l2a_plan_uses_graph(const l2a_plan* pl) {
+  if (!pl) return 0;
+  for (int f = 0; f < 4; ++f)
+    if (pl->exec_flags[f]) return 1;
+  return 0;
+}
+
+extern "C" int l2a_plan_copy_returns(l2a_ctx* c, l2a_plan* pl, float* host_out) {
+  if (!c || !pl || !host_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!pl->returns) return fail(L2A_ERR_INVALID, "this plan keeps no per-candidate returns (random-shooting plans reduce them on the fly)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(pl->stream));
+  CUDA_TRY(cudaMemcpy(host_out, pl->returns, sizeof(float) * (size_t)pl->p.n_candidates * pl->p.n_envs, cudaMemcpyDeviceToHost));
+  return L2A_OK;
+}
 
 extern "C" int l2a_plan_copy_candidates(l2a_ctx* c, l2a_plan* pl, float* host_out) {
   if (!c || !pl || !host_out) return fail(L2A_ERR_INVALID, "NULL argument");
@@ -1171,7 +1392,7 @@ extern "C" int l2a_window_set_normalization(l2a_ctx* c, l2a_window* w, const dou
 extern "C" int l2a_window_push(l2a_ctx* c, l2a_window* w, const double* obs, const double* act, void* stream) {
   if (!c || !w || !obs || !act) return fail(L2A_ERR_INVALID, "NULL argument");
   CUDA_TRY(cudaSetDevice(c->device));
-  window_push_kernel<<<w->dev.n_envs, 64, 0, (cudaStream_t)stream>>>(w->dev, obs, act);
+  window_push_kernel<<<w->dev.n_envs, 64, 0, (cudaStream_t)stream>>>(w->dev, obs, act, w->dev.A);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   for (int& l : w->length) l += 1;
@@ -1219,6 +1440,45 @@ extern "C" int l2a_adapt_from_window(l2a_ctx* c, l2a_model* m, l2a_window* w, fl
   return adapt_impl(c, m, w->x, w->target, w->dev.n_envs, w->M, inner_lr, src_set, dst_first_set, stream);
 }
 
+// ---- helpers of the host-buffer planning call (GrBAL step inside the plan's graph)
+static bool window_matches(const l2a_window* w, int n_envs, int D, int A) {
+  return w && w->dev.n_envs == n_envs && w->dev.D == D && w->dev.A == A;
+}
+static void window_count_push(l2a_window* w) {
+  for (int& l : w->length) l += 1;
+}
+static int window_gather_own(l2a_ctx* c, l2a_window* w, const float** x_out, const float** target_out, int* K_out, int* M_out, cudaStream_t st) {
+  const int rc = l2a_window_gather(c, w, w->x, w->target, st);
+  if (rc != L2A_OK) return rc;
+  *x_out = w->x;
+  *target_out = w->target;
+  *K_out = w->dev.n_envs;
+  *M_out = w->M;
+  return L2A_OK;
+}
+static int window_push_strided(l2a_ctx* c, l2a_window* w, const double* obs, const double* act, int act_stride, bool count_on_host, cudaStream_t st) {
+  window_push_kernel<<<w->dev.n_envs, 64, 0, st>>>(w->dev, obs, act, act_stride);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  if (count_on_host)
+    for (int& l : w->length) l += 1;
+  return L2A_OK;
+}
+
+extern "C" int l2a_plan_attach_window(l2a_ctx* c, l2a_plan* pl, l2a_window* w, float inner_lr, int src_set, int dst_first_set) {
+  if (!c || !pl || !w) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (!window_matches(w, pl->p.n_envs, pl->D, pl->A))
+    return fail(L2A_ERR_INVALID, "window (envs %d, dims %d/%d) does not match the plan (envs %d, dims %d/%d)", w->dev.n_envs, w->dev.D,
+                w->dev.A, pl->p.n_envs, pl->D, pl->A);
+  pl->window = w;
+  pl->win_lr = inner_lr;
+  pl->win_src_set = src_set;
+  pl->win_dst_first_set = dst_first_set;
+  for (int f = 1; f < 4; ++f)
+    if (pl->exec_flags[f]) { cudaGraphExecDestroy(pl->exec_flags[f]); pl->exec_flags[f] = nullptr; }
+  return L2A_OK;
+}
+
 extern "C" int l2a_cem_sample(l2a_ctx* c, const float* z, const double* mean, const double* std_, const float* clip_low,
                               const float* clip_high, int n, int m, int ha, float* samples, float* clipped, void* stream) {
   if (!c || !z || !mean || !std_ || !clip_low || !clip_high || !samples || !clipped) return fail(L2A_ERR_INVALID, "NULL argument");
@@ -1242,7 +1502,7 @@ extern "C" int l2a_cem_refit(l2a_ctx* c, const float* returns, const float* clip
   cem_rank_kernel<<<g1, 256, 0, st>>>(returns, n, rank_scratch);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
-  cem_refit_kernel<<<ha, 256, 0, st>>>(rank_scratch, clipped, n, m, ha, num_elites, alpha, compat, mean, std_);
+  cem_refit_kernel<float><<<ha, 256, 0, st>>>(rank_scratch, clipped, n, m, ha, num_elites, alpha, compat, mean, std_);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return L2A_OK;
@@ -1336,9 +1596,9 @@ extern "C" int l2a_debug_pair(l2a_ctx* c, int mode, int iters, int copy_bytes, l
 
 extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long long* cycles_out, void* stream) {
   if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
-  if (mode < 0 || mode > 10 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
+  if (mode < 0 || mode > 15 || iters < 1) return fail(L2A_ERR_INVALID, "bad mode/iters");
   CUDA_TRY(cudaSetDevice(c->device));
-  const size_t smem = 4 * 16384 + 2 * (size_t)nc * 128 + 64 + (mode >= 9 ? 2 * 32768 + 2048 : 0);
+  const size_t smem = 4 * 16384 + 2 * (size_t)nc * 128 + 64 + ((mode == 9 || mode == 10) ? 2 * 32768 + 2048 : 0);
   if (nc == 80) {
     CUDA_TRY(cudaFuncSetAttribute(debug_mma_rate_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     debug_mma_rate_kernel<80><<<1, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_out);

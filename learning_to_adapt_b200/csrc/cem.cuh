@@ -21,6 +21,29 @@ __global__ void cem_sample_kernel(const float* __restrict__ z, const double* __r
   }
 }
 
+// The same with float64 draws (the host-buffer planning call keeps numpy's float64 normals): additionally writes the float64
+// first action of every row, first64[row][A] with row = flat index / (H*A) of the (n*m, H, A) view -- the value the reference
+// returns for the winning row (mpc_controller.py:94, 106: cand_a from the UNclipped float64 samples).
+__global__ void cem_sample64_kernel(const double* __restrict__ z, const double* __restrict__ mean, const double* __restrict__ std_,
+                                    const float* __restrict__ clip_low, const float* __restrict__ clip_high, int n, int m, int ha, int A,
+                                    float* __restrict__ samples, double* __restrict__ clipped, double* __restrict__ first64) {
+  const long long total = (long long)n * m * ha;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % ha);
+    const int e = (int)((i / ha) % m);
+    const double a = __dadd_rn(mean[e * ha + j], __dmul_rn(z[i], std_[e * ha + j]));       // mean + z * std (:86), no FMA
+    samples[i] = (float)a;
+    clipped[i] = fmin(fmax(a, (double)clip_low[j]), (double)clip_high[j]);      // np.clip of the float64 samples (:87)
+    if (j < A) first64[(i / ha) * A + j] = a;
+  }
+}
+
+// mean = 0, std = 1 (:79-80) at the start of every planning call
+__global__ void cem_init_kernel(double* __restrict__ mean, double* __restrict__ std_, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) { mean[i] = 0.0; std_[i] = 1.0; }
+}
+
 // rank[e][c] = position of candidate c in the descending-return order of env e (= np.argsort(-returns) inverse).
 // Ties: the lower index ranks first.  grid = (ceil(n/256), m).
 __global__ void cem_rank_kernel(const float* __restrict__ returns, int n, int* __restrict__ rank) {
@@ -42,7 +65,8 @@ __global__ void cem_rank_kernel(const float* __restrict__ returns, int n, int* _
 //    candidates 0..k-1: rows {rank[e][c] : c < k}; pooled over envs (:102).
 //  compat == 0: rows {c : rank[e][c] < k} (true top-k).
 // mean' = alpha*mean + (1-alpha)*mean(elites) (:103), std' = std(elites) (ddof 0, :104), broadcast to all envs.
-__global__ void cem_refit_kernel(const int* __restrict__ rank, const float* __restrict__ clipped, int n, int m, int ha, int k,
+template <typename T>
+__global__ void cem_refit_kernel(const int* __restrict__ rank, const T* __restrict__ clipped, int n, int m, int ha, int k,
                                  double alpha, int compat, double* __restrict__ mean, double* __restrict__ std_) {
   const int j = blockIdx.x;
   __shared__ double s_sum[256];

@@ -204,6 +204,41 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
   // writes compete for the shared-memory bandwidth.  cycles_out[2] = 32 KB copies completed while the MMAs ran.
   __shared__ uint64_t s_bars[2];
   __shared__ volatile int s_stop;
+  // modes 11-13 = mode 4 with the per-pair handshake instructions of the rollout kernel's issuer on always-satisfied barriers:
+  //   11: mbarrier wait + tcgen05.fence::after before the 12 MMAs and tcgen05.commit after them   12: commit only   13: wait + fence only
+  // modes 14, 15 = mode 4 fed by a REAL 2 x 32 KB weight ring (producer thread in warp 2 streaming g_rate_stream_src, full / empty
+  //   mbarriers, one commit per pair = the rollout kernel's hidden-layer loop in isolation); 15 = W_hi / W_lo halves with their own
+  //   barriers and two producer threads (L2A_TC_SPLIT_RING).
+  __shared__ uint64_t s_ring[8];                      // full[2], empty[2], full2[2], empty2[2]
+  __shared__ uint64_t s_dummy[2];                     // [0]: never arrived (parity 1 is always complete), [1]: commit sink
+  const int hs_mode = (mode >= 11 && mode <= 13) ? mode : 0;
+  const int ring_mode = (mode == 14 || mode == 15) ? mode : 0;
+  if (hs_mode || ring_mode) {
+    if (tid == 0) {
+      for (int i = 0; i < 8; ++i) umma::mbar_init(&s_ring[i], 1);
+      umma::mbar_init(&s_dummy[0], 1);
+      umma::mbar_init(&s_dummy[1], 1);
+      umma::fence_barrier_init();
+    }
+    __syncthreads();
+    mode = 4;
+  }
+  if (ring_mode && (warp == 2 || (warp == 3 && ring_mode == 15)) && (tid & 31) == 0) {
+    // producer(s): stage s of the ring IS a_tiles + s * 32 KB (the MMA operands themselves)
+    const bool second = (warp == 3);
+    uint64_t* fullb = second ? &s_ring[4] : &s_ring[0];
+    uint64_t* emptyb = second ? &s_ring[6] : &s_ring[2];
+    const uint32_t bytes = (ring_mode == 15) ? 16384u : 32768u;
+    const uint32_t off = second ? 16384u : 0u;
+    uint32_t phase = 0;
+    int st = 0;
+    for (int it = 0; it < iters; ++it) {
+      umma::mbar_wait(&emptyb[st], phase ^ 1u);
+      umma::mbar_arrive_expect_tx(&fullb[st], bytes);
+      umma::bulk_g2s(a_tiles + st * 32768 + off, g_rate_stream_src + st * 32768 + off, bytes, &fullb[st]);
+      if (++st == 2) { st = 0; phase ^= 1u; }
+    }
+  }
   const bool streaming = (mode == 9 || mode == 10);
   if (streaming) {
     if (tid == 0) { umma::mbar_init(&s_bars[0], 1); umma::mbar_init(&s_bars[1], 1); umma::fence_barrier_init(); s_stop = 0; }
@@ -249,6 +284,8 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
       const uint32_t st = (uint32_t)(it & 1);
       const uint32_t a_hi = a0 + st * stage_step, a_lo = a_hi + lo_step;
       const uint32_t d = tmem_base + (uint32_t)((it & 3) * NC);
+      if (hs_mode == 11 || hs_mode == 13) { umma::mbar_wait(&s_dummy[0], 1u); umma::tc_fence_after(); }
+      if (ring_mode) { umma::mbar_wait(&s_ring[st], (uint32_t)((it >> 1) & 1)); umma::tc_fence_after(); }
       if (umma::elect_one()) {
         if (mode == 0) {
 #pragma unroll
@@ -257,7 +294,7 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
             umma::mma_bf16_ss_lo(d, a_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
             umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
           }
-        } else if (mode == 4) {
+        } else if (mode == 4 && ring_mode != 15) {
           // SS with A-collector hints: W_hi is read from shared memory once for its two passes
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -265,6 +302,16 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
             umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
             umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
           }
+          if (hs_mode == 11 || hs_mode == 12) umma::mma_commit(&s_dummy[1]);
+          if (ring_mode == 14) umma::mma_commit(&s_ring[2 + st]);
+        } else if (mode == 4) {
+          // split ring: the two W_hi passes, release the W_hi half, then (below, after the W_lo wait) the W_lo pass
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma::mma_bf16_ss_lo_hint<umma::kAKeep>(d, a_hi + 2 * ks, bh + 2 * ks, idesc, 1u);
+            umma::mma_bf16_ss_lo_hint<umma::kAReuse>(d, a_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
+          }
+          umma::mma_commit(&s_ring[2 + st]);
         } else if (mode >= 5 && mode <= 8) {
           // output-layer shape (roles swapped): M = 128 candidates (A = a 16 KB activation chunk), N = 32 (modes 5, 6) or
           // 48 (modes 7, 8) features; odd modes with the A-collector hints, even modes without
@@ -306,6 +353,16 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(int mode, int it
         }
       }
       __syncwarp();
+      if (ring_mode == 15) {
+        umma::mbar_wait(&s_ring[4 + st], (uint32_t)((it >> 1) & 1));
+        umma::tc_fence_after();
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ss_lo(d, a_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
+          umma::mma_commit(&s_ring[6 + st]);
+        }
+        __syncwarp();
+      }
     }
     const long long t_issued = clock64();             // every MMA has been accepted by the tensor pipe's queue
     if (umma::elect_one()) umma::mma_commit(bar);

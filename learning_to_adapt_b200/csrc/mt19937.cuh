@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) mt19937_gauss_kernel(const uint32_t* __re
 __global__ void __launch_bounds__(1024, 1) mt19937_gauss_scatter_kernel(const uint8_t* __restrict__ flags, const double* __restrict__ vals,
                                                                         long long n_attempts, long long n_normals,
                                                                         const int* __restrict__ gauss_in, const double* __restrict__ cached_in,
-                                                                        float* __restrict__ z_out, int* __restrict__ meta_out,
+                                                                        double* __restrict__ z_out, int* __restrict__ meta_out,
                                                                         double* __restrict__ cached_out) {
   __shared__ int warp_sums[32];
   __shared__ long long s_base;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(1024, 1) mt19937_gauss_scatter_kernel(const ui
   const long long need = n_normals - carry;                  // normals to draw from fresh attempts
   const long long pairs_needed = (need + 1) / 2;
   if (tid == 0) { s_base = 0; s_consumed = (pairs_needed == 0) ? 0 : -1; }
-  if (carry && tid == 0 && n_normals > 0) z_out[0] = (float)cached_in[0];
+  if (carry && tid == 0 && n_normals > 0) z_out[0] = cached_in[0];
   __syncthreads();
   constexpr int kPer = 4;                                    // consecutive attempts per thread and sweep
   for (long long start = 0; start < n_attempts; start += (long long)blockDim.x * kPer) {
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(1024, 1) mt19937_gauss_scatter_kernel(const ui
       if (f[q] && rank < pairs_needed) {
         const long long i = i0 + q;
         const long long o = carry + 2 * rank;
-        z_out[o] = (float)vals[2 * i];
-        if (o + 1 < n_normals) z_out[o + 1] = (float)vals[2 * i + 1];
+        z_out[o] = vals[2 * i];
+        if (o + 1 < n_normals) z_out[o + 1] = vals[2 * i + 1];
         if (rank == pairs_needed - 1) {
           s_consumed = i + 1;
           const int leftover = (need & 1) ? 1 : 0;           // an odd draw leaves f * x1 cached

@@ -64,6 +64,11 @@ constexpr int kTcMaxObs = 48;           // obs dim limit of this variant (candid
 #ifndef L2A_TC_SPLIT_RING
 #define L2A_TC_SPLIT_RING 1
 #endif
+// timing experiments only (results are garbage): 1 = the issuer never waits for the weight ring; 2 = the producers signal the
+// stages full without copying anything
+#ifndef L2A_TC_EXPERIMENT
+#define L2A_TC_EXPERIMENT 0
+#endif
 constexpr int kTcXChunk = L2A_TC_EARLY_EPI ? (kTcMaxChunks - 1) : 0;   // activation chunk that holds the layer-0 input
 
 // Tile enumeration of one weight set's blob; consumed in exactly this order by the kernel.  Within a layer the M-blocks
@@ -275,6 +280,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
   using S = TcSmem<NC>;
   constexpr int kChunkBytes = S::kChunkBytes;
   constexpr int kTcStages = S::kStages;
+  // split hi / lo ring only where the ring is 2 deep (NC = 80): deeper rings (NC <= 64) already cover the refill latency and
+  // measured slower with the extra handshakes (cfg1 +7 %, cfg2 +6 %; headline -1.4 %)
+  constexpr bool kSplit = (L2A_TC_SPLIT_RING != 0) && (S::kStages == 2);
   constexpr uint32_t kIdesc = umma::make_idesc_bf16(128, NC);
   static_assert(NC % 16 == 0 && NC >= 16 && 6 * NC <= 512, "UMMA N constraint / six accumulator slots must fit the 512 TMEM columns");
 
@@ -450,8 +458,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         pair_a = (pair_a + 2) % 3;
       }
     }
-#if L2A_TC_SPLIT_RING
-    else if (warp == 10 && lane == 0) {
+    else if (kSplit && warp == 10 && lane == 0) {
       // ============================================================== second TMA producer: the W_lo half of every ring stage
       int stage = 0;
       uint32_t phase = 0;
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           if (pr >= plan.hidden_pairs) bytes = (uint32_t)(min(plan.out_kcs, out_nkc - (pr - plan.hidden_pairs) * plan.out_kcs) * out_part2);
           const uint32_t bytes_l = bytes > (uint32_t)kTcTileBytes ? bytes - (uint32_t)kTcTileBytes : 0u;
           umma::mbar_wait(&empty2[stage], phase ^ 1u);
-          if (bytes_l) {
+          if (bytes_l && L2A_TC_EXPERIMENT != 2) {
             umma::mbar_arrive_expect_tx(&full2[stage], bytes_l);
             umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes + kTcTileBytes, blob + (size_t)pr * S::kStageBytes + kTcTileBytes, bytes_l, &full2[stage]);
           } else {
@@ -473,7 +480,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         }
       }
     }
-#endif
   } else if (warp == 4) {
     // ================================================================ TMA producer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
@@ -486,10 +492,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         for (int pr = 0; pr < plan.stages_per_set; ++pr) {
           uint32_t bytes = S::kStageBytes;
           if (pr >= plan.hidden_pairs) bytes = (uint32_t)(min(plan.out_kcs, out_nkc - (pr - plan.hidden_pairs) * plan.out_kcs) * out_part2);
-#if L2A_TC_SPLIT_RING
-          if (bytes > (uint32_t)kTcTileBytes) bytes = (uint32_t)kTcTileBytes;       // the W_hi half; warp 10 streams the rest
-#endif
+          if (kSplit && bytes > (uint32_t)kTcTileBytes) bytes = (uint32_t)kTcTileBytes;       // the W_hi half; warp 10 streams the rest
           umma::mbar_wait(&empty[stage], phase ^ 1u);
+          if (L2A_TC_EXPERIMENT == 2) { umma::mbar_arrive(&full[stage]); if (++stage == kTcStages) { stage = 0; phase ^= 1u; } continue; }
           umma::mbar_arrive_expect_tx(&full[stage], bytes);
           umma::bulk_g2s(stages + (size_t)stage * S::kStageBytes, blob + (size_t)pr * S::kStageBytes, bytes, &full[stage]);
           if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
@@ -511,18 +516,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)S::kStageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
       // ring protocol of the consumer side: acquire (wait unless a probe already saw the stage full) -> MMAs -> commit -> advance
       auto acquire = [&]() {
-        if (!ready) umma::mbar_wait(&full[stage], phase);
-#if L2A_TC_SPLIT_RING
-        umma::mbar_wait(&full2[stage], phase);
-#endif
+        if (!ready && L2A_TC_EXPERIMENT != 1) umma::mbar_wait(&full[stage], phase);
+        if (kSplit && L2A_TC_EXPERIMENT != 1) umma::mbar_wait(&full2[stage], phase);
         umma::tc_fence_after();
       };
       // whole stage consumed (elected lane only)
       auto release = [&]() {
         umma::mma_commit(&empty[stage]);
-#if L2A_TC_SPLIT_RING
-        umma::mma_commit(&empty2[stage]);
-#endif
+        if (kSplit) umma::mma_commit(&empty2[stage]);
       };
       auto probe_next = [&]() {
 #if L2A_TC_PIPE_WAIT
@@ -537,12 +538,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       // one (hi tile, lo tile) pair = the three split-bf16 passes of one [128 x 64] weight block against activation chunk `ch`
       auto tile_pair = [&](uint32_t d_tmem, int ch, bool first, bool full_k, int nks_last) {
         const uint32_t bh = hi_lo32 + (uint32_t)ch * kChunkStep, bl = lo_lo32 + (uint32_t)ch * kChunkStep;
-#if L2A_TC_SPLIT_RING
-        {
+        if constexpr (kSplit) {
           const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
           const int nks = full_k ? 4 : nks_last;
           // the two W_hi passes of every k-step (W_hi slice read from shared memory once: A-collector keep / reuse) ...
-          umma::mbar_wait(&full[stage], phase);
+          if (L2A_TC_EXPERIMENT != 1) umma::mbar_wait(&full[stage], phase);
           umma::tc_fence_after();
           if (umma::elect_one()) {
             if (full_k) {
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           }
           __syncwarp();
           // ... then the W_lo * x_hi pass
-          umma::mbar_wait(&full2[stage], phase);
+          if (L2A_TC_EXPERIMENT != 1) umma::mbar_wait(&full2[stage], phase);
           umma::tc_fence_after();
           if (umma::elect_one()) {
             if (full_k) {
@@ -576,7 +576,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           advance(false);
           return;
         }
-#endif
         acquire();
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         // per 16-wide k-step: W_hi * x_hi, W_hi * x_lo (the W_hi slice is fetched from shared memory once for the two:

@@ -47,4 +47,30 @@ __global__ void __launch_bounds__(256) sample_uniform_kernel(const float* __rest
   }
 }
 
+// Standard normals from the same Philox stream (throughput-mode replacement of np.random.normal in the CEM planner,
+// policies/mpc_controller.py:85): Box-Muller on two 24-bit uniforms per output pair, u1 in (0, 1], u2 in [0, 1):
+//   r = sqrt(-2 ln u1),  z0 = r cos(2 pi u2),  z1 = r sin(2 pi u2)      (float32 arithmetic, stored as float64).
+// One Philox block (4 words) -> 4 normals: pairs (w0, w1) and (w2, w3).  call_index: device pointer to the 64-bit call counter;
+// `stream_id` separates the CEM iterations of one call.
+__global__ void __launch_bounds__(256) sample_normal_kernel(double* __restrict__ out, long long total, uint64_t seed,
+                                                            const uint32_t* __restrict__ call_index, uint32_t stream_id) {
+  const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = blk * 4;
+  if (i0 >= total) return;
+  uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32) ^ (stream_id << 16), call_index[0], call_index[1]};
+  philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5EEDu);
+  float z[4];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float u1 = (float)((ctr[2 * q] >> 8) + 1u) * (1.0f / 16777216.0f);
+    const float u2 = (float)(ctr[2 * q + 1] >> 8) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * q] = r * cs;
+    z[2 * q + 1] = r * sn;
+  }
+  for (int q = 0; q < 4 && i0 + q < total; ++q) out[i0 + q] = (double)z[q];
+}
+
 }  // namespace l2a

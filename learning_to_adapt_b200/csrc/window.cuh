@@ -19,12 +19,13 @@ struct WindowDev {
 };
 
 // running_paths[idx]["observations"].append(observation); ["actions"].append(action)   (sampler.py:109-110)
-__global__ void window_push_kernel(WindowDev w, const double* __restrict__ obs, const double* __restrict__ act) {
+// act_stride: doubles between consecutive envs' action rows (A for a packed [n_envs, A] array)
+__global__ void window_push_kernel(WindowDev w, const double* __restrict__ obs, const double* __restrict__ act, int act_stride) {
   const int env = blockIdx.x;
   const int slot = w.count[env] % w.cap;
   for (int c = threadIdx.x; c < w.D + w.A; c += blockDim.x) {
     if (c < w.D) w.obs[((size_t)env * w.cap + slot) * w.D + c] = obs[(size_t)env * w.D + c];
-    else w.act[((size_t)env * w.cap + slot) * w.A + (c - w.D)] = act[(size_t)env * w.A + (c - w.D)];
+    else w.act[((size_t)env * w.cap + slot) * w.A + (c - w.D)] = act[(size_t)env * act_stride + (c - w.D)];
   }
   __syncthreads();
   if (threadIdx.x == 0) w.count[env] += 1;

@@ -72,6 +72,7 @@ class MetaMLPDynamicsModel(MLPDynamicsModel):
         eng = self._engine
         x = eng._f32(np.concatenate([obs_n, act_n], axis=2))
         target = eng._f32(delta_n)
+        self._pending_window = None
         eng.adapt(x, target, self.inner_learning_rate, src_set=0, dst_first_set=1)
         self._num_adapted_models = k
         self._adapted = True
@@ -80,31 +81,51 @@ class MetaMLPDynamicsModel(MLPDynamicsModel):
         from learning_to_adapt_b200.samplers.window import AdaptWindow
         return AdaptWindow(self._engine, n_envs, adapt_batch_size)
 
-    def adapt_from_window(self, window):
+    def adapt_from_window(self, window, defer=True):
         """adapt() on the windows held by a device-resident AdaptWindow (samplers/window.py): the gather of
         obs[-M-1:-1] / act[-M-1:-1] / obs[-M:] (samplers/sampler.py:83-88) and the float64 normalisation (:334-339) run in a
-        kernel in front of K2; inputs to K2 are bit-identical to adapt()'s."""
+        kernel in front of K2; inputs to K2 are bit-identical to adapt()'s.
+        defer=True (default): nothing is launched here -- the next MPCController planning call runs window-gather -> K2 ->
+        re-tile in front of the planner inside its own C call / CUDA graph (l2a_plan_run_ex with L2A_PLAN_ADAPT); any other use
+        of the adapted sets (predict, get_adapted_params) first runs the adaptation on the spot."""
         k = window.n_envs
         if k > self.meta_batch_size:
             raise ValueError("window holds %d envs but meta_batch_size is %d" % (k, self.meta_batch_size))
+        if (window.obs_dim, window.act_dim) != (self._engine.obs_dim, self._engine.act_dim) or window._engine is not self._engine:
+            raise RuntimeError("the adaptation window belongs to another model (dims %d/%d vs %d/%d)"
+                               % (window.obs_dim, window.act_dim, self._engine.obs_dim, self._engine.act_dim))
+        if not window.ready_for_adapt():
+            raise RuntimeError("an env's running path is shorter than adapt_batch_size + 1 transitions")
+        self._num_adapted_models = k
+        self._adapted = True
+        self._pending_window = window
+        if not defer:
+            self._flush_pending_adapt()
+
+    def _flush_pending_adapt(self):
+        window = getattr(self, "_pending_window", None)
+        if window is None:
+            return
+        self._pending_window = None
         if window._norm_src is not self.normalization:
             window.set_normalization(self.normalization)
         eng = self._engine
         N.check(eng.lib.l2a_adapt_from_window(eng._ctx, eng._model, window._h, float(self.inner_learning_rate), 0, 1,
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        self._num_adapted_models = k
-        self._adapted = True
 
     def switch_to_pre_adapt(self):
         self._adapted = False                       # theta itself was never modified (:347-351)
+        self._pending_window = None
 
     def get_adapted_params(self, k):
         assert self._adapted and k < self._num_adapted_models
+        self._flush_pending_adapt()
         return self._engine.get_params(1 + k)
 
     # ------------------------------------------------------------------ K4 with per-task weights
     def _predict_delta(self, obs, act):
         eng = self._engine
+        self._flush_pending_adapt()
         if self._adapted:
             k = self._num_adapted_models
             assert obs.shape[0] % k == 0, "rows must split evenly over the adapted tasks (meta_mlp_dynamics.py:308-312)"

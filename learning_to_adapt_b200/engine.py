@@ -172,7 +172,8 @@ class PlanningEngine(object):
 
     # ------------------------------------------------------------------ host-buffer planning call (l2a_plan_*)
     def plan_rs_host(self, observations, n_candidates, horizon, reward_kind, dt, low, high, discount=1.0,
-                     set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO, seed=0, sampler="philox", shard=None):
+                     set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO, seed=0, sampler="philox", shard=None,
+                     window=None, flags=0, inner_lr=0.0):
         """One random-shooting planning call with HOST arrays on both sides (policies/mpc_controller.py:59-65, 108-129):
         observations float64 [m, D] -> (actions float64 [m, A], best_ret float32 [m], best_idx int64 [m]).  ONE C call; after the
         first call the whole sequence H2D -> sample -> K1 [-> peer exchange] -> D2H is one CUDA graph replay inside libl2a_b200.
@@ -183,7 +184,10 @@ class PlanningEngine(object):
             would have left it, and the returned actions are the float64 candidates the reference returns.
         shard: None, or dict(rank, world, all_gather) -- this process rolls its slice of the `n_candidates` of every env and the
             ranks' winners are exchanged over peer memory inside the call (`all_gather(bytes) -> list of bytes` is only used once,
-            to exchange the IPC handles of the exchange buffers)."""
+            to exchange the IPC handles of the exchange buffers).
+        window / flags / inner_lr: the GrBAL env step inside the same call (samplers/sampler.py:81-91): with an AdaptWindow and
+            N.PLAN_ADAPT the call first adapts weight set 0 into sets 1.. on the window's last M transitions (K2), with N.PLAN_PUSH
+            it appends (observation, chosen action) to the window afterwards."""
         obs = np.ascontiguousarray(observations, dtype=np.float64)
         m = obs.shape[0]
         assert obs.shape == (m, self.obs_dim)
@@ -192,7 +196,8 @@ class PlanningEngine(object):
         assert low64.shape == (self.act_dim,) and high64.shape == (self.act_dim,)
         rank, world = (int(shard["rank"]), int(shard["world"])) if shard else (0, 1)
         key = (m, int(n_candidates), int(horizon), int(reward_kind), float(dt), float(discount), int(set_mode), int(first_set),
-               int(n_sets), int(kernel), low64.tobytes(), high64.tobytes(), int(seed), sampler, rank, world)
+               int(n_sets), int(kernel), low64.tobytes(), high64.tobytes(), int(seed), sampler, rank, world,
+               id(window) if window is not None else 0, float(inner_lr))
         plan = self._plans.get(key)
         if plan is None:
             from .parallel import shard_bounds
@@ -217,7 +222,11 @@ class PlanningEngine(object):
             io.mt_key, io.mt_pos = plan["key"].ctypes.data, C.addressof(plan["pos"])
             if world > 1:
                 self._attach_peers(plan, rank, world, shard["all_gather"])
+            if window is not None:
+                N.check(self.lib.l2a_plan_attach_window(self._ctx, handle, window._h, float(inner_lr), 0, 1))
+                plan["window"] = window                    # keeps it alive
             self._plans[key] = plan
+        plan["io"].flags = int(flags) if window is not None else 0
         if sampler == "mt19937":
             st = np.random.get_state()
             assert st[0] == "MT19937"
@@ -228,6 +237,63 @@ class PlanningEngine(object):
             np.random.set_state(("MT19937", plan["key"], int(plan["pos"].value), st[3], st[4]))
         self._last_plan = plan
         return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy()
+
+    def plan_cem_host(self, observations, n_candidates, horizon, reward_kind, dt, low, high, num_cem_iters, num_elites, alpha,
+                      discount=1.0, set_mode=N.SETS_SHARED, first_set=0, n_sets=1, kernel=N.KERNEL_AUTO, seed=0, sampler="philox",
+                      compat=True, window=None, flags=0, inner_lr=0.0):
+        """The whole CEM planning call (policies/mpc_controller.py:71-106, all `num_cem_iters` iterations) as ONE C call / one CUDA
+        graph replay: observations float64 [m, D] -> (actions float64 [m, A], best_ret [m], best_idx [m], mean [m, H*A], std [m, H*A]).
+        sampler "mt19937" continues numpy's global stream exactly like np.random.normal(size=(n, m, H*A)) per iteration (:85),
+        including the cached second value of the polar method; "philox" draws on the device stream."""
+        obs = np.ascontiguousarray(observations, dtype=np.float64)
+        m = obs.shape[0]
+        assert obs.shape == (m, self.obs_dim)
+        low64 = np.ascontiguousarray(low, dtype=np.float64)
+        high64 = np.ascontiguousarray(high, dtype=np.float64)
+        ha = int(horizon) * self.act_dim
+        key = ("cem", m, int(n_candidates), int(horizon), int(reward_kind), float(dt), float(discount), int(set_mode), int(first_set),
+               int(n_sets), int(kernel), low64.tobytes(), high64.tobytes(), int(seed), sampler, int(num_cem_iters), int(num_elites),
+               float(alpha), bool(compat), id(window) if window is not None else 0, float(inner_lr))
+        plan = self._plans.get(key)
+        if plan is None:
+            p = N.RolloutParams()
+            p.n_candidates, p.n_envs, p.horizon = int(n_candidates), int(m), int(horizon)
+            p.set_mode, p.first_set, p.n_sets = int(set_mode), int(first_set), int(n_sets)
+            p.reward_kind, p.dt, p.kernel = int(reward_kind), float(dt), int(kernel)
+            o = N.PlanOpts()
+            o.sampler = {"philox": N.SAMPLER_PHILOX, "mt19937": N.SAMPLER_MT19937}[sampler]
+            o.shard_rank, o.shard_world, o.n_candidates_total, o.shard_offset = 0, 1, int(n_candidates), 0
+            o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            o.planner, o.cem_iters, o.cem_num_elites = N.PLANNER_CEM, int(num_cem_iters), int(num_elites)
+            o.cem_compat, o.cem_alpha = (1 if compat else 0), float(alpha)
+            handle = C.c_void_p()
+            N.check(self.lib.l2a_plan_create_ex(self._ctx, self._model, C.byref(p), float(discount),
+                                                low64.ctypes.data_as(C.c_void_p), high64.ctypes.data_as(C.c_void_p),
+                                                C.byref(o), C.byref(handle)))
+            plan = dict(handle=handle, act=np.empty((m, self.act_dim), np.float64), ret=np.empty(m, np.float32),
+                        idx=np.empty(m, np.int64), shape=(int(n_candidates), m, ha), key=np.empty(624, np.uint32), pos=C.c_int32(0),
+                        has_gauss=C.c_int32(0), cached=C.c_double(0.0), mean=np.empty((m, ha), np.float64),
+                        std=np.empty((m, ha), np.float64), io=N.PlanIO(), peers=[])
+            io = plan["io"]
+            io.act_out, io.ret_out, io.idx_out = plan["act"].ctypes.data, plan["ret"].ctypes.data, plan["idx"].ctypes.data
+            io.mt_key, io.mt_pos = plan["key"].ctypes.data, C.addressof(plan["pos"])
+            io.mt_has_gauss, io.mt_cached = C.addressof(plan["has_gauss"]), C.addressof(plan["cached"])
+            io.cem_mean_out, io.cem_std_out = plan["mean"].ctypes.data, plan["std"].ctypes.data
+            if window is not None:
+                N.check(self.lib.l2a_plan_attach_window(self._ctx, handle, window._h, float(inner_lr), 0, 1))
+                plan["window"] = window
+            self._plans[key] = plan
+        plan["io"].flags = int(flags) if window is not None else 0
+        if sampler == "mt19937":
+            st = np.random.get_state()
+            assert st[0] == "MT19937"
+            plan["key"][:] = st[1]
+            plan["pos"].value, plan["has_gauss"].value, plan["cached"].value = int(st[2]), int(st[3]), float(st[4])
+        N.check(self.lib.l2a_plan_run_ex(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p), C.byref(plan["io"]), _stream()))
+        if sampler == "mt19937":
+            np.random.set_state(("MT19937", plan["key"], int(plan["pos"].value), int(plan["has_gauss"].value), float(plan["cached"].value)))
+        self._last_plan = plan
+        return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy(), plan["mean"].copy(), plan["std"].copy()
 
     def _attach_peers(self, plan, rank, world, all_gather):
         """Exchange the CUDA IPC handles of the ranks' exchange buffers once and hand the peers' pointers to the plan."""
@@ -265,6 +331,12 @@ class PlanningEngine(object):
         plan = self._last_plan
         out = np.empty(plan["shape"], np.float32)
         N.check(self.lib.l2a_plan_copy_candidates(self._ctx, plan["handle"], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def last_plan_returns(self, m, n):
+        """[m, N] float32 returns of the last iteration of the most recent plan_cem_host call (tests / diagnostics)."""
+        out = np.empty((m, n), np.float32)
+        N.check(self.lib.l2a_plan_copy_returns(self._ctx, self._last_plan["handle"], out.ctypes.data_as(C.c_void_p)))
         return out
 
     def last_plan_uses_graph(self):

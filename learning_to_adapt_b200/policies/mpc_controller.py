@@ -11,7 +11,8 @@ Candidate sampling
       regenerated bit-exactly ON THE DEVICE from ``np.random.get_state()`` inside the one host-buffer C call (l2a_plan_run_ex:
       H2D obs + generator state -> MT19937 -> K1 -> D2H action + advanced state, replayed as a CUDA graph);
       ``np.random.set_state()`` leaves the global stream where the reference would have left it -> identical candidates, hence
-      identical chosen actions for a fixed ``np.random.seed``, at device speed.  CEM draws ``np.random.normal`` (:85) on the host.
+      identical chosen actions for a fixed ``np.random.seed``, at device speed.  CEM likewise: ``np.random.normal`` (:85, numpy's
+      legacy polar method with its cached second value) is regenerated on the device and all iterations run inside one C call.
   sampler="numpy_host": the same stream drawn by numpy on the host and uploaded as fp32 (the round-1 parity path; kept as the
       cross-check of the device generator).
   sampler="device": Philox draws on the GPU (throughput mode; env var L2A_B200_SAMPLER=device selects it without touching
@@ -75,7 +76,9 @@ class MPCController(Policy, Serializable):
             raise TypeError("dynamics_model must be an engine-backed learning_to_adapt_b200 model "
                             "(MLPDynamicsModel / MetaMLPDynamicsModel); there is no CPU fallback")
         self._reward_kind, self._dt = reward_kind_of(self.unwrapped_env)
-        self.last_plan = None             # device tensors of the most recent planning call (diagnostics / tests)
+        self.last_plan = None             # results of the most recent planning call (diagnostics / tests)
+        self.keep_returns = False         # CEM: also fetch the last iteration's per-candidate returns into last_plan (tests)
+        self.push_window = None           # AdaptWindow the planning call appends (obs, action) to (set by the Sampler)
 
         Serializable.quick_init(self, locals())
         super(MPCController, self).__init__(env=env)
@@ -104,6 +107,25 @@ class MPCController(Policy, Serializable):
         return np.random.uniform(low=self.action_space.low, high=self.action_space.high,
                                  size=(n,) + self.action_space.low.shape)
 
+    def _grbal_step_args(self):
+        """GrBAL env step folded into the planning call (samplers/sampler.py:81-91): a deferred adapt_from_window() of the model
+        runs in front of the planner, and (obs, chosen action) is appended to the Sampler's window behind it."""
+        model = self.dynamics_model
+        pending = getattr(model, "_pending_window", None)
+        window = pending if pending is not None else self.push_window
+        if window is None:
+            return dict()
+        assert pending is None or self.push_window is None or pending is self.push_window
+        flags = (N.PLAN_ADAPT if pending is not None else 0) | (N.PLAN_PUSH if self.push_window is not None else 0)
+        if pending is not None and window._norm_src is not model.normalization:
+            window.set_normalization(model.normalization)
+        return dict(window=window, flags=flags, inner_lr=float(getattr(model, "inner_learning_rate", 0.0)))
+
+    def _grbal_step_done(self, kw):
+        if kw.get("flags", 0) & N.PLAN_ADAPT:
+            self.dynamics_model._pending_window = None
+        self.pushed_window = bool(kw.get("flags", 0) & N.PLAN_PUSH)      # the Sampler skips its own push when the call did it
+
     # ------------------------------------------------------------------ random shooting (mpc_controller.py:108-129)
     def get_rs_action(self, observations):
         observations = np.asarray(observations, np.float64)
@@ -111,16 +133,20 @@ class MPCController(Policy, Serializable):
         eng = self.dynamics_model._engine
         act_dim = self.action_space.shape[0]
         set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
+        self.pushed_window = False
         if self.sampler in ("device", "numpy"):
+            step = self._grbal_step_args()
             shard = None
             if self.parallel is not None:
                 shard = dict(rank=self.parallel.rank, world=self.parallel.world_size, all_gather=self.parallel.all_gather_bytes)
             acts, ret, idx = eng.plan_rs_host(observations, n, h, self._reward_kind, self._dt, self.action_space.low,
                                               self.action_space.high, discount=self.discount, set_mode=set_mode,
                                               first_set=first_set, n_sets=n_sets, kernel=self.kernel, seed=self.seed,
-                                              sampler="philox" if self.sampler == "device" else "mt19937", shard=shard)
+                                              sampler="philox" if self.sampler == "device" else "mt19937", shard=shard, **step)
+            self._grbal_step_done(step)
             self.last_plan = dict(best_ret=_host(ret), best_idx=_host(idx), best_act=_host(acts), returns=None)    # host arrays
             return acts
+        self.dynamics_model._flush_pending_adapt() if hasattr(self.dynamics_model, "_flush_pending_adapt") else None
         obs_dev = eng._f32(observations)
         if self.parallel is not None:
             return self.parallel.plan_rs(self, observations, obs_dev, set_mode, first_set, n_sets)
@@ -143,6 +169,21 @@ class MPCController(Policy, Serializable):
         ha = h * act_dim
         set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
         num_elites = max(int(self.n_candidates * self.percent_elites), 1)                 # :78
+        self.pushed_window = False
+        if self.sampler in ("numpy", "device") and self.parallel is None:
+            # all iterations in ONE host-buffer C call (l2a_plan_run_ex, CEM planner), replayed as a CUDA graph
+            step = self._grbal_step_args()
+            acts, ret, idx, mean, std = eng.plan_cem_host(
+                observations, n, h, self._reward_kind, self._dt, self.action_space.low, self.action_space.high,
+                self.num_cem_iters, num_elites, self.alpha, discount=self.discount, set_mode=set_mode, first_set=first_set,
+                n_sets=n_sets, kernel=self.kernel, seed=self.seed, sampler="philox" if self.sampler == "device" else "mt19937",
+                compat=self.cem_compat, **step)
+            self._grbal_step_done(step)
+            returns = _host(eng.last_plan_returns(m, n)) if self.keep_returns else None
+            self.last_plan = dict(best_ret=_host(ret), best_idx=_host(idx), best_act=_host(acts), returns=returns)
+            self.last_cem_state = (_host(mean), _host(std))
+            return acts
+        self.dynamics_model._flush_pending_adapt() if hasattr(self.dynamics_model, "_flush_pending_adapt") else None
         mean = torch.zeros((m, ha), device=eng.device, dtype=torch.float64)               # :79
         std = torch.ones((m, ha), device=eng.device, dtype=torch.float64)                 # :80
         clip_low = eng._f32(np.concatenate([self.action_space.low] * h))                  # :81

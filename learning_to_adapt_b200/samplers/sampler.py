@@ -64,6 +64,8 @@ class Sampler(object):
         policy.reset(dones=[True] * num_envs)
         if win is not None:
             win.reset()
+        if hasattr(policy, "push_window"):
+            policy.push_window = win                 # planning calls append (obs, action) to the window inside their own graph
         obses = np.asarray(self.vec_env.reset())
         while n_samples < self.total_samples:
             t = time.time()
@@ -90,7 +92,7 @@ class Sampler(object):
             if not agent_infos:
                 agent_infos = [dict() for _ in range(num_envs)]
 
-            if win is not None:
+            if win is not None and not (not random and getattr(policy, "pushed_window", False)):
                 win.push(obses, actions)
             new_samples = 0
             for idx in range(num_envs):

@@ -69,6 +69,10 @@ class AdaptWindow(object):
             N.check(n)
         return n
 
+    def ready_for_adapt(self):
+        """Every env holds at least M + 1 pairs (what the gather kernel needs)."""
+        return all(self.length(e) >= self.M + 1 for e in range(self.n_envs))
+
     def ready(self):
         """The reference's trigger: `len(running_paths[0]['observations']) > adapt_batch_size + 1` (sampler.py:82)."""
         return self.length(0) > self.M + 1

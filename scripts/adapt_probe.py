@@ -68,6 +68,21 @@ for env_name, K, M, n, h in (("half_cheetah", 5, 16, 1000, 15), ("ant", 5, 16, 2
         step_window()
     torch.cuda.synchronize()
     e2e_win = (time.perf_counter() - t0) / 20
+    # ... and with the append of (obs, action) folded into the planning call too: the whole env step is ONE C call / graph replay
+    ctrl.push_window = win
+    def step_fused():
+        model.switch_to_pre_adapt()
+        model.adapt_from_window(win)
+        return ctrl.get_actions(obs)
+    for _ in range(3):
+        step_fused()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step_fused()
+    torch.cuda.synchronize()
+    e2e_fused = (time.perf_counter() - t0) / 20
+    ctrl.push_window = None
     # host formulation including the list slicing the reference's sampler does each step
     paths = [dict(observations=list(rng.normal(size=(M + 4, prob["obs_dim"]))), actions=list(rng.normal(size=(M + 4, prob["act_dim"])))) for _ in range(K)]
     def step_lists():
@@ -87,4 +102,4 @@ for env_name, K, M, n, h in (("half_cheetah", 5, 16, 1000, 15), ("ant", 5, 16, 2
     O.adapt(*ctx, prob["param_sets"][0], prob["norm"], 1e-3)
     cpu = time.perf_counter() - t0
     print(json.dumps(dict(cfg="%s K=%d M=%d N=%d H=%d" % (env_name, K, M, n, h), adapt_kernels_ms=float(np.median(tms)),
-                          grbal_step_e2e_ms=e2e * 1e3, grbal_step_lists_ms=e2e_lists * 1e3, grbal_step_device_window_ms=e2e_win * 1e3, cpu_oracle_adapt_ms=cpu * 1e3)), flush=True)
+                          grbal_step_e2e_ms=e2e * 1e3, grbal_step_lists_ms=e2e_lists * 1e3, grbal_step_device_window_ms=e2e_win * 1e3, grbal_step_one_call_ms=e2e_fused * 1e3, cpu_oracle_adapt_ms=cpu * 1e3)), flush=True)

@@ -34,3 +34,12 @@ for mode, base in ((9, 4), (10, 0)):
     cyc, copies = out[0].item(), out[2].item()
     print("NC= 80 %-20s + concurrent bulk-copy stream: %7.1f cycles / tile pair; %d x 32 KB landed in %d cycles = %.1f B/clk of fill writes"
           % (names[base], cyc / 2000.0, copies, cyc, copies * 32768.0 / cyc))
+
+# what the issuer's per-pair handshake instructions cost on always-satisfied barriers, and the real 2-deep weight ring in isolation
+hs = {11: "wait + fence + commit per pair", 12: "commit per pair", 13: "wait + fence per pair",
+      14: "REAL ring 2 x 32 KB (1 producer)", 15: "REAL split ring hi/lo (2 producers)"}
+for mode in (4, 11, 12, 13, 14, 15):
+    for _ in range(2):
+        N.check(lib.l2a_debug_mma_rate(ctx, 80, mode, 2000, C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+    print("NC= 80 SS + hints, %-36s %7.1f cycles / tile pair" % (hs.get(mode, "bare loop"), out[0].item() / 2000.0))

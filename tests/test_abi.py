@@ -34,8 +34,8 @@ def test_struct_layouts_match_header():
     from learning_to_adapt_b200 import _native
     assert ctypes.sizeof(_native.MlpDesc) == 4 * (3 + 7 + 1)
     assert ctypes.sizeof(_native.RolloutParams) == 8 * 4 + 2 * 8 + 2 * 4
-    assert ctypes.sizeof(_native.PlanOpts) == 4 * 4 + 8 + 8
-    assert ctypes.sizeof(_native.PlanIO) == 5 * 8
+    assert ctypes.sizeof(_native.PlanOpts) == 4 * 4 + 8 + 8 + 4 * 4 + 8
+    assert ctypes.sizeof(_native.PlanIO) == 9 * 8 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")

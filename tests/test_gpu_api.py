@@ -120,6 +120,7 @@ def test_cem_full_size_corrected_mode_improves_returns():
     for compat in (True, False):
         ctrl = MPCController("policy", env, model, use_cem=True, n_candidates=5000, horizon=30, num_cem_iters=3,
                              percent_elites=0.1, alpha=0.1, sampler="device", cem_compat=compat)
+        ctrl.keep_returns = True
         torch.manual_seed(0)
         a, _ = ctrl.get_actions(prob["obs0"])
         assert a.shape == (1, 6) and np.all(np.isfinite(a))

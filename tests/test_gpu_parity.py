@@ -369,6 +369,7 @@ def test_cem_bug_compatible_matches_reference_golden(golden, tag):
     model.set_normalization(prob["norm"])
     ctrl = MPCController("policy", env, model, use_cem=True, n_candidates=n, horizon=h, num_cem_iters=iters,
                          percent_elites=pct, alpha=alpha)
+    ctrl.keep_returns = True
     np.random.seed(seed + 100)
     acts, _ = ctrl.get_actions(prob["obs0"])
     ref_returns = golden[tag + "_last_step_rewards"].sum(axis=0).reshape(m, n)
