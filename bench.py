@@ -1,23 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- candidate-rollouts/s of the MPC planning hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config NAME] [--scaling weak|strong]    # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W [--config NAME]           # the reference algorithm on the host
 
-A "step" is ONE planning call (one pass of the hot path over one batch of candidates): sample-free K1 rollout of
-N candidates x H steps through the E-member dynamics ensemble + reward + argmax (+ the all-gather of the per-rank best
-triple when N_gpus > 1).  Workload = BASELINE.md "headline": HalfCheetah, N=2000 per GPU, H=20, ensemble E=5,
-MLP 26->512->512->512->20.  Weak scaling: every rank plans its own 2000 candidates, global N = 2000 x gpus.
+A "step" is ONE planning call (one pass of the hot path over one batch of candidates).  --config picks the workload
+(BASELINE.md section 2); the default is the north-star headline: HalfCheetah random shooting, N=2000 per GPU, H=20, ensemble
+E=5 (mean of deltas), MLP 26->512->512->512->20.
+    headline  HC RS N=2000 H=20 E=5 (512^3), m=1                   cfg1   HC RS N=500 H=10 (512^2), m=1 (the reference's CPU case)
+    cfg1p     HC RS N=2000 H=20 (512^2), m=10 (run_mb_mpc.py)      cfg2   HC GrBAL: 5 envs x N=1000 H=15 (512^3), adapt M=16 every step
+    cfg3      Ant RS N=2000 H=20 E=5 (512^3)                       cfg4   HC CEM N=5000, 500 elites, 3 iterations, H=30 (512^2)
+    cfg5      Ant RS N=4096 per GPU H=25 E=5 (512^3) (the 8-GPU shard's per-GPU share; --gpus 8 = 32768 candidates)
+Scaling: weak (default; every rank plans its own N candidates, global N = N x gpus) or strong (--scaling strong: the config's N
+is split over the ranks).
 
-value  : whole-job candidate-rollouts/s with the candidate tensor already resident in HBM, CUDA-event timed per step,
-         L2 flushed (256 MB write) between steps, max over ranks.
-e2e    : the same metric through the public API call MPCController.get_actions(obs ndarray) -> ndarray = ONE host-buffer
-         C-ABI call (l2a_plan_run): host->device copy of the observations, Philox candidate sampling on the device, K1,
-         device->host copy of the chosen actions -- all inside the timed region (sampler="device"; at N>1 GPUs the
-         candidate shard adds the NCCL all-gather).
-roofline: dominant kernel rollout_tc_kernel, tensor-pipe bound; achieved = algorithmic FLOPs per launch (N*H*E*F, counted once
-         although split-bf16 issues 3 MMA passes) / mean launch duration.
-cpu_baseline: oracle port (numpy planner + float32 BLAS MLP) timed on the host cores on a bounded sample of the same workload.
+value  : whole-job candidate-rollouts/s with the inputs already resident in HBM (pre-materialised candidate tensor / normal
+         draws), CUDA-event timed per step on the launching stream, L2 flushed (256 MB write) between steps, max over ranks.
+         At N>1 the step includes the exchange of the per-rank best triple (NCCL all-gather through torch.distributed).
+e2e    : the same metric through the public API call MPCController.get_actions(obs ndarray) -> ndarray = ONE host-buffer C-ABI
+         call (l2a_plan_run_ex): host->device copy of the observations (+ RNG state), candidate sampling on the device, K1
+         (cfg4: all CEM iterations; cfg2: window gather + K2 adapt in front, window push behind; N>1: peer-memory exchange of
+         the ranks' winners over NVLink), device->host copy of the chosen actions -- all inside the timed region.  Sampler =
+         device Philox; `default_sampler_value` = the same with the package's DEFAULT sampler (the reference's numpy stream
+         regenerated on the device), which is what unchanged run scripts get.
+roofline: dominant kernel rollout_tc_kernel, tensor-pipe bound; achieved = algorithmic FLOPs per launch (rows*H*E*F, counted once
+         although split-bf16 issues 3 MMA passes) / mean launch duration measured here with CUDA events.
+cpu_baseline / --impl reference: the reference's planner on the host cores: the VERBATIM upstream MPCController (oracle/_ref, made
+         by oracle/make_ref.py) when present -- kind "reference" -- else its oracle restatement (kind "port"); the dynamics model
+         behind it is the oracle's float32 BLAS port in both cases (TF 1.13.1 cannot be installed; "ensemble" has no upstream code).
 """
 import argparse
 import json
@@ -33,8 +43,26 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-WORKLOAD = dict(env="half_cheetah", hidden=(512, 512, 512), n_candidates=2000, horizon=20, ensemble=5, n_envs=1)
+CONFIGS = {
+    "headline": dict(env="half_cheetah", hidden=(512, 512, 512), n=2000, h=20, m=1, E=5, mode="ensemble", planner="rs",
+                     desc="BASELINE.md headline: HalfCheetah random-shooting MPC, ensemble E=5 (mean of deltas), MLP 26-512-512-512-20"),
+    "cfg1": dict(env="half_cheetah", hidden=(512, 512), n=500, h=10, m=1, E=1, mode="shared", planner="rs",
+                 desc="BASELINE cfg1: run_mb_mpc.py HalfCheetah random shooting, single MLP 26-512-512-20"),
+    "cfg1p": dict(env="half_cheetah", hidden=(512, 512), n=2000, h=20, m=10, E=1, mode="shared", planner="rs",
+                  desc="BASELINE cfg1' (run_mb_mpc.py defaults): HalfCheetah random shooting, 10 envs per call, MLP 26-512-512-20"),
+    "cfg2": dict(env="half_cheetah", hidden=(512, 512, 512), n=1000, h=15, m=5, E=5, mode="per_env", planner="rs", grbal=True,
+                 desc="BASELINE cfg2: HalfCheetah GrBAL, 5 envs each with its own adapted weight set (inner adapt M=16, lr=1e-3, every "
+                      "env step), MLP 26-512-512-512-20"),
+    "cfg3": dict(env="ant", hidden=(512, 512, 512), n=2000, h=20, m=1, E=5, mode="ensemble", planner="rs",
+                 desc="BASELINE cfg3: Ant random shooting, ensemble E=5, MLP 49-512-512-512-41, ctrl +-150"),
+    "cfg4": dict(env="half_cheetah", hidden=(512, 512), n=5000, h=30, m=1, E=1, mode="shared", planner="cem", iters=3, pct=0.1, alpha=0.1,
+                 desc="BASELINE cfg4: HalfCheetah CEM planner, 5000 candidates x 3 iterations, 500 elites, MLP 26-512-512-20 "
+                      "(a call rolls N x iters candidate sequences)"),
+    "cfg5": dict(env="ant", hidden=(512, 512, 512), n=4096, h=25, m=1, E=5, mode="ensemble", planner="rs",
+                 desc="BASELINE cfg5: Ant candidate shard, N=4096 per GPU (32768 on 8 GPUs), ensemble E=5, MLP 49-512-512-512-41"),
+}
 METRIC = "candidate-rollouts/sec (N x H dynamics steps) HalfCheetah MPC"
+MODE = {"shared": 0, "per_env": 1, "ensemble": 2}
 
 
 def flops_per_dyn_step(obs_dim, act_dim, hidden):
@@ -99,27 +127,6 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def pick_blas_threads(O, prob, horizon):
-    """The numpy/OpenBLAS port is not fastest with every host thread (a 128-core box oversubscribes 2000x512 GEMMs):
-    time one small planning call per candidate thread count and keep the best, so the CPU baseline is the port at its best."""
-    from threadpoolctl import threadpool_limits
-    cores = os.cpu_count() or 1
-    cands = sorted(set([c for c in (4, 8, 16, 32, 64, cores) if c <= cores]))
-    best, best_t = cores, float("inf")
-    acts = O.sample_rs_actions(0, prob["low"], prob["high"], 6, 2000)
-    for c in cands:
-        with threadpool_limits(limits=c):
-            O.rs_plan(prob["obs0"], acts, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
-            dt = float("inf")
-            for _ in range(3):
-                t0 = time.perf_counter()
-                O.rs_plan(prob["obs0"], acts, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
-                dt = min(dt, time.perf_counter() - t0)
-        if dt < best_t * 0.97:
-            best, best_t = c, dt
-    return best
-
-
 _REAL_STDOUT = None
 
 
@@ -142,54 +149,152 @@ def emit(line_dict):
         os.write(_REAL_STDOUT, data)
 
 
-def make_problem():
+def make_problem(cfg):
     from oracle import mpc_oracle as O
-    w = WORKLOAD
-    return O, O.make_problem(w["env"], hidden_sizes=w["hidden"], n_sets=w["ensemble"], m=w["n_envs"], seed=0)
+    n_sets = cfg["E"] if cfg["mode"] == "ensemble" else 1
+    return O, O.make_problem(cfg["env"], hidden_sizes=cfg["hidden"], n_sets=n_sets, m=cfg["m"], seed=0)
 
 
-# =================================================================================================== reference arm
+def split_candidates(cfg, gpus, scaling):
+    """(candidates per GPU, global candidates) of one planning call."""
+    gpus = max(1, gpus)
+    if scaling == "strong":
+        return (cfg["n"] + gpus - 1) // gpus, cfg["n"]
+    return cfg["n"], cfg["n"] * gpus
+
+
+def config_dict(name, cfg, gpus, scaling, sampler):
+    n_gpu, n_glob = split_candidates(cfg, gpus, scaling)
+    d = dict(workload="%s; N=%d candidates/GPU x H=%d, m=%d env(s)" % (cfg["desc"], n_gpu, cfg["h"], cfg["m"]), name=name,
+             n_candidates_per_gpu=n_gpu, global_candidates=n_glob, horizon=cfg["h"], n_envs=cfg["m"], weight_sets=cfg["E"],
+             set_mode=cfg["mode"], planner=cfg["planner"],
+             dyn_steps_per_call_per_gpu=n_gpu * cfg["m"] * cfg["h"] * (cfg["E"] if cfg["mode"] == "ensemble" else 1) * cfg.get("iters", 1),
+             parallelism="candidate-shard x%d, winners exchanged once per call (value: NCCL all-gather; e2e: peer-memory exchange inside the C call)" % max(1, gpus),
+             sampler=sampler,
+             l2="flushed between timed steps (256 MB write); inputs (candidates + weight tiles, < 40 MB) are smaller than L2")
+    if cfg["planner"] == "cem":
+        d["cem"] = dict(iters=cfg["iters"], percent_elites=cfg["pct"], alpha=cfg["alpha"], compat=True)
+    return d
+
+
+# =================================================================================================== host (reference) planner
+class _OracleModel(object):
+    """dynamics_model stand-in for the verbatim reference controller: the oracle's predict for the config's weight-set mode."""
+
+    def __init__(self, O, prob, mode, sets):
+        self.O, self.prob, self.mode, self.sets = O, prob, mode, sets
+
+    def predict(self, obs, act):
+        O, p = self.O, self.prob
+        if self.mode == "ensemble":
+            return O.predict_ensemble_mean(obs, act, self.sets, p["norm"])
+        if self.mode == "per_env":
+            return O.predict_per_task(obs, act, self.sets, p["norm"])
+        return O.predict(obs, act, self.sets[0], p["norm"])
+
+
+def host_planner(cfg, O, prob, n, sets):
+    """Returns (callable planning once on the host, kind, description)."""
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from oracle.make_ref import import_reference_controller
+    ref_cls = import_reference_controller()
+    h, m = cfg["h"], cfg["m"]
+    if ref_cls is not None:
+        env = SyntheticEnv(cfg["env"])
+        kw = dict(n_candidates=n, horizon=h)
+        if cfg["planner"] == "cem":
+            kw.update(use_cem=True, num_cem_iters=cfg["iters"], percent_elites=cfg["pct"], alpha=cfg["alpha"])
+        ctrl = ref_cls("policy", env, _OracleModel(O, prob, cfg["mode"], sets), **kw)
+        return (lambda seed: ctrl.get_actions(prob["obs0"]), "reference",
+                "verbatim upstream MPCController.get_actions (oracle/_ref) over the oracle's float32 BLAS port of the dynamics model")
+    if cfg["planner"] == "cem":
+        def plan(seed):
+            rng = np.random.RandomState(seed)
+            zs = [rng.normal(size=(n, m, h * prob["act_dim"])) for _ in range(cfg["iters"])]
+            return O.cem_plan(prob["obs0"], zs, prob["low"], prob["high"], sets, prob["norm"], prob["reward_kind"], prob["dt"], h,
+                              cfg["pct"], cfg["alpha"], 1.0, cfg["mode"])
+    else:
+        def plan(seed):
+            actions = O.sample_rs_actions(seed, prob["low"], prob["high"], h, n * m)
+            return O.rs_plan(prob["obs0"], actions, sets, prob["norm"], prob["reward_kind"], prob["dt"], 1.0, cfg["mode"])
+    return plan, "port", "oracle restatement of MPCController.get_actions (numpy planner) over its float32 BLAS port of the dynamics model"
+
+
+def host_sets(cfg, O, prob):
+    if cfg["mode"] == "per_env":          # GrBAL: per-env adapted sets (the host adapt itself is part of the step below)
+        ctx = O.make_adapt_context(4, prob, cfg["m"], 16)
+        return O.adapt(*ctx, prob["param_sets"][0], prob["norm"], 1e-3), ctx
+    return prob["param_sets"], None
+
+
+def pick_blas_threads(plan_small):
+    """The numpy/OpenBLAS port is not fastest with every host thread (a 128-core box oversubscribes 2000x512 GEMMs): time one
+    small planning call per candidate thread count and keep the best, so the CPU baseline is the host planner at its best."""
+    from threadpoolctl import threadpool_limits
+    cores = os.cpu_count() or 1
+    cands = sorted(set([c for c in (4, 8, 16, 32, 64, cores) if c <= cores]))
+    best, best_t = cores, float("inf")
+    for c in cands:
+        with threadpool_limits(limits=c):
+            plan_small(0)
+            dt = float("inf")
+            for i in range(2):
+                t0 = time.perf_counter()
+                plan_small(1 + i)
+                dt = min(dt, time.perf_counter() - t0)
+        if dt < best_t * 0.97:
+            best, best_t = c, dt
+    return best
+
+
+def time_host_planner(cfg, n, budget_s, min_calls, max_calls, warmup):
+    """Times the host planner on a bounded sample: whole planning calls of the workload when a call takes < 2 s, else calls on a
+    fraction of the candidates (per-candidate cost is flat in N: every step is N-row GEMMs)."""
+    from threadpoolctl import threadpool_limits
+    O, prob = make_problem(cfg)
+    sets, ctx = host_sets(cfg, O, prob)
+    small, _, _ = host_planner(cfg, O, prob, max(64, min(n, 256)), sets)
+    cores = pick_blas_threads(small)
+    with threadpool_limits(limits=cores):
+        t0 = time.perf_counter()
+        small(0)
+        per_cand = (time.perf_counter() - t0) / max(64, min(n, 256))
+        n_s = n
+        while n_s > 250 and per_cand * n_s > 2.0:
+            n_s //= 2
+        plan, kind, what = host_planner(cfg, O, prob, n_s, sets)
+
+        def step(seed):
+            if ctx is not None:
+                O.adapt(*ctx, prob["param_sets"][0], prob["norm"], 1e-3)          # GrBAL: the env step adapts first
+            return plan(seed)
+        for i in range(warmup):
+            step(i)
+        calls = 0
+        t0 = time.perf_counter()
+        while calls < min_calls or (time.perf_counter() - t0 < budget_s and calls < max_calls):
+            step(100 + calls)
+            calls += 1
+        dt = (time.perf_counter() - t0) / calls
+    rollouts = n_s * cfg["m"] * cfg.get("iters", 1)
+    sample = "%d planning calls of N=%d%s, H=%d, m=%d, %d weight set(s) (%s); %s; best of {4..%d} BLAS threads = %d; %.1f s" % (
+        calls, n_s, "" if n_s == n else " (1/%d of the workload's candidates)" % (n // n_s), cfg["h"], cfg["m"], cfg["E"], cfg["mode"], what,
+        os.cpu_count(), cores, dt * calls)
+    return dict(value=rollouts / dt, unit="rollouts/s", cores=cores, kind=kind, sample=sample), dt, n_s
+
+
 def run_reference(args):
-    """The reference algorithm on the host: numpy planner loop (policies/mpc_controller.py:108-129 restated in oracle/)
-    over a float32 BLAS dense stack, all host threads.  TF1 itself cannot be installed here (no py3.12 wheels)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    O, prob = make_problem()
-    w = WORKLOAD
-    n = w["n_candidates"] * max(1, args.gpus)        # same whole-job workload as the CUDA arm at this N_gpus
-    from threadpoolctl import threadpool_limits
-    cores = pick_blas_threads(O, prob, w["horizon"])
-    limiter = threadpool_limits(limits=cores)
-
-    def plan(seed):
-        actions = O.sample_rs_actions(seed, prob["low"], prob["high"], w["horizon"], n * w["n_envs"])   # the reference samples inside the call
-        return O.rs_plan(prob["obs0"], actions, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
-
-    for i in range(args.warmup):
-        plan(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        plan(100 + i)
-    dt = (time.perf_counter() - t0) / max(1, args.steps)
-    value = n * w["n_envs"] / dt
-    line = dict(impl="reference", metric=METRIC, value=value, unit="rollouts/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", config=config_dict(args.gpus, sampler="numpy (host, inside the timed call)"),
-                cpu_baseline=dict(value=value, unit="rollouts/s", cores=cores, kind="port",
-                                  sample="%d full planning calls of the workload (numpy planner + fp32 BLAS MLP, best of {4..%d} BLAS threads = %d)" % (args.steps, os.cpu_count(), cores)),
-                e2e=dict(value=value, unit="rollouts/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    cfg = CONFIGS[args.config]
+    n_gpu, n_glob = split_candidates(cfg, args.gpus, args.scaling)
+    cpu, dt, n_s = time_host_planner(cfg, n_glob, budget_s=1e9, min_calls=args.steps, max_calls=args.steps, warmup=args.warmup)
+    line = dict(impl="reference", metric=METRIC, value=cpu["value"], unit="rollouts/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
+                dtype="f32", data="synthetic", config=config_dict(args.config, cfg, args.gpus, args.scaling, "numpy (host, inside the timed call)"),
+                cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit="rollouts/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
-
-
-def config_dict(gpus, sampler):
-    w = WORKLOAD
-    return dict(workload="BASELINE.md headline: HalfCheetah random-shooting MPC, N=%d candidates/GPU x H=%d, ensemble E=%d (mean of deltas), "
-                         "MLP 26-512-512-512-20, m=%d env" % (w["n_candidates"], w["horizon"], w["ensemble"], w["n_envs"]),
-                n_candidates_per_gpu=w["n_candidates"], global_candidates=w["n_candidates"] * max(1, gpus), horizon=w["horizon"],
-                ensemble=w["ensemble"], dyn_steps_per_call_per_gpu=w["n_candidates"] * w["horizon"] * w["ensemble"],
-                parallelism="candidate-shard x%d + 1 all-gather of (ret, idx, act)" % max(1, gpus), sampler=sampler,
-                l2="flushed between timed steps (256 MB write); inputs (0.96 MB candidates + 11 MB weights) are smaller than L2")
 
 
 # =================================================================================================== CUDA arm
@@ -197,6 +302,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from learning_to_adapt_b200 import _native as N
+    from learning_to_adapt_b200.dynamics.meta_mlp_dynamics import MetaMLPDynamicsModel
     from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
     from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
     from learning_to_adapt_b200.parallel import CandidateShard
@@ -209,31 +315,67 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    O, prob = make_problem()
-    w = WORKLOAD
-    env = SyntheticEnv(w["env"])
-    model = MLPDynamicsModel("dyn", env, hidden_sizes=w["hidden"], ensemble_size=w["ensemble"], device=local_rank)
-    for e, p in enumerate(prob["param_sets"]):
-        model.set_params(p, member=e)
+    cfg = CONFIGS[args.config]
+    if distributed and (cfg["planner"] == "cem" or cfg.get("grbal")):
+        raise SystemExit("config %s is a single-GPU workload" % args.config)
+    O, prob = make_problem(cfg)
+    env = SyntheticEnv(cfg["env"])
+    n, n_glob = split_candidates(cfg, world, args.scaling)
+    h, m, E = cfg["h"], cfg["m"], cfg["E"]
+    A = prob["act_dim"]
+    grbal = bool(cfg.get("grbal"))
+    if grbal:
+        model = MetaMLPDynamicsModel("dyn", env, hidden_sizes=cfg["hidden"], meta_batch_size=10, inner_learning_rate=1e-3, device=local_rank)
+        model.set_params(prob["param_sets"][0])
+    else:
+        model = MLPDynamicsModel("dyn", env, hidden_sizes=cfg["hidden"], ensemble_size=E if cfg["mode"] == "ensemble" else 1, device=local_rank)
+        for e, p in enumerate(prob["param_sets"]):
+            model.set_params(p, member=e)
     model.set_normalization(prob["norm"])
     eng = model._engine
     shard = CandidateShard() if distributed else None
-    n, h, m, E = w["n_candidates"], w["horizon"], w["n_envs"], w["ensemble"]
-    A = prob["act_dim"]
     low, high = eng._f32(prob["low"]), eng._f32(prob["high"])
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
-    pool = [torch.rand((h, n * m, A), device="cuda", generator=gen) * (high - low) + low for _ in range(4)]
     obs_dev = eng._f32(prob["obs0"])
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    win = None
+    if grbal:
+        # a running path of M + 2 transitions per env in the device window, then adapt once so sets 1..m are live
+        ctx = O.make_adapt_context(4, prob, m, 16)
+        win = model.make_adapt_window(m, 16)
+        for j in range(18):
+            win.push(np.stack([c[min(j, 15)] for c in ctx[0]]), np.stack([c[min(j, 15)] for c in ctx[1]]))
+        model.adapt_from_window(win, defer=False)
     set_mode, first_set, n_sets = model.planning_sets(m)
+    iters = cfg.get("iters", 1)
+    cem = cfg["planner"] == "cem"
+    ha = h * A
+    if cem:
+        pool = [torch.randn((n, m, ha), device="cuda", generator=gen) for _ in range(iters)]
+        num_elites = max(int(n * cfg["pct"]), 1)
+        clip_low, clip_high = eng._f32(np.concatenate([prob["low"]] * h)), eng._f32(np.concatenate([prob["high"]] * h))
+        mean = torch.zeros((m, ha), device="cuda", dtype=torch.float64)
+        std = torch.ones((m, ha), device="cuda", dtype=torch.float64)
+    else:
+        pool = [torch.rand((h, n * m, A), device="cuda", generator=gen) * (high - low) + low for _ in range(4)]
+
+    def rollout(actions, layout="thra", want_returns=False):
+        return eng.rollout(obs_dev, actions, n, h, prob["reward_kind"], prob["dt"], set_mode=set_mode, first_set=first_set,
+                           n_sets=n_sets, layout=layout, want_returns=want_returns)
 
     def plan_resident(i):
-        res = eng.rollout(obs_dev, pool[i % len(pool)], n, h, prob["reward_kind"], prob["dt"], set_mode=set_mode,
-                          first_set=first_set, n_sets=n_sets, want_returns=False)
+        """One planning call on device-resident inputs."""
+        if cem:
+            for it in range(iters):
+                samples, clipped = eng.cem_sample(pool[it], mean, std, clip_low, clip_high)
+                res = rollout(samples, "nmha", True)
+                eng.cem_refit(res["returns"], clipped, num_elites, cfg["alpha"], mean, std, compat=True)
+            return res
+        res = rollout(pool[i % len(pool)])
         if shard is not None:
-            return shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
-        return res["best_ret"], res["best_idx"], res["best_act"]
+            shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
+        return res
 
     def barrier():
         if distributed:
@@ -247,61 +389,91 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------------------------------------------------------- device-resident timing ("value", roofline)
-    for i in range(max(3, args.warmup)):
+    # ---------------------------------------------------------------- device-resident timing ("value")
+    W = max(3, args.warmup)
+    for i in range(W):
+        if cem:
+            mean.zero_(); std.fill_(1.0)
         plan_resident(i)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count
-    step_ms, kern_ms = [], []
+    step_ms = []
     barrier()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                                   # evict weights + candidates from L2 (outside the events)
-        s, k, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        if cem:
+            mean.zero_(); std.fill_(1.0)                        # mean = 0, std = 1 at the start of a call (:79-80)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        res = eng.rollout(obs_dev, pool[i % len(pool)], n, h, prob["reward_kind"], prob["dt"], set_mode=set_mode,
-                          first_set=first_set, n_sets=n_sets, want_returns=False)
-        k.record()
-        if shard is not None:
-            shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
+        plan_resident(i)
         e.record()
         torch.cuda.synchronize()
-        kern_ms.append(s.elapsed_time(k))
         step_ms.append(s.elapsed_time(e))
     barrier()
     wall = time.perf_counter() - wall0
     launches = eng.launch_count - launches0
     ms_step = max_over_ranks(float(np.mean(step_ms)))
+    rollouts_per_call = world * n * m * iters if args.scaling == "weak" else n_glob * m * iters
+    value = rollouts_per_call / (ms_step * 1e-3)
+
+    # ---------------------------------------------------------------- dominant kernel alone (roofline)
+    kern_ms = []
+    k_actions = (eng.cem_sample(pool[0], torch.zeros_like(mean), torch.ones_like(std), clip_low, clip_high)[0] if cem else pool[0])
+    for i in range(3 + min(args.steps, 20)):
+        flush.fill_(i & 0xFF)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rollout(k_actions, "nmha" if cem else "thra", cem)
+        e.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            kern_ms.append(s.elapsed_time(e))
     ms_kernel = max_over_ranks(float(np.mean(kern_ms)))
-    value = world * n * m / (ms_step * 1e-3)
 
     # ---------------------------------------------------------------- end-to-end through the public API
-    ctrl = MPCController("policy", env, model, n_candidates=n * world if distributed else n, horizon=h, sampler="device",
-                         parallel=shard)
+    def controller(sampler_name):
+        kw = dict(n_candidates=n_glob if distributed else n, horizon=h, sampler=sampler_name, parallel=shard)
+        if cem:
+            kw.update(use_cem=True, num_cem_iters=iters, percent_elites=cfg["pct"], alpha=cfg["alpha"])
+        c = MPCController("policy", env, model, **kw)
+        if grbal:
+            c.push_window = win
+        return c
+
     obs_host = np.array(prob["obs0"])
-    for i in range(max(3, args.warmup)):
-        ctrl.get_actions(obs_host)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        acts, _ = ctrl.get_actions(obs_host)                    # H2D obs, sample, K1 (+ all-gather), D2H actions
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    e2e_value = world * n * m / e2e_s
-    ctrl_np = MPCController("policy", env, model, n_candidates=n, horizon=h, sampler="numpy") if not distributed else None
-    if os.environ.get("L2A_BENCH_SKIP_CPU"):
-        ctrl_np = None
-    e2e_numpy = None
-    if ctrl_np is not None:
+
+    def e2e_rate(ctrl, steps):
+        def step():
+            if grbal:                                           # the GrBAL env step: samplers/sampler.py:81-91
+                model.switch_to_pre_adapt()
+                model.adapt_from_window(win)
+            return ctrl.get_actions(obs_host)
+        for i in range(W):
+            step()
+        barrier()
+        total = 0.0
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            if distributed:
+                dist.barrier()
+            t0 = time.perf_counter()
+            step()                                              # H2D obs, [adapt], sample, K1, [exchange], D2H actions
+            total += time.perf_counter() - t0
+        return max_over_ranks(total / steps)
+
+    ctrl = controller("device")
+    e2e_s = e2e_rate(ctrl, args.steps)
+    h2d, d2h = eng.last_plan_io_bytes()
+    e2e_value = rollouts_per_call / e2e_s
+    e2e_default = None
+    if not distributed:
         np.random.seed(0)
-        ctrl_np.get_actions(obs_host)
-        t0 = time.perf_counter()
-        for i in range(min(args.steps, 5)):
-            ctrl_np.get_actions(obs_host)
-        e2e_numpy = n * m / ((time.perf_counter() - t0) / min(args.steps, 5))
+        e2e_default = rollouts_per_call / e2e_rate(controller("numpy"), min(args.steps, 20))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -311,42 +483,33 @@ def run_cuda(args):
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only), bounded sample
     cpu = None
-    if world == 1 and not os.environ.get("L2A_BENCH_SKIP_CPU"):      # (development runs may skip the 15 s host leg)
-        from threadpoolctl import threadpool_limits
-        cores = pick_blas_threads(O, prob, h)
-        calls = 0
-        with threadpool_limits(limits=cores):
-            t0 = time.perf_counter()
-            while calls < 3 or (time.perf_counter() - t0 < 12.0 and calls < 40):
-                actions = O.sample_rs_actions(calls, prob["low"], prob["high"], h, n * m)
-                O.rs_plan(prob["obs0"], actions, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "ensemble")
-                calls += 1
-            dt = (time.perf_counter() - t0) / calls
-        cpu = dict(value=n * m / dt, unit="rollouts/s", cores=cores, kind="port",
-                   sample="%d full planning calls (N=%d,H=%d,E=%d) of the oracle port: numpy planner + fp32 BLAS MLP, best of {4..%d} BLAS "
-                          "threads = %d, %.1f s" % (calls, n, h, E, os.cpu_count(), cores, dt * calls))
+    if world == 1 and not os.environ.get("L2A_BENCH_SKIP_CPU"):      # (development runs may skip the host leg)
+        cpu, _, _ = time_host_planner(cfg, n, budget_s=12.0, min_calls=3, max_calls=40, warmup=1)
 
     peaks = load_peaks()
-    F = flops_per_dyn_step(prob["obs_dim"], prob["act_dim"], w["hidden"])
-    flops_per_launch = n * m * h * E * F
+    F = flops_per_dyn_step(prob["obs_dim"], prob["act_dim"], cfg["hidden"])
+    e_eff = E if cfg["mode"] == "ensemble" else 1
+    flops_per_launch = n * m * h * e_eff * F
     achieved = flops_per_launch / (ms_kernel * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(REPO, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("rollout_tc_kernel")
-    line = dict(metric=METRIC, value=value, unit="rollouts/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
-                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16x3-split (fp32 accumulate)",
-                data="synthetic", config=config_dict(world, "device (Philox, inside the e2e call; pre-materialised for `value`)"),
-                dyn_steps_per_s=world * n * m * h * E / (ms_step * 1e-3),
-                e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=int(m * prob["obs_dim"] * 4),
-                         d2h_bytes_per_step=int(m * A * 4), ms_per_call=e2e_s * 1e3,
-                         numpy_sampler_parity_mode_value=e2e_numpy),
+        traffic = json.load(open(tpath)).get("rollout_tc_kernel:" + args.config)
+    line = dict(metric=METRIC, value=value, unit="rollouts/s", n_gpus=world, steps=args.steps, warmup=W,
+                ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="bf16x3-split (fp32 accumulate)",
+                data="synthetic", config=config_dict(args.config, cfg, world, args.scaling,
+                                                     "device (Philox, inside the e2e call; pre-materialised for `value`)"),
+                dyn_steps_per_s=rollouts_per_call * h * e_eff / (ms_step * 1e-3),
+                e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                         ms_per_call=e2e_s * 1e3, default_sampler_value=e2e_default,
+                         note="value: sampler='device' (Philox); default_sampler_value: the package default, the reference's numpy "
+                              "stream regenerated on the device (N=1 only)"),
                 gpu_launches=int(launches),
                 roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"],
-                              traffic=traffic, kernel="rollout_tc_kernel<80>", kernel_ms=ms_kernel,
+                              traffic=traffic, kernel="rollout_tc_kernel", kernel_ms=ms_kernel,
                               flops_per_launch=flops_per_launch, peak_source=peaks["source"],
                               note="algorithmic FLOPs counted once; the kernel issues 3 bf16 MMA passes per product (split-bf16), so the "
-                                   "attainable fraction of the bf16 peak is 1/3"),
+                                   "attainable fraction of the bf16 peak is 1/3; traffic = ncu dram bytes per launch (profiles/)"),
                 cpu_baseline=cpu, clocks=clocks, wall_s_timed_region=wall)
     emit(line)
     if distributed:
@@ -359,6 +522,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

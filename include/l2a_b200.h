@@ -106,6 +106,14 @@ int l2a_model_set_params(l2a_ctx* ctx, l2a_model* model, int set, const float* c
                          void* stream);
 /* copies set `set` out into caller-provided device buffers (MLP.get_param_values, layers.py:71-79) */
 int l2a_model_get_params(l2a_ctx* ctx, l2a_model* model, int set, float* const* W, float* const* b, void* stream);
+/* Resident parameters in place (on-device training; replaces the sess.run(train_op) variable updates of
+ * mlp_dynamics.py:150-160 / meta_mlp_dynamics.py:218-226): device pointer to the fp32 block of weight set `set`
+ * (floats_per_set floats; kernel of layer l at w_off[l] as [in_l, out_l] row-major, bias at b_off[l]; w_off / b_off: HOST
+ * int32[n_hidden+1] or NULL).  The caller updates the values on the device and then calls l2a_model_refresh, which re-tiles
+ * sets [first_set, first_set + n_sets) for the tensor-core rollout. */
+int l2a_model_param_block(l2a_ctx* ctx, l2a_model* model, int set, float** ptr_out, int64_t* floats_per_set, int32_t* w_off,
+                          int32_t* b_off);
+int l2a_model_refresh(l2a_ctx* ctx, l2a_model* model, int first_set, int n_sets, void* stream);
 /* mean / denominators of the reference's normalize()/denormalize() (mlp_dynamics.py:265-270):
  * x_n = (x - mean) / den with den = std + 1e-10 already folded in by the caller (in float64), and
  * delta = y * delta_scale + delta_mean with delta_scale = std_delta + 1e-10.  Six device fp32 arrays. */
@@ -146,6 +154,8 @@ int l2a_plan_uses_graph(const l2a_plan* plan);   /* 1 once the call sequence has
 int l2a_plan_copy_candidates(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
 /* CEM plans: the returns [m, N] float32 of the LAST iteration's rollout (what mpc_controller.py:100 holds), to a HOST buffer */
 int l2a_plan_copy_returns(l2a_ctx* ctx, l2a_plan* plan, float* host_out);
+/* bytes the plan copies host->device / device->host inside every l2a_plan_run[_ex] call (its pinned input / output blocks) */
+int l2a_plan_io_bytes(const l2a_plan* plan, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 /* ---- the general host-buffer planning call ------------------------------------------------------------------------------
  * l2a_plan_create_ex / l2a_plan_run_ex extend the call above along two axes, still ONE C call and one CUDA-graph replay per

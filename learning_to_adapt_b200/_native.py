@@ -14,13 +14,13 @@ KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "l2a_last_error", "l2a_version", "l2a_ctx_create", "l2a_ctx_destroy", "l2a_ctx_launch_count",
     "l2a_model_create", "l2a_model_destroy", "l2a_model_set_params", "l2a_model_get_params",
-    "l2a_model_set_normalization", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
+    "l2a_model_set_normalization", "l2a_model_param_block", "l2a_model_refresh", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
     "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_debug_pair", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window", "l2a_plan_attach_window",
     "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_create_ex", "l2a_plan_run_ex", "l2a_plan_exchange_buffer",
-    "l2a_plan_attach_peers", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_plan_copy_returns", "l2a_sample_uniform", "l2a_tc_plan_query",
+    "l2a_plan_attach_peers", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_plan_copy_returns", "l2a_plan_io_bytes", "l2a_sample_uniform", "l2a_tc_plan_query",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     lib.l2a_model_set_params.argtypes = [vp, vp, i32, pp, pp, vp]
     lib.l2a_model_get_params.argtypes = [vp, vp, i32, pp, pp, vp]
     lib.l2a_model_set_normalization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.l2a_model_param_block.argtypes = [vp, vp, i32, pp, C.POINTER(C.c_int64), vp, vp]
+    lib.l2a_model_refresh.argtypes = [vp, vp, i32, i32, vp]
     lib.l2a_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_plan_create.argtypes = [vp, vp, C.POINTER(RolloutParams), f32, vp, vp, C.c_uint64, pp]
     lib.l2a_plan_run.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -95,6 +97,7 @@ def load():
     lib.l2a_plan_uses_graph.argtypes = [vp]
     lib.l2a_plan_copy_candidates.argtypes = [vp, vp, vp]
     lib.l2a_plan_copy_returns.argtypes = [vp, vp, vp]
+    lib.l2a_plan_io_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.l2a_tc_plan_query.argtypes = [C.POINTER(MlpDesc), vp]
     lib.l2a_sample_uniform.argtypes = [vp, vp, vp, vp, i64, i32, C.c_uint64, C.c_uint64, vp]
     lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]

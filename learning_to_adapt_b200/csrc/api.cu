@@ -251,6 +251,28 @@ extern "C" int l2a_model_get_params(l2a_ctx* c, l2a_model* m, int set, float* co
   return L2A_OK;
 }
 
+// Direct access to the resident fp32 parameters of weight sets (training on the device without a host round trip, SURVEY.md
+// 8(f) f2): the block of set `set` ([W_0 | b_0 | pad | W_1 | ...], floats_per_set floats, layer l at w_off / b_off as in
+// fill_dims).  After writing, l2a_model_refresh re-tiles the sets for the tensor-core rollout.
+extern "C" int l2a_model_param_block(l2a_ctx* c, l2a_model* m, int set, float** ptr_out, int64_t* floats_per_set, int32_t* w_off, int32_t* b_off) {
+  if (!c || !m || !ptr_out || !floats_per_set) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (set < 0 || set >= m->desc.n_sets) return fail(L2A_ERR_INVALID, "set %d out of range [0,%d)", set, m->desc.n_sets);
+  *ptr_out = m->params + (size_t)set * m->dims.set_stride;
+  *floats_per_set = m->dims.set_stride;
+  for (int l = 0; l < m->dims.n_layers; ++l) {
+    if (w_off) w_off[l] = m->dims.w_off[l];
+    if (b_off) b_off[l] = m->dims.b_off[l];
+  }
+  return L2A_OK;
+}
+
+extern "C" int l2a_model_refresh(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, void* stream) {
+  if (!c || !m) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (first_set < 0 || n_sets < 1 || first_set + n_sets > m->desc.n_sets) return fail(L2A_ERR_INVALID, "sets [%d,%d) out of range", first_set, first_set + n_sets);
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_prep(c, m, first_set, n_sets, (cudaStream_t)stream);
+}
+
 extern "C" int l2a_model_set_normalization(l2a_ctx* c, l2a_model* m, const float* obs_mean, const float* obs_den,
                                            const float* act_mean, const float* act_den, const float* delta_mean,
                                            const float* delta_scale, void* stream) {
@@ -523,6 +545,7 @@ struct l2a_plan {
   double* first64 = nullptr;     // [N*m, A] float64 first actions of the rows
   uint8_t* gflags = nullptr;     // MT19937 gauss attempts: accept flags, values
   double* gvals = nullptr;
+  int* gcounts = nullptr;        // per-chunk accept counts / offsets
   long long attempts = 0;        // attempt budget per iteration
   uint8_t* mt_scratch = nullptr; // two generator-state blocks (MtStateBlock) + per-iteration meta int[2 * iters]
   size_t out_mean = 0, out_meta = 0;
@@ -676,6 +699,7 @@ extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   cudaFree(pl->first64);
   cudaFree(pl->gflags);
   cudaFree(pl->gvals);
+  cudaFree(pl->gcounts);
   cudaFree(pl->mt_scratch);
   delete pl;
   return L2A_OK;
@@ -783,6 +807,7 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
       e = cudaMalloc(&pl->mt_raw, sizeof(uint32_t) * (size_t)blocks * kMtN);
       if (e == cudaSuccess) e = cudaMalloc(&pl->gflags, (size_t)pl->attempts);
       if (e == cudaSuccess) e = cudaMalloc(&pl->gvals, sizeof(double) * 2 * (size_t)pl->attempts);
+      if (e == cudaSuccess) e = cudaMalloc(&pl->gcounts, sizeof(int) * (size_t)((pl->attempts + kGaussChunk - 1) / kGaussChunk + 1));
       if (e == cudaSuccess) e = cudaMalloc(&pl->mt_scratch, 2 * sizeof(MtStateBlock) + 64);
     }
   }
@@ -914,13 +939,17 @@ static int plan_enqueue_cem(l2a_ctx* c, l2a_plan* pl) {
     if (mt) {
       // np.random.normal(size=(n, m, h*A)) (:85) continued from where the previous iteration left the generator
       MtStateBlock* state_out = last ? reinterpret_cast<MtStateBlock*>(pl->out_dev + pl->out_key) : &scratch[it & 1];
-      mt19937_raw_kernel<<<1, 256, 0, st>>>(state_in->key, &state_in->pos, pl->mt_words, pl->mt_raw);
+      mt19937_raw_kernel<<<1, kMtRawThreads, 0, st>>>(state_in->key, &state_in->pos, pl->mt_words, pl->mt_raw);
       mt19937_gauss_kernel<<<(unsigned)((pl->attempts + 255) / 256), 256, 0, st>>>(pl->mt_raw, &state_in->pos, pl->attempts, pl->gflags, pl->gvals);
-      mt19937_gauss_scatter_kernel<<<1, 1024, 0, st>>>(pl->gflags, pl->gvals, pl->attempts, tot, &state_in->has_gauss, &state_in->cached,
-                                                       pl->z64, meta_out + 2 * it, &state_out->cached);
+      const int n_chunks = (int)((pl->attempts + kGaussChunk - 1) / kGaussChunk);
+      CUDA_TRY(cudaMemsetAsync(meta_out + 2 * it, 0xFF, 2 * sizeof(int32_t), st));                 // attempts consumed = -1 until found
+      mt19937_gauss_count_kernel<<<n_chunks, 256, 0, st>>>(pl->gflags, pl->attempts, pl->gcounts);
+      mt19937_gauss_scan_kernel<<<1, 1024, 0, st>>>(pl->gcounts, n_chunks);
+      mt19937_gauss_scatter_kernel<<<n_chunks, 256, 0, st>>>(pl->gflags, pl->gvals, pl->gcounts, pl->attempts, tot, &state_in->has_gauss,
+                                                             &state_in->cached, pl->z64, meta_out + 2 * it, &state_out->cached);
       mt19937_state_out_kernel<<<1, 256, 0, st>>>(pl->mt_raw, &state_in->pos, 0, meta_out + 2 * it, state_out->key, &state_out->pos);
       CUDA_TRY(cudaMemcpyAsync(&state_out->has_gauss, meta_out + 2 * it + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-      c->launches += 4;
+      c->launches += 6;
       state_in = state_out;
     } else {
       sample_normal_kernel<<<(unsigned)((tot + 4 * 256 - 1) / (4 * 256)), 256, 0, st>>>(pl->z64, tot, pl->o.seed, call_dev, (uint32_t)it);
@@ -938,7 +967,8 @@ static int plan_enqueue_cem(l2a_ctx* c, l2a_plan* pl) {
                                                                reinterpret_cast<double*>(pl->out_dev + pl->out_final));   // :106
       c->launches++;
     }
-    dim3 g1((n + 255) / 256, mm);
+    dim3 g1((n + 255) / 256, mm, kRankSplit);
+    CUDA_TRY(cudaMemsetAsync(pl->rank, 0, sizeof(int32_t) * (size_t)n * mm, st));
     cem_rank_kernel<<<g1, 256, 0, st>>>(pl->returns, n, pl->rank);                                   // :101
     cem_refit_kernel<double><<<ha, 256, 0, st>>>(pl->rank, pl->clipped, n, mm, ha, pl->o.cem_num_elites, pl->o.cem_alpha, pl->o.cem_compat, mean, std_);   // :102-104
     c->launches += 2;
@@ -986,7 +1016,7 @@ static int plan_enqueue_rs(l2a_ctx* c, l2a_plan* pl) {
   if (mt) {
     const uint32_t* key = reinterpret_cast<const uint32_t*>(pl->in_dev + pl->in_key);
     const int* pos = reinterpret_cast<const int*>(pl->in_dev + pl->in_pos);
-    mt19937_raw_kernel<<<1, 256, 0, st>>>(key, pos, pl->mt_words, pl->mt_raw);
+    mt19937_raw_kernel<<<1, kMtRawThreads, 0, st>>>(key, pos, pl->mt_words, pl->mt_raw);
     c->launches++;
     const long long blocks = (total + 255) / 256;
     mt19937_uniform_slice_kernel<<<(unsigned)blocks, 256, 0, st>>>(pl->mt_raw, pos, pl->consts64, pl->consts64 + A, total,
@@ -1155,6 +1185,13 @@ extern "C" int l2a_plan_uses_graph(const l2a_plan* pl) {
   for (int f = 0; f < 4; ++f)
     if (pl->exec_flags[f]) return 1;
   return 0;
+}
+
+extern "C" int l2a_plan_io_bytes(const l2a_plan* pl, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!pl || !h2d_bytes || !d2h_bytes) return fail(L2A_ERR_INVALID, "NULL argument");
+  *h2d_bytes = pl->in_bytes;
+  *d2h_bytes = pl->out_bytes;
+  return L2A_OK;
 }
 
 extern "C" int l2a_plan_copy_returns(l2a_ctx* c, l2a_plan* pl, float* host_out) {
@@ -1498,7 +1535,8 @@ extern "C" int l2a_cem_refit(l2a_ctx* c, const float* returns, const float* clip
   if (n < 1 || m < 1 || ha < 1 || num_elites < 1 || num_elites > n) return fail(L2A_ERR_INVALID, "bad n/m/ha/num_elites");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 g1((n + 255) / 256, m);
+  dim3 g1((n + 255) / 256, m, kRankSplit);
+  CUDA_TRY(cudaMemsetAsync(rank_scratch, 0, sizeof(int32_t) * (size_t)n * m, st));
   cem_rank_kernel<<<g1, 256, 0, st>>>(returns, n, rank_scratch);
   c->launches++;
   CUDA_TRY(cudaGetLastError());

@@ -45,19 +45,32 @@ __global__ void cem_init_kernel(double* __restrict__ mean, double* __restrict__ 
 }
 
 // rank[e][c] = position of candidate c in the descending-return order of env e (= np.argsort(-returns) inverse).
-// Ties: the lower index ranks first.  grid = (ceil(n/256), m).
-__global__ void cem_rank_kernel(const float* __restrict__ returns, int n, int* __restrict__ rank) {
+// Ties: the lower index ranks first.  Counting rank: candidate c is preceded by every j with a larger return (or an equal one
+// and a lower index).  grid = (ceil(n/256), m, kRankSplit): the j range is split over blockIdx.z, each part counted against a
+// shared-memory tile of the returns and added atomically -- `rank` must be ZERO on entry (the launcher clears it).
+constexpr int kRankSplit = 4;
+constexpr int kRankTile = 1024;
+__global__ void __launch_bounds__(256) cem_rank_kernel(const float* __restrict__ returns, int n, int* __restrict__ rank) {
+  __shared__ float tile[kRankTile];
   const int e = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
   const float* r = returns + (size_t)e * n;
-  const float rc = r[c];
+  const float rc = (c < n) ? r[c] : 0.f;
+  const int per = (n + kRankSplit - 1) / kRankSplit;
+  const int j_begin = blockIdx.z * per, j_end = min(n, j_begin + per);
   int cnt = 0;
-  for (int j = 0; j < n; ++j) {
-    const float rj = r[j];
-    cnt += (rj > rc) || (rj == rc && j < c);
+  for (int j0 = j_begin; j0 < j_end; j0 += kRankTile) {
+    const int lim = min(kRankTile, j_end - j0);
+    for (int i = threadIdx.x; i < lim; i += blockDim.x) tile[i] = r[j0 + i];
+    __syncthreads();
+#pragma unroll 8
+    for (int i = 0; i < lim; ++i) {
+      const float rj = tile[i];
+      cnt += (rj > rc) || (rj == rc && (j0 + i) < c);
+    }
+    __syncthreads();
   }
-  rank[(size_t)e * n + c] = cnt;
+  if (c < n && cnt) atomicAdd(&rank[(size_t)e * n + c], cnt);
 }
 
 // Elite statistics + refit.  One CTA per action dimension j (< H*A).

@@ -136,24 +136,39 @@ class MetaMLPDynamicsModel(MLPDynamicsModel):
 
     def fit(self, obs, act, obs_next, epochs=1000, compute_normalization=True, valid_split_ratio=None,
             rolling_average_persitency=None, verbose=False, log_tabular=False):
-        """MAML outer loop (meta_mlp_dynamics.py:167-274): torch autograd through the one-step inner update.
-        Host-side glue, off the planning hot path."""
-        from learning_to_adapt_b200.dynamics.fit import fit_maml
-        assert obs.ndim == 3 and act.ndim == 3 and obs_next.ndim == 3
+        """MAML outer loop (meta_mlp_dynamics.py:167-274) on the engine's resident prior theta (weight set 0): per step a meta
+        batch of `meta_batch_size` windows of 2*batch_size consecutive transitions (_get_batch :353-383, same np.random draws),
+        Adam on the mean post-update loss differentiated through the one-step inner update (second order, :96-140); paths are
+        split into train / validation and aggregated over fit() calls (:191-204); validation = plain MSE of theta (:242)."""
+        from learning_to_adapt_b200.dynamics.fit import fit_maml, train_test_split
+        assert obs.ndim == 3 and obs.shape[2] == self.obs_space_dims
+        assert obs_next.ndim == 3 and obs_next.shape[2] == self.obs_space_dims
+        assert act.ndim == 3 and act.shape[2] == self.action_space_dims
+        valid_split_ratio = self.valid_split_ratio if valid_split_ratio is None else valid_split_ratio
+        rolling_average_persitency = self.rolling_average_persitency if rolling_average_persitency is None else rolling_average_persitency
+        assert 1 > valid_split_ratio >= 0
         if compute_normalization or self.normalization is None:
             self.compute_normalization(obs, act, obs_next)
         obs_n = normalize(obs, *self.normalization["obs"])
         act_n = normalize(act, *self.normalization["act"])
         delta_n = normalize(obs_next - obs, *self.normalization["delta"])
-        params = fit_maml(self._engine.get_params(0), obs_n, act_n, delta_n, epochs=epochs, batch_size=self.batch_size,
-                          meta_batch_size=self.meta_batch_size, learning_rate=self.learning_rate,
-                          inner_learning_rate=self.inner_learning_rate,
-                          valid_split_ratio=self.valid_split_ratio if valid_split_ratio is None else valid_split_ratio,
-                          rolling_average_persitency=(self.rolling_average_persitency
-                                                      if rolling_average_persitency is None else rolling_average_persitency),
-                          device=self._engine.device, verbose=verbose)
-        self._engine.set_params(0, params)
+        o_tr, a_tr, d_tr, o_te, a_te, d_te = train_test_split(obs_n, act_n, delta_n, test_split_ratio=valid_split_ratio)
+        if len(o_te) == 0:
+            raise ValueError("valid_split_ratio=%r leaves no validation path out of %d" % (valid_split_ratio, obs.shape[0]))
+        self._aggregate(dict(obs=o_tr, act=a_tr, delta=d_tr), dict(obs=o_te, act=a_te, delta=d_te))
+        train, test = self._device_dataset(self._dataset_train), self._device_dataset(self._dataset_test)
+        if train["x"].shape[1] <= 2 * self.batch_size:
+            raise ValueError("paths of %d steps are too short for (pre, post) windows of 2 x batch_size = %d steps (:356)"
+                             % (train["x"].shape[1], 2 * self.batch_size))
+        params, adam = self._train_views(0)
+        stats = fit_maml(params, adam, train, test, epochs=epochs, batch_size=self.batch_size, meta_batch_size=self.meta_batch_size,
+                         learning_rate=self.learning_rate, inner_learning_rate=self.inner_learning_rate,
+                         rolling_average_persitency=rolling_average_persitency, verbose=verbose)
+        self._engine.refresh_sets(0, 1)
         self._adapted = False
+        self._pending_window = None
+        self._log_fit(stats, log_tabular, {"AvgModelEpochTime": float(np.mean(stats["epoch_times"])), "Post-Loss": stats["post_loss"],
+                                           "Pre-Loss": stats["pre_loss"], "Epochs": stats["epochs"]})
 
     def __getstate__(self):
         state = dict()

@@ -139,23 +139,65 @@ class MLPDynamicsModel(Serializable):
         assert delta.ndim == 2
         return np.asarray(obs, np.float64) + delta
 
-    # ------------------------------------------------------------------ fit (host-side glue, off the hot path)
+    # ------------------------------------------------------------------ fit: on the engine's resident parameters (f2)
+    def _aggregate(self, train, test):
+        """self._dataset_train / _dataset_test keep every fit() call's normalised split and training runs on everything
+        collected so far (mlp_dynamics.py:119-129; the trainer passes only the newest iteration's samples, mb_trainer.py:89-94)."""
+        if getattr(self, "_dataset_test", None) is None:
+            self._dataset_train, self._dataset_test = train, test
+        else:
+            for k in ("obs", "act", "delta"):
+                self._dataset_test[k] = np.concatenate([self._dataset_test[k], test[k]])
+                self._dataset_train[k] = np.concatenate([self._dataset_train[k], train[k]])
+
+    def _device_dataset(self, d):
+        dev = self._engine.device
+        x = np.concatenate([d["obs"], d["act"]], axis=-1).astype(np.float32)           # the float32 placeholders (:63-68)
+        return dict(x=torch.as_tensor(x, device=dev), y=torch.as_tensor(d["delta"].astype(np.float32), device=dev))
+
+    def _train_views(self, member):
+        """(leaf tensors onto the resident parameters of `member`, its Adam slots) -- created once, kept like TF variables."""
+        from learning_to_adapt_b200.dynamics.fit import AdamState
+        if not hasattr(self, "_fit_state"):
+            self._fit_state = {}
+        if member not in self._fit_state:
+            views = [v.requires_grad_(True) for v in self._engine.param_views(member)]
+            self._fit_state[member] = (views, AdamState(views))
+        return self._fit_state[member]
+
     def fit(self, obs, act, obs_next, epochs=1000, compute_normalization=True, valid_split_ratio=None,
             rolling_average_persitency=None, verbose=False, log_tabular=False):
-        """Adam on mean((delta_n - f(x_n))^2), validation-based early stop (mlp_dynamics.py:91-202).  Runs in torch on
-        the engine's device and writes the result back into the engine's weight sets.  Off the planning hot path."""
-        from learning_to_adapt_b200.dynamics.fit import fit_mlp
+        """Adam on mean((delta_n - f(x_n))^2) over everything collected so far, validation-based early stop
+        (mlp_dynamics.py:91-202), on the engine's resident parameters (no host round trip of the weights).
+        log_tabular: the statistics the reference logs (Epochs, AvgModelEpochTime) are left in ``self.last_fit_stats`` and, when
+        a ``logger`` with logkv() has been attached as ``self.logger``, logged through it."""
+        from learning_to_adapt_b200.dynamics.fit import fit_mlp, train_test_split
+        assert obs.ndim == 2 and obs.shape[1] == self.obs_space_dims
+        assert obs_next.ndim == 2 and obs_next.shape[1] == self.obs_space_dims
+        assert act.ndim == 2 and act.shape[1] == self.action_space_dims
+        valid_split_ratio = self.valid_split_ratio if valid_split_ratio is None else valid_split_ratio
+        rolling_average_persitency = self.rolling_average_persitency if rolling_average_persitency is None else rolling_average_persitency
+        assert 1 > valid_split_ratio >= 0
         if compute_normalization or self.normalization is None:
             self.compute_normalization(obs, act, obs_next)
         obs_n, act_n, delta_n = self._normalize_data(obs, act, obs_next)
+        o_tr, a_tr, d_tr, o_te, a_te, d_te = train_test_split(obs_n, act_n, delta_n, test_split_ratio=valid_split_ratio)
+        self._aggregate(dict(obs=o_tr, act=a_tr, delta=d_tr), dict(obs=o_te, act=a_te, delta=d_te))
+        train, test = self._device_dataset(self._dataset_train), self._device_dataset(self._dataset_test)
+        stats = None
         for e in range(self.ensemble_size):
-            params = fit_mlp(self._engine.get_params(e), obs_n, act_n, delta_n, epochs=epochs, batch_size=self.batch_size,
-                             learning_rate=self.learning_rate,
-                             valid_split_ratio=self.valid_split_ratio if valid_split_ratio is None else valid_split_ratio,
-                             rolling_average_persitency=(self.rolling_average_persitency
-                                                         if rolling_average_persitency is None else rolling_average_persitency),
-                             device=self._engine.device, verbose=verbose)
-            self._engine.set_params(e, params)
+            params, adam = self._train_views(e)
+            stats = fit_mlp(params, adam, train, test, epochs=epochs, batch_size=self.batch_size, learning_rate=self.learning_rate,
+                            rolling_average_persitency=rolling_average_persitency, verbose=verbose)
+        self._engine.refresh_sets(0, self.ensemble_size)
+        self._log_fit(stats, log_tabular, dict(AvgModelEpochTime=float(np.mean(stats["epoch_times"])), Epochs=stats["epochs"]))
+
+    def _log_fit(self, stats, log_tabular, kv):
+        self.last_fit_stats = dict(stats, **kv)
+        logger = getattr(self, "logger", None)
+        if log_tabular and logger is not None:
+            for k, v in kv.items():
+                logger.logkv(k, v)
 
     # ------------------------------------------------------------------ pickling: ctor args + statistics + weights
     def __getstate__(self):

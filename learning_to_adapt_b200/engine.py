@@ -118,6 +118,27 @@ class PlanningEngine(object):
             out[key] = t.cpu().numpy()
         return out
 
+    def param_views(self, set_idx):
+        """Torch views [W_0, b_0, W_1, b_1, ...] ONTO the resident fp32 parameters of weight set `set_idx` (no copy): training
+        updates them in place on the device; call refresh_sets() afterwards so the tensor-core tiles follow."""
+        nl = len(self._layer_shapes)
+        ptr, count = C.c_void_p(), C.c_int64()
+        w_off, b_off = (C.c_int32 * nl)(), (C.c_int32 * nl)()
+        N.check(self.lib.l2a_model_param_block(self._ctx, self._model, int(set_idx), C.byref(ptr), C.byref(count), w_off, b_off))
+
+        class _Block(object):
+            __cuda_array_interface__ = dict(shape=(int(count.value),), typestr="<f4", data=(int(ptr.value), False), version=2)
+
+        flat = torch.as_tensor(_Block(), device=self.device)
+        views = []
+        for l, (din, dout) in enumerate(self._layer_shapes):
+            views.append(flat[w_off[l]:w_off[l] + din * dout].view(din, dout))
+            views.append(flat[b_off[l]:b_off[l] + dout])
+        return views
+
+    def refresh_sets(self, first_set=0, n_sets=1):
+        N.check(self.lib.l2a_model_refresh(self._ctx, self._model, int(first_set), int(n_sets), _stream()))
+
     def set_normalization(self, normalization):
         """normalization: the reference's dict {'obs': (mean, std), 'act': (...), 'delta': (...)} in float64
         (mlp_dynamics.py:253-262).  Denominators std + 1e-10 are formed in float64, then rounded to fp32."""
@@ -338,6 +359,12 @@ class PlanningEngine(object):
         out = np.empty((m, n), np.float32)
         N.check(self.lib.l2a_plan_copy_returns(self._ctx, self._last_plan["handle"], out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def last_plan_io_bytes(self):
+        """(host->device, device->host) bytes copied inside every call of the most recent plan."""
+        a, b = C.c_uint64(), C.c_uint64()
+        N.check(self.lib.l2a_plan_io_bytes(self._last_plan["handle"], C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def last_plan_uses_graph(self):
         return bool(self.lib.l2a_plan_uses_graph(self._last_plan["handle"]))

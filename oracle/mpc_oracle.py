@@ -461,3 +461,150 @@ def sample_rs_actions_device(seed, call_index, low, high, horizon, rows):
     span = (high32 - low32).astype(np.float32)           # the kernel forms hi - lo in float32
     val = span[j].astype(np.float64) * u + low32[j].astype(np.float64)   # exact product (24 x 24 bits), one rounding below = fma
     return val.astype(np.float32).reshape(horizon, rows, A)
+
+
+# --------------------------------------------------------------------------------------------------
+# training: the reference's fit procedures restated on the host
+#   MLPDynamicsModel.fit      dynamics/mlp_dynamics.py:91-202   (Adam on the batch MSE, batches of consecutive rows)
+#   MetaMLPDynamicsModel.fit  dynamics/meta_mlp_dynamics.py:96-140, 167-274, 353-383 (MAML: Adam on the post-update loss)
+# tf.train.AdamOptimizer (TF 1.13, published update rule -- TensorFlow is not installable here, PARITY UNPINNED for the optimiser):
+#   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  theta -= lr_t * m / (sqrt(v) + eps)
+# The numpy draws (train/validation split, batch order, MAML windows) are the ones the product makes, in the same order, so
+# a seeded product fit and a seeded oracle fit see identical batches.
+# --------------------------------------------------------------------------------------------------
+def mlp_loss_and_grads(x32, y32, params):
+    """mean((y - f(x))^2) and its gradient w.r.t. every parameter, float32 (manual backprop of the dense/ReLU stack)."""
+    keys = list(params.keys())
+    n_layers = len(keys) // 2
+    out, acts = mlp_forward(x32, params, keep_activations=True)
+    rows, dout = out.shape
+    loss = np.float32(np.mean((y32 - out) ** 2))
+    g = (np.float32(2.0) / np.float32(rows * dout)) * (out - y32)
+    grads = OrderedDict()
+    for l in reversed(range(n_layers)):
+        grads[keys[2 * l]] = (acts[l].T @ g).astype(np.float32)
+        grads[keys[2 * l + 1]] = g.sum(axis=0).astype(np.float32)
+        if l > 0:
+            g = (g @ params[keys[2 * l]].T) * (acts[l] > 0).astype(np.float32)
+    return loss, OrderedDict((k, grads[k]) for k in keys)
+
+
+class AdamTF(object):
+    def __init__(self, params, lr, b1=0.9, b2=0.999, eps=1e-8, dtype=np.float32):
+        self.lr, self.b1, self.b2, self.eps, self.t = lr, b1, b2, eps, 0
+        self.m = OrderedDict((k, np.zeros_like(v, dtype=dtype)) for k, v in params.items())
+        self.v = OrderedDict((k, np.zeros_like(v, dtype=dtype)) for k, v in params.items())
+
+    def step(self, params, grads):
+        self.t += 1
+        lr_t = self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for k in params:
+            g = grads[k]
+            self.m[k] = (self.b1 * self.m[k] + (1.0 - self.b1) * g).astype(g.dtype)
+            self.v[k] = (self.b2 * self.v[k] + (1.0 - self.b2) * g * g).astype(g.dtype)
+            params[k] = (params[k] - lr_t * self.m[k] / (np.sqrt(self.v[k]) + self.eps)).astype(g.dtype)
+
+
+def train_test_split(obs, act, delta, test_split_ratio=0.2):
+    """mlp_dynamics.py:273-285 (np.random.shuffle on the global stream)."""
+    indices = np.arange(obs.shape[0])
+    np.random.shuffle(indices)
+    split_idx = int(obs.shape[0] * (1 - test_split_ratio))
+    tr, te = indices[:split_idx], indices[split_idx:]
+    return obs[tr], act[tr], delta[tr], obs[te], act[te], delta[te]
+
+
+def fit_mlp(params, obs, act, obs_next, norm, epochs, batch_size, learning_rate, valid_split_ratio=0.2, persistency=0.99):
+    """One MLPDynamicsModel.fit call from fresh optimiser state on raw (obs, act, obs_next); returns (params, valid losses)."""
+    obs_n, act_n = normalize(obs, *norm["obs"]), normalize(act, *norm["act"])
+    delta_n = normalize(obs_next - obs, *norm["delta"])
+    o_tr, a_tr, d_tr, o_te, a_te, d_te = train_test_split(obs_n, act_n, delta_n, valid_split_ratio)
+    xt, yt = np.concatenate([o_tr, a_tr], axis=1).astype(np.float32), d_tr.astype(np.float32)
+    xv, yv = np.concatenate([o_te, a_te], axis=1).astype(np.float32), d_te.astype(np.float32)
+    params = OrderedDict((k, v.copy()) for k, v in params.items())
+    adam = AdamTF(params, learning_rate)
+    avg = prev = None
+    valid = []
+    for epoch in range(epochs):
+        starts = np.arange(0, xt.shape[0], batch_size)
+        starts = starts[np.random.permutation(len(starts))]
+        for s in starts:
+            _, grads = mlp_loss_and_grads(xt[s:s + batch_size], yt[s:s + batch_size], params)
+            adam.step(params, grads)
+        vl = float(np.mean((yv - mlp_forward(xv, params)) ** 2))
+        valid.append(vl)
+        if avg is None:
+            avg, prev = (vl / 1.5, vl / 2) if vl < 0 else (1.5 * vl, 2 * vl)
+        avg = persistency * avg + (1.0 - persistency) * vl
+        if prev < avg or epoch == epochs - 1:
+            break
+        prev = avg
+    return params, valid
+
+
+def fit_maml(params, obs, act, obs_next, norm, epochs, batch_size, meta_batch_size, learning_rate, inner_learning_rate,
+             valid_split_ratio=0.2, persistency=0.99):
+    """One MetaMLPDynamicsModel.fit call from fresh optimiser state; obs/act/obs_next [paths, T, dim].  The second-order
+    gradient of the post-update loss is taken by torch autograd on the CPU in FLOAT64 (an independent execution of the math
+    the product runs in float32 on the device)."""
+    import torch
+    obs_n, act_n = normalize(obs, *norm["obs"]), normalize(act, *norm["act"])
+    delta_n = normalize(obs_next - obs, *norm["delta"])
+    o_tr, a_tr, d_tr, o_te, a_te, d_te = train_test_split(obs_n, act_n, delta_n, valid_split_ratio)
+    f32 = lambda a: torch.tensor(np.asarray(a, np.float32).astype(np.float64))      # the float32 feed, then float64 math
+    xtr, ytr = f32(np.concatenate([o_tr, a_tr], axis=2)), f32(d_tr)
+    xte, yte = f32(np.concatenate([o_te, a_te], axis=2)), f32(d_te)
+    keys = list(params.keys())
+    theta = [torch.tensor(params[k].astype(np.float64), requires_grad=True) for k in keys]
+    np_theta = OrderedDict((k, params[k].astype(np.float64)) for k in keys)
+    adam = AdamTF(np_theta, learning_rate, dtype=np.float64)
+
+    def fwd(x, ps):
+        h = x
+        for l in range(len(ps) // 2):
+            h = h @ ps[2 * l] + ps[2 * l + 1]
+            if l < len(ps) // 2 - 1:
+                h = torch.relu(h)
+        return h
+
+    def get_batch(x):
+        num_paths, len_path = x.shape[:2]
+        ip = np.random.randint(0, num_paths, size=meta_batch_size)
+        ib = np.random.randint(batch_size, len_path - batch_size, size=meta_batch_size)
+        return ip, ib
+
+    steps_train = max(int(np.prod(xtr.shape[:2]) / (meta_batch_size * batch_size * 2)), 1)
+    steps_test = max(int(np.prod(xte.shape[:2]) / (meta_batch_size * batch_size * 2)), 1)
+    avg = prev = None
+    valid = []
+    for epoch in range(epochs):
+        for _ in range(steps_train):
+            ip, ib = get_batch(xtr)
+            post = []
+            for p, b in zip(ip, ib):
+                xw, yw = xtr[p, b - batch_size:b + batch_size], ytr[p, b - batch_size:b + batch_size]
+                pre_loss = torch.mean((yw[:batch_size] - fwd(xw[:batch_size], theta)) ** 2)
+                g = torch.autograd.grad(pre_loss, theta, create_graph=True)
+                adapted = [w - inner_learning_rate * gi for w, gi in zip(theta, g)]
+                post.append(torch.mean((yw[batch_size:] - fwd(xw[batch_size:], adapted)) ** 2))
+            grads = torch.autograd.grad(torch.stack(post).mean(), theta)
+            adam.step(np_theta, OrderedDict((k, gi.numpy()) for k, gi in zip(keys, grads)))
+            with torch.no_grad():
+                for t, k in zip(theta, keys):
+                    t.copy_(torch.tensor(np_theta[k]))
+        vls = []
+        with torch.no_grad():
+            for _ in range(steps_test):
+                ip, ib = get_batch(xte)
+                xs = torch.cat([xte[p, b - batch_size:b + batch_size] for p, b in zip(ip, ib)])
+                ys = torch.cat([yte[p, b - batch_size:b + batch_size] for p, b in zip(ip, ib)])
+                vls.append(float(torch.mean((ys - fwd(xs, theta)) ** 2)))
+        vl = float(np.mean(vls))
+        valid.append(vl)
+        if avg is None:
+            avg, prev = (vl / 1.5, vl / 2) if vl < 0 else (1.5 * vl, 2 * vl)
+        avg = persistency * avg + (1.0 - persistency) * vl
+        if prev < avg or epoch == epochs - 1:
+            break
+        prev = avg
+    return OrderedDict((k, np_theta[k].astype(np.float32)) for k in keys), valid

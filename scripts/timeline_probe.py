@@ -9,7 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import mpc_oracle as O  # noqa: E402
 from learning_to_adapt_b200.engine import PlanningEngine  # noqa: E402
 
-env, hidden, n, h, m, nsets, mode = "half_cheetah", (512, 512, 512), 2000, 20, 1, 5, 2
+CFG = {"headline": ("half_cheetah", (512, 512, 512), 2000, 20, 1, 5, 2), "cfg1": ("half_cheetah", (512, 512), 500, 10, 1, 1, 0),
+       "cfg2i": ("half_cheetah", (512, 512, 512), 1000, 15, 5, 5, 1), "cfg1p": ("half_cheetah", (512, 512), 2000, 20, 10, 1, 0)}
+env, hidden, n, h, m, nsets, mode = CFG[sys.argv[1] if len(sys.argv) > 1 else "headline"]
 prob = O.make_problem(env, hidden_sizes=hidden, n_sets=nsets, m=m, seed=0)
 eng = PlanningEngine(prob["obs_dim"], prob["act_dim"], hidden, n_sets=nsets)
 for i, p in enumerate(prob["param_sets"]):
