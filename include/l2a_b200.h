@@ -331,6 +331,9 @@ int l2a_shard_select(l2a_ctx* ctx, const float* gathered, int G, int m, int A, f
  * stage), out_stages, stages_per_set, set_bytes (low and high 32 bits).  Used by the CPU-side tests of the host logic. */
 int l2a_tc_plan_query(const l2a_mlp_desc* desc, int32_t* out8);
 
+/* Diagnostics and microbenchmarks: only in the DEBUG build of the library (-DL2A_DEBUG_KERNELS -> lib/libl2a_b200_debug.so,
+ * `python -m learning_to_adapt_b200.build --debug`); the product library does not contain them. */
+#ifdef L2A_DEBUG_KERNELS
 /* ---- diagnostics -----------------------------------------------------------------------------------------
  * Single tcgen05 GEMM tile through the same descriptor / TMEM code as the rollout kernel:
  * C[128, n] = A[128, k] * B[n, k]^T with A, B fp32 split into bf16 hi/lo on the device. */
@@ -357,6 +360,8 @@ int l2a_debug_pair(l2a_ctx* ctx, int mode, int iters, int copy_bytes, long long*
 /* When set (device int64[128]), CTA 0 of the tcgen05 rollout records clock64() stamps of its pipeline events during
  * horizon step 1 (see L2A_STAMP slots in csrc/rollout_tc.cuh).  NULL switches it off. */
 int l2a_debug_set_timeline(l2a_ctx* ctx, long long* buf128);
+
+#endif /* L2A_DEBUG_KERNELS */
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,7 @@ missing or no B200 is present the product path raises."""
 import ctypes as C
 import os
 
-from .build import LIB_PATH
+from .build import DEBUG_LIB_PATH, LIB_PATH
 
 L2A_MAX_LAYERS = 8
 
@@ -15,13 +15,17 @@ EXPORTS = [
     "l2a_last_error", "l2a_version", "l2a_ctx_create", "l2a_ctx_destroy", "l2a_ctx_launch_count",
     "l2a_model_create", "l2a_model_destroy", "l2a_model_set_params", "l2a_model_get_params",
     "l2a_model_set_normalization", "l2a_model_param_block", "l2a_model_refresh", "l2a_rollout", "l2a_predict", "l2a_adapt", "l2a_cem_sample", "l2a_cem_refit",
-    "l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_shard_pack", "l2a_shard_select", "l2a_debug_mma_rate", "l2a_debug_pair", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
+    "l2a_shard_pack", "l2a_shard_select", "l2a_rnn_model_create", "l2a_rnn_model_destroy",
     "l2a_rnn_model_set_params", "l2a_rnn_model_set_normalization", "l2a_rnn_rollout", "l2a_rnn_predict",
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window", "l2a_plan_attach_window",
     "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_create_ex", "l2a_plan_run_ex", "l2a_plan_exchange_buffer",
     "l2a_plan_attach_peers", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_plan_copy_returns", "l2a_plan_io_bytes", "l2a_sample_uniform", "l2a_tc_plan_query",
 ]
+
+
+# only in the debug build (lib/libl2a_b200_debug.so, -DL2A_DEBUG_KERNELS)
+DEBUG_EXPORTS = ["l2a_debug_umma_tile", "l2a_debug_stream", "l2a_debug_set_timeline", "l2a_debug_mma_rate", "l2a_debug_pair"]
 
 
 class MlpDesc(C.Structure):
@@ -53,19 +57,20 @@ class PlanIO(C.Structure):
                 ("cem_std_out", C.c_void_p), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load the shared library (once) and declare the prototypes.  Raises ImportError when it is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = os.environ.get("L2A_B200_LIB", LIB_PATH)      # development: A/B two builds on the same box
+def load(debug=False):
+    """Load the shared library (once per flavour) and declare the prototypes.  Raises ImportError when it is missing.
+    debug=True: the debug build, which also exports the l2a_debug_* diagnostics (tests of the MMA tile path, probes)."""
+    if debug in _libs:
+        return _libs[debug]
+    default = DEBUG_LIB_PATH if debug else LIB_PATH
+    path = os.environ.get("L2A_B200_LIB", default) if not debug else default      # development: A/B two builds on the same box
     if not os.path.exists(path):
         raise ImportError(
-            "learning_to_adapt_b200: %s is missing. Build it with `python -m learning_to_adapt_b200.build` "
-            "(nvcc, sm_100a). There is no CPU fallback for the planning path." % LIB_PATH)
+            "learning_to_adapt_b200: %s is missing. Build it with `python -m learning_to_adapt_b200.build%s` "
+            "(nvcc, sm_100a). There is no CPU fallback for the planning path." % (path, " --debug" if debug else ""))
     lib = C.CDLL(path)
     vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     pp = C.POINTER(vp)
@@ -113,27 +118,29 @@ def load():
     lib.l2a_plan_attach_window.argtypes = [vp, vp, vp, f32, i32, i32]
     lib.l2a_cem_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.l2a_cem_refit.argtypes = [vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp]
-    lib.l2a_debug_umma_tile.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
-    lib.l2a_debug_set_timeline.argtypes = [vp, vp]
     lib.l2a_rnn_model_create.argtypes = [vp, i32, i32, i32, pp]
     lib.l2a_rnn_model_destroy.argtypes = [vp, vp]
     lib.l2a_rnn_model_set_params.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_rnn_model_set_normalization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_rnn_rollout.argtypes = [vp, vp, C.POINTER(RolloutParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.l2a_rnn_predict.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
-    lib.l2a_debug_mma_rate.argtypes = [vp, i32, i32, i32, vp, vp]
-    lib.l2a_debug_pair.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.l2a_shard_pack.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.l2a_shard_select.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
-    lib.l2a_debug_stream.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
-    for name in EXPORTS:
+    if debug:
+        lib.l2a_debug_umma_tile.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+        lib.l2a_debug_set_timeline.argtypes = [vp, vp]
+        lib.l2a_debug_mma_rate.argtypes = [vp, i32, i32, i32, vp, vp]
+        lib.l2a_debug_pair.argtypes = [vp, i32, i32, i32, vp, vp]
+        lib.l2a_debug_stream.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    for name in EXPORTS + (DEBUG_EXPORTS if debug else []):
         fn = getattr(lib, name)
         if name not in ("l2a_last_error", "l2a_ctx_launch_count"):
             fn.restype = i32
-    _lib = lib
+    _libs[debug] = lib
     return lib
 
 
 def check(status):
     if status != 0:
-        raise RuntimeError("libl2a_b200: %s (status %d)" % (load().l2a_last_error().decode(), status))
+        msgs = [lib.l2a_last_error().decode() for lib in _libs.values()]
+        raise RuntimeError("libl2a_b200: %s (status %d)" % (" / ".join(m for m in msgs if m) or "error", status))

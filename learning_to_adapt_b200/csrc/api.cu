@@ -13,7 +13,9 @@
 #include "adapt.cuh"
 #include "cem.cuh"
 #include "common.cuh"
+#ifdef L2A_DEBUG_KERNELS
 #include "debug_tile.cuh"
+#endif
 #include "mt19937.cuh"
 #include "rollout_simt.cuh"
 #include "rollout_rnn_simt.cuh"
@@ -1546,6 +1548,7 @@ extern "C" int l2a_cem_refit(l2a_ctx* c, const float* returns, const float* clip
   return L2A_OK;
 }
 
+#ifdef L2A_DEBUG_KERNELS
 // --------------------------------------------------------------------------------------------- diagnostics
 extern "C" int l2a_debug_umma_tile(l2a_ctx* c, const float* A, const float* B, float* C, int n, int k, int variant, void* stream) {
   if (!c || !A || !B || !C) return fail(L2A_ERR_INVALID, "NULL argument");
@@ -1583,6 +1586,8 @@ extern "C" int l2a_debug_set_timeline(l2a_ctx* c, long long* buf128) {
   return L2A_OK;
 }
 
+#endif  // L2A_DEBUG_KERNELS
+
 // --------------------------------------------------------------------------------------------- K3 shard glue
 extern "C" int l2a_shard_pack(l2a_ctx* c, const float* best_ret, const int32_t* best_idx, const float* best_act,
                               int64_t idx_offset, int m, int A, float* packed, void* stream) {
@@ -1606,6 +1611,7 @@ extern "C" int l2a_shard_select(l2a_ctx* c, const float* gathered, int G, int m,
   return L2A_OK;
 }
 
+#ifdef L2A_DEBUG_KERNELS
 extern "C" int l2a_debug_pair(l2a_ctx* c, int mode, int iters, int copy_bytes, long long* cycles_out, void* stream) {
   if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
   if (mode < 0 || mode > 1 || iters < 1 || copy_bytes < 16 || copy_bytes > 16384 || copy_bytes % 16 != 0)
@@ -1653,6 +1659,8 @@ extern "C" int l2a_debug_mma_rate(l2a_ctx* c, int nc, int mode, int iters, long 
   CUDA_TRY(cudaGetLastError());
   return L2A_OK;
 }
+
+#endif  // L2A_DEBUG_KERNELS
 
 // --------------------------------------------------------------------------------------------- ReBAL (LSTM) model
 struct l2a_rnn_model {

@@ -271,7 +271,13 @@ struct TcSmem {
 
 template <int V> struct IntTag { static constexpr int value = V; };
 
+#ifdef L2A_DEBUG_KERNELS
 #define L2A_STAMP(slot) do { if (a.timeline && blockIdx.x == 0 && t == 1 && (threadIdx.x & 31) == 0) a.timeline[(slot)] = clock64(); } while (0)
+#define L2A_TIMELINE(expr) do { expr; } while (0)
+#else
+#define L2A_STAMP(slot) do { } while (0)
+#define L2A_TIMELINE(expr) do { } while (0)
+#endif
 
 // DMAX: compile-time bound of the observation dimension (24 with act_dim <= 8, or 48): sizes the register-resident candidate state and the
 // unrolled env-step code (a 48-wide instance costs HalfCheetah's D = 20 twice the instruction-cache footprint).
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           const int cpe = (l == 0) ? nkc : 2;                       // activation chunks published per event
           const int ch0 = (l == 0) ? kTcXChunk : 0;                 // layer 0 reads its single input chunk from kTcXChunk
           L2A_STAMP(4 * l + 0);
-          if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64();   // step length
+          L2A_TIMELINE(if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64());   // step length
           // phase A: K-outer over the chunks as the previous layer's epilogue publishes them
           for (int ev = 0; ev < nsrc; ++ev) {
             if (l == 0) {
@@ -843,9 +849,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
           for (int g = used; g < need; ++g) store_group(g, z);
         }
       }
-      if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[70] = clock64();
+      L2A_TIMELINE(if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[70] = clock64());
       umma::fence_proxy_async_smem();
-      if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[71] = clock64();
+      L2A_TIMELINE(if (warp == 0 && t_stamp == 1 && a.timeline && blockIdx.x == 0 && lane == 0) a.timeline[71] = clock64());
       umma::tc_fence_before();
       umma::mbar_arrive(x_ready);
     };
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
       pair_a = (pair_a + 2) % 3;
       umma::tc_fence_before();
       if (warp == 0) L2A_STAMP(61);
-      if (a.timeline && blockIdx.x < 5 && t == 1 && tid == 0) a.timeline[86 + 2 * blockIdx.x] = clock64();       // member skew
+      L2A_TIMELINE(if (a.timeline && blockIdx.x < 5 && t == 1 && tid == 0) a.timeline[86 + 2 * blockIdx.x] = clock64());       // member skew
       if (ensemble) {
         // Exchange of the E members' deltas through L2: every candidate thread publishes its own row (DMAX floats, 16-byte
         // stores), the cluster meets on the peers' mbarriers (release / acquire at cluster scope), then the thread reads
@@ -963,7 +969,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const TcArgs 
         }
       }
       if (warp == 0) L2A_STAMP(62);
-      if (a.timeline && blockIdx.x < 5 && t == 1 && tid == 0) a.timeline[87 + 2 * blockIdx.x] = clock64();
+      L2A_TIMELINE(if (a.timeline && blockIdx.x < 5 && t == 1 && tid == 0) a.timeline[87 + 2 * blockIdx.x] = clock64());
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;

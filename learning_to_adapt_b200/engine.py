@@ -33,10 +33,10 @@ def param_keys(n_hidden):
 class PlanningEngine(object):
     """One (process, device) planning context + one dynamics model with `n_sets` resident weight sets."""
 
-    def __init__(self, obs_dim, act_dim, hidden_sizes, n_sets=1, device=0):
+    def __init__(self, obs_dim, act_dim, hidden_sizes, n_sets=1, device=0, debug=False):
         if not torch.cuda.is_available():
             raise RuntimeError("learning_to_adapt_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-        self.lib = N.load()
+        self.lib = N.load(debug=debug)                # debug=True: the build that also carries the l2a_debug_* diagnostics
         self.device = torch.device("cuda", device)
         self.obs_dim, self.act_dim = int(obs_dim), int(act_dim)
         self.hidden_sizes = tuple(int(h) for h in hidden_sizes)

@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from learning_to_adapt_b200 import _native as N  # noqa: E402
 
-lib = N.load()
+lib = N.load(debug=True)
 ctx = C.c_void_p()
 N.check(lib.l2a_ctx_create(0, C.byref(ctx)))
 out = torch.zeros(4, dtype=torch.int64, device="cuda")

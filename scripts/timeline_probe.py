@@ -13,7 +13,7 @@ CFG = {"headline": ("half_cheetah", (512, 512, 512), 2000, 20, 1, 5, 2), "cfg1":
        "cfg2i": ("half_cheetah", (512, 512, 512), 1000, 15, 5, 5, 1), "cfg1p": ("half_cheetah", (512, 512), 2000, 20, 10, 1, 0)}
 env, hidden, n, h, m, nsets, mode = CFG[sys.argv[1] if len(sys.argv) > 1 else "headline"]
 prob = O.make_problem(env, hidden_sizes=hidden, n_sets=nsets, m=m, seed=0)
-eng = PlanningEngine(prob["obs_dim"], prob["act_dim"], hidden, n_sets=nsets)
+eng = PlanningEngine(prob["obs_dim"], prob["act_dim"], hidden, n_sets=nsets, debug=True)
 for i, p in enumerate(prob["param_sets"]):
     eng.set_params(i, p)
 eng.set_normalization(prob["norm"])

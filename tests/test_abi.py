@@ -10,17 +10,22 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
+def _declared_symbols(debug=False):
+    """l2a_* functions include/l2a_b200.h declares; debug=True: the ones inside #ifdef L2A_DEBUG_KERNELS only."""
     text = open(os.path.join(REPO, "include", "l2a_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(l2a_[a-z0-9_]+)\s*\(", text)))
+    m = re.search(r"#ifdef L2A_DEBUG_KERNELS(.*?)#endif", text, flags=re.S)
+    assert m, "the diagnostics must sit behind L2A_DEBUG_KERNELS"
+    part = m.group(1) if debug else text.replace(m.group(0), "")
+    return sorted(set(re.findall(r"\b(l2a_[a-z0-9_]+)\s*\(", part)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():
     from learning_to_adapt_b200 import _native
-    from learning_to_adapt_b200.build import LIB_PATH, build
+    from learning_to_adapt_b200.build import DEBUG_LIB_PATH, LIB_PATH, build
     build()
-    assert os.path.exists(LIB_PATH)
+    build(debug=True)
+    assert os.path.exists(LIB_PATH) and os.path.exists(DEBUG_LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     declared = _declared_symbols()
     assert len(declared) >= 15
@@ -28,6 +33,15 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), "libl2a_b200.so does not export %s" % name
     assert sorted(_native.EXPORTS) == declared
     assert _native.load().l2a_version() >= 100
+    # the diagnostics exist only in the debug build
+    debug_syms = _declared_symbols(debug=True)
+    assert sorted(_native.DEBUG_EXPORTS) == debug_syms and len(debug_syms) == 5
+    dbg = ctypes.CDLL(DEBUG_LIB_PATH)
+    for name in debug_syms:
+        assert hasattr(dbg, name), "libl2a_b200_debug.so does not export %s" % name
+        assert not hasattr(lib, name), "the product library must not carry %s" % name
+    for name in declared:
+        assert hasattr(dbg, name)
 
 
 def test_struct_layouts_match_header():

@@ -81,6 +81,41 @@ def test_pickle_round_trip_keeps_weights_and_statistics():
     np.testing.assert_array_equal(clone.predict(obs, act), model.predict(obs, act))
 
 
+def test_snapshot_written_by_the_reference_loads_into_the_b200_model():
+    """f4: tests/golden/reference_snapshot_params.pkl was written by the reference's own pickling code (its Serializable,
+    MetaMLPDynamicsModel.__getstate__, Layer.__getstate__ and the logger's joblib.dump; tests/golden/make_golden_snapshot.py).
+    Through the drop-in import hook the upstream class path resolves to the B200 model, whose __setstate__ must rebuild the
+    engine with the stored constructor arguments, statistics and weights."""
+    import joblib
+    import learning_to_adapt_b200.dropin as dropin
+    from learning_to_adapt_b200.dynamics.meta_mlp_dynamics import MetaMLPDynamicsModel
+    dropin.install()
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    snap = joblib.load(os.path.join(here, "reference_snapshot_params.pkl"))
+    expect = np.load(os.path.join(here, "reference_snapshot_expect.npz"))
+    assert snap["itr"] == 3
+    model = snap["dynamics_model"]
+    assert isinstance(model, MetaMLPDynamicsModel)
+    assert model.meta_batch_size == 7 and model.inner_learning_rate == 0.05 and model.batch_size == 16
+    assert model.hidden_sizes == (32, 32)
+    got = model.get_params()
+    assert list(got.keys()) == ["hidden_0/kernel", "hidden_0/bias", "hidden_1/kernel", "hidden_1/bias", "output/kernel", "output/bias"]
+    for k, v in got.items():
+        np.testing.assert_array_equal(v, expect[k.replace("/", ".")])
+    np.testing.assert_array_equal(model.normalization["obs"][0], expect["obs_mean"])
+    np.testing.assert_array_equal(model.normalization["obs"][1], expect["obs_std"])
+    # the loaded model plans: predict == oracle predict with the stored weights / statistics
+    prob = O.make_problem("half_cheetah", hidden_sizes=(32, 32), n_sets=1, m=1, seed=21)
+    rng = np.random.RandomState(2)
+    obs = prob["norm"]["obs"][0] + rng.normal(size=(6, prob["obs_dim"]))
+    act = rng.uniform(prob["low"], prob["high"], size=(6, prob["act_dim"]))
+    np.testing.assert_allclose(model.predict(obs, act), O.predict(obs, act, prob["param_sets"][0], prob["norm"]), rtol=1e-4, atol=1e-5)
+    # and a snapshot of the B200 model has the reference's layout again (round trip)
+    state = model.__getstate__()
+    assert set(state.keys()) == {"init_args", "normalization", "networks"} and set(state["init_args"].keys()) == {"__args", "__kwargs"}
+    assert list(state["networks"][0].keys()) == ["network_params"]
+
+
 def test_fit_then_plan():
     """fit() (torch glue, off the hot path) leaves the engine with trained weights + statistics the planner uses."""
     from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel

@@ -25,7 +25,7 @@ def _native():
 @pytest.mark.parametrize("n,k", [(16, 64), (32, 128), (80, 64), (80, 256), (128, 128)])
 def test_umma_tile_matches_fp32_matmul(n, k):
     from learning_to_adapt_b200.engine import PlanningEngine
-    eng = PlanningEngine(20, 6, (128,), n_sets=1)
+    eng = PlanningEngine(20, 6, (128,), n_sets=1, debug=True)       # l2a_debug_umma_tile lives in the debug build
     rng = np.random.RandomState(n + k)
     A = rng.normal(size=(128, k)).astype(np.float32)
     B = rng.normal(size=(n, k)).astype(np.float32)
