@@ -16,7 +16,9 @@ is split over the ranks).
 
 value  : whole-job candidate-rollouts/s with the inputs already resident in HBM (pre-materialised candidate tensor / normal
          draws), CUDA-event timed per step on the launching stream, L2 flushed (256 MB write) between steps, max over ranks.
-         At N>1 the step includes the exchange of the per-rank best triple (NCCL all-gather through torch.distributed).
+         At N>1 the step includes the exchange of the per-rank best triple: the library's peer-memory kernel over NVLink (the
+         same kernel the e2e call runs inside its graph); `exchange.ms_per_step_nccl_allgather` is the same step with one NCCL
+         all-gather through torch.distributed instead.
 e2e    : the same metric through the public API call MPCController.get_actions(obs ndarray) -> ndarray = ONE host-buffer C-ABI
          call (l2a_plan_run_ex): host->device copy of the observations (+ RNG state), candidate sampling on the device, K1
          (cfg4: all CEM iterations; cfg2: window gather + K2 adapt in front, window push behind; N>1: peer-memory exchange of
@@ -169,7 +171,7 @@ def config_dict(name, cfg, gpus, scaling, sampler):
              n_candidates_per_gpu=n_gpu, global_candidates=n_glob, horizon=cfg["h"], n_envs=cfg["m"], weight_sets=cfg["E"],
              set_mode=cfg["mode"], planner=cfg["planner"],
              dyn_steps_per_call_per_gpu=n_gpu * cfg["m"] * cfg["h"] * (cfg["E"] if cfg["mode"] == "ensemble" else 1) * cfg.get("iters", 1),
-             parallelism="candidate-shard x%d, winners exchanged once per call (value: NCCL all-gather; e2e: peer-memory exchange inside the C call)" % max(1, gpus),
+             parallelism="candidate-shard x%d, winners exchanged once per call over peer memory (NVLink); NCCL (torch.distributed) for the bench's barriers / max-over-ranks" % max(1, gpus),
              sampler=sampler,
              l2="flushed between timed steps (256 MB write); inputs (candidates + weight tiles, < 40 MB) are smaller than L2")
     if cfg["planner"] == "cem":
@@ -364,8 +366,9 @@ def run_cuda(args):
         return eng.rollout(obs_dev, actions, n, h, prob["reward_kind"], prob["dt"], set_mode=set_mode, first_set=first_set,
                            n_sets=n_sets, layout=layout, want_returns=want_returns)
 
-    def plan_resident(i):
-        """One planning call on device-resident inputs."""
+    def plan_resident(i, exchange="peer"):
+        """One planning call on device-resident inputs.  N>1: + the exchange of the ranks' winners, either the library's
+        peer-memory kernel (what the e2e call uses) or one NCCL all-gather through torch.distributed."""
         if cem:
             for it in range(iters):
                 samples, clipped = eng.cem_sample(pool[it], mean, std, clip_low, clip_high)
@@ -374,7 +377,10 @@ def run_cuda(args):
             return res
         res = rollout(pool[i % len(pool)])
         if shard is not None:
-            shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
+            if exchange == "peer":
+                eng.exchange_resident(res, out=xrec)
+            else:
+                shard.combine(res["best_ret"], res["best_idx"], res["best_act"], rank * n, engine=eng)
         return res
 
     def barrier():
@@ -388,6 +394,23 @@ def run_cuda(args):
         t = torch.tensor([x], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---------------------------------------------------------------- the public-API controller (its sharded plan also serves
+    # the device-resident exchange below)
+    def controller(sampler_name):
+        kw = dict(n_candidates=n_glob if distributed else n, horizon=h, sampler=sampler_name, parallel=shard)
+        if cem:
+            kw.update(use_cem=True, num_cem_iters=iters, percent_elites=cfg["pct"], alpha=cfg["alpha"])
+        c = MPCController("policy", env, model, **kw)
+        if grbal:
+            c.push_window = win
+        return c
+
+    obs_host = np.array(prob["obs0"])
+    ctrl = controller("device")
+    if distributed:
+        ctrl.get_actions(obs_host)                               # creates the plan and attaches the peers' exchange buffers
+        xrec = torch.empty((m, 2 + A), device="cuda", dtype=torch.float64)
 
     # ---------------------------------------------------------------- device-resident timing ("value")
     W = max(3, args.warmup)
@@ -407,6 +430,7 @@ def run_cuda(args):
         flush.fill_(i & 0xFF)                                   # evict weights + candidates from L2 (outside the events)
         if cem:
             mean.zero_(); std.fill_(1.0)                        # mean = 0, std = 1 at the start of a call (:79-80)
+        barrier()                                               # ranks start the step together (outside the events)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         plan_resident(i)
@@ -415,6 +439,20 @@ def run_cuda(args):
         step_ms.append(s.elapsed_time(e))
     barrier()
     wall = time.perf_counter() - wall0
+    nccl_ms = None
+    if distributed:                                             # the same step with the NCCL all-gather as the exchange
+        ts = []
+        for i in range(3 + min(args.steps, 10)):
+            flush.fill_(i & 0xFF)
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            plan_resident(i, exchange="nccl")
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(s.elapsed_time(e))
+        nccl_ms = max_over_ranks(float(np.mean(ts)))
     launches = eng.launch_count - launches0
     ms_step = max_over_ranks(float(np.mean(step_ms)))
     rollouts_per_call = world * n * m * iters if args.scaling == "weak" else n_glob * m * iters
@@ -435,17 +473,6 @@ def run_cuda(args):
     ms_kernel = max_over_ranks(float(np.mean(kern_ms)))
 
     # ---------------------------------------------------------------- end-to-end through the public API
-    def controller(sampler_name):
-        kw = dict(n_candidates=n_glob if distributed else n, horizon=h, sampler=sampler_name, parallel=shard)
-        if cem:
-            kw.update(use_cem=True, num_cem_iters=iters, percent_elites=cfg["pct"], alpha=cfg["alpha"])
-        c = MPCController("policy", env, model, **kw)
-        if grbal:
-            c.push_window = win
-        return c
-
-    obs_host = np.array(prob["obs0"])
-
     def e2e_rate(ctrl, steps):
         def step():
             if grbal:                                           # the GrBAL env step: samplers/sampler.py:81-91
@@ -466,7 +493,6 @@ def run_cuda(args):
             total += time.perf_counter() - t0
         return max_over_ranks(total / steps)
 
-    ctrl = controller("device")
     e2e_s = e2e_rate(ctrl, args.steps)
     h2d, d2h = eng.last_plan_io_bytes()
     e2e_value = rollouts_per_call / e2e_s
@@ -505,6 +531,8 @@ def run_cuda(args):
                          note="value: sampler='device' (Philox); default_sampler_value: the package default, the reference's numpy "
                               "stream regenerated on the device (N=1 only)"),
                 gpu_launches=int(launches),
+                exchange=(dict(value_uses="peer-memory exchange kernel (l2a_plan_exchange_resident)", ms_per_step_peer=ms_step,
+                               ms_per_step_nccl_allgather=nccl_ms) if distributed else None),
                 roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"],
                               traffic=traffic, kernel="rollout_tc_kernel", kernel_ms=ms_kernel,
                               flops_per_launch=flops_per_launch, peak_source=peaks["source"],

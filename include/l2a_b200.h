@@ -224,6 +224,10 @@ int l2a_plan_create_ex(l2a_ctx* ctx, l2a_model* model, const l2a_rollout_params*
 int l2a_plan_run_ex(l2a_ctx* ctx, l2a_plan* plan, const double* obs, l2a_plan_io* io, void* stream);
 int l2a_plan_exchange_buffer(l2a_plan* plan, void** ptr_out, uint64_t* bytes_out);
 int l2a_plan_attach_peers(l2a_ctx* ctx, l2a_plan* plan, void* const* peer_bufs /* HOST array [shard_world] of device pointers */);
+/* the exchange step alone on DEVICE-resident per-rank results of l2a_rollout (best_ret [m], best_idx [m] local, best_act [m, A]):
+ * final_rec_out [m, 2 + A] float64 DEVICE = (return, global candidate index, action) of the winner over all ranks, on every rank */
+int l2a_plan_exchange_resident(l2a_ctx* ctx, l2a_plan* plan, const float* best_ret, const int32_t* best_idx, const float* best_act,
+                               double* final_rec_out, void* stream);
 int l2a_ipc_get_handle(l2a_ctx* ctx, void* dev_ptr, void* handle64_out);
 int l2a_ipc_open_handle(l2a_ctx* ctx, const void* handle64, void** dev_ptr_out);
 int l2a_ipc_close_handle(l2a_ctx* ctx, void* dev_ptr);

@@ -560,7 +560,8 @@ struct l2a_plan {
   cudaGraphExec_t exec_flags[4] = {nullptr, nullptr, nullptr, nullptr};   // one captured graph per flag combination
   // candidate shard (o.shard_world > 1): exchange buffer of THIS rank (peers write into it) and the peers' buffers
   uint8_t* xbuf = nullptr;
-  size_t xbuf_bytes = 0;
+  size_t xbuf_bytes = 0, xarea_bytes = 0;
+  uint8_t* res_scratch = nullptr;   // l2a_plan_exchange_resident: this rank's records + its sequence counter
   void** peers_dev = nullptr;    // device array [world] of peer xbuf pointers
   bool peers_attached = false;
   long long calls_flags[4] = {0, 0, 0, 0};
@@ -587,7 +588,8 @@ static_assert(sizeof(MtStateBlock) == 2512, "MtStateBlock layout");
 struct ShardXArgs {
   void* const* peers;            // [world] device pointers to the ranks' exchange buffers (own included)
   int rank, world, m, rec;
-  const uint32_t* call_index;    // 64-bit call counter in the input block (low word first)
+  const uint32_t* call_index;    // 64-bit call counter in the input block (low word first), or NULL:
+  unsigned long long* own_seq;   // ... a device counter this kernel advances itself (l2a_plan_exchange_resident)
   const double* mine;            // [m][rec] this rank's records
   double* final_rec;             // [m][rec] winner per env
 };
@@ -603,7 +605,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 
 __global__ void __launch_bounds__(128) shard_exchange_kernel(const ShardXArgs a) {
   const int tid = threadIdx.x;
-  const unsigned long long seq = ((unsigned long long)a.call_index[0] | ((unsigned long long)a.call_index[1] << 32)) + 1ull;
+  __shared__ unsigned long long s_seq;
+  if (tid == 0) s_seq = a.call_index ? (((unsigned long long)a.call_index[0] | ((unsigned long long)a.call_index[1] << 32)) + 1ull)
+                                     : ++(*a.own_seq);
+  __syncthreads();
+  const unsigned long long seq = s_seq;
   const int par = (int)(seq & 1ull);
   const size_t flag_bytes = ((size_t)a.world * 8 + 255) / 256 * 256;
   const size_t blk = (size_t)a.m * a.rec;                                   // doubles per (parity, rank) block
@@ -692,6 +698,7 @@ extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   cudaFree(pl->consts);
   cudaFree(pl->consts64);
   cudaFree(pl->xbuf);
+  cudaFree(pl->res_scratch);
   cudaFree(pl->peers_dev);
   cudaFree(pl->z64);
   cudaFree(pl->clipped);
@@ -820,10 +827,14 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
     if (e == cudaSuccess) e = cudaMalloc(&pl->act64_t0, sizeof(double) * (size_t)rows * A);
   }
   if (world > 1 && e == cudaSuccess) {
-    pl->xbuf_bytes = align_up((size_t)world * 8, 256) + sizeof(double) * 2 * (size_t)world * mm * pl->rec;
+    // two independent exchange areas in one allocation: [0] for l2a_plan_run_ex, [1] for l2a_plan_exchange_resident
+    pl->xarea_bytes = align_up(align_up((size_t)world * 8, 256) + sizeof(double) * 2 * (size_t)world * mm * pl->rec, 256);
+    pl->xbuf_bytes = 2 * pl->xarea_bytes;
     e = cudaMalloc(&pl->xbuf, pl->xbuf_bytes);
     if (e == cudaSuccess) e = cudaMemset(pl->xbuf, 0, pl->xbuf_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->peers_dev, sizeof(void*) * world);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->peers_dev, sizeof(void*) * 2 * world);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->res_scratch, sizeof(double) * (size_t)mm * pl->rec + 64);
+    if (e == cudaSuccess) e = cudaMemset(pl->res_scratch, 0, sizeof(double) * (size_t)mm * pl->rec + 64);
   }
   if (e != cudaSuccess) {
     l2a_plan_destroy(c, pl);
@@ -881,10 +892,12 @@ extern "C" int l2a_plan_attach_peers(l2a_ctx* c, l2a_plan* pl, void* const* peer
   if (!c || !pl || !peer_bufs) return fail(L2A_ERR_INVALID, "NULL argument");
   if (pl->o.shard_world < 2) return fail(L2A_ERR_INVALID, "the plan is not sharded");
   CUDA_TRY(cudaSetDevice(c->device));
-  std::vector<void*> ptrs(pl->o.shard_world);
-  for (int g = 0; g < pl->o.shard_world; ++g) {
+  const int world = pl->o.shard_world;
+  std::vector<void*> ptrs(2 * (size_t)world);
+  for (int g = 0; g < world; ++g) {
     ptrs[g] = (g == pl->o.shard_rank) ? (void*)pl->xbuf : peer_bufs[g];
     if (!ptrs[g]) return fail(L2A_ERR_INVALID, "peer buffer %d is NULL", g);
+    ptrs[world + g] = (uint8_t*)ptrs[g] + pl->xarea_bytes;
   }
   CUDA_TRY(cudaMemcpy(pl->peers_dev, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice));
   pl->peers_attached = true;
@@ -1051,6 +1064,7 @@ static int plan_enqueue_rs(l2a_ctx* c, l2a_plan* pl) {
     xa.m = mm;
     xa.rec = pl->rec;
     xa.call_index = call_dev;
+    xa.own_seq = nullptr;
     xa.mine = rec;
     xa.final_rec = fin;
     shard_exchange_kernel<<<1, 128, 0, st>>>(xa);
@@ -1187,6 +1201,35 @@ extern "C" int l2a_plan_uses_graph(const l2a_plan* pl) {
   for (int f = 0; f < 4; ++f)
     if (pl->exec_flags[f]) return 1;
   return 0;
+}
+
+// The shard exchange alone, on DEVICE-resident per-rank results (what l2a_rollout wrote): record -> peer exchange -> winner
+// records final_rec_out [m, 2 + A] float64 (return, global index, action) on every rank.  Uses its own exchange buffers and
+// sequence counter (a second set next to the ones l2a_plan_run_ex uses), so it may be interleaved with plan runs as long as
+// every rank makes the same sequence of calls.
+extern "C" int l2a_plan_exchange_resident(l2a_ctx* c, l2a_plan* pl, const float* best_ret, const int32_t* best_idx, const float* best_act,
+                                          double* final_rec_out, void* stream) {
+  if (!c || !pl || !best_ret || !best_idx || !best_act || !final_rec_out) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (pl->o.shard_world < 2 || !pl->peers_attached) return fail(L2A_ERR_INVALID, "needs a sharded plan with attached peers");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mm = pl->p.n_envs, A = pl->A;
+  double* rec = reinterpret_cast<double*>(pl->res_scratch);
+  plan_record_kernel<<<(mm + 127) / 128, 128, 0, st>>>(best_ret, best_idx, best_act, nullptr, pl->o.shard_offset, pl->p.n_candidates, mm, A, rec);
+  ShardXArgs xa;
+  xa.peers = pl->peers_dev + pl->o.shard_world;          // the second set of exchange buffers
+  xa.rank = pl->o.shard_rank;
+  xa.world = pl->o.shard_world;
+  xa.m = mm;
+  xa.rec = pl->rec;
+  xa.call_index = nullptr;
+  xa.own_seq = reinterpret_cast<unsigned long long*>(pl->res_scratch + sizeof(double) * (size_t)mm * pl->rec);
+  xa.mine = rec;
+  xa.final_rec = final_rec_out;
+  shard_exchange_kernel<<<1, 128, 0, st>>>(xa);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return L2A_OK;
 }
 
 extern "C" int l2a_plan_io_bytes(const l2a_plan* pl, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {

@@ -316,6 +316,17 @@ class PlanningEngine(object):
         self._last_plan = plan
         return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy(), plan["mean"].copy(), plan["std"].copy()
 
+    def exchange_resident(self, res, out=None):
+        """Peer-memory exchange of device-resident per-rank rollout results `res` (dict from rollout()) through the sharded plan
+        of the most recent plan_rs_host call: float64 [m, 2 + A] winner records (return, global index, action) on every rank."""
+        plan = self._last_plan
+        m = res["best_ret"].shape[0]
+        if out is None:
+            out = torch.empty((m, 2 + self.act_dim), device=self.device, dtype=torch.float64)
+        N.check(self.lib.l2a_plan_exchange_resident(self._ctx, plan["handle"], _ptr(res["best_ret"]), _ptr(res["best_idx"]),
+                                                    _ptr(res["best_act"]), _ptr(out), _stream()))
+        return out
+
     def _attach_peers(self, plan, rank, world, all_gather):
         """Exchange the CUDA IPC handles of the ranks' exchange buffers once and hand the peers' pointers to the plan."""
         ptr, nbytes = C.c_void_p(), C.c_uint64()
