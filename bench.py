@@ -423,37 +423,31 @@ def run_cuda(args):
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count
-    step_ms = []
-    barrier()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)                                   # evict weights + candidates from L2 (outside the events)
-        if cem:
-            mean.zero_(); std.fill_(1.0)                        # mean = 0, std = 1 at the start of a call (:79-80)
-        barrier()                                               # ranks start the step together (outside the events)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        plan_resident(i)
-        e.record()
-        torch.cuda.synchronize()
-        step_ms.append(s.elapsed_time(e))
-    barrier()
-    wall = time.perf_counter() - wall0
-    nccl_ms = None
-    if distributed:                                             # the same step with the NCCL all-gather as the exchange
-        ts = []
-        for i in range(3 + min(args.steps, 10)):
-            flush.fill_(i & 0xFF)
-            barrier()
+
+    def timed_steps(k, exchange):
+        """k steps enqueued back to back (the ranks then run in lockstep through the per-step exchange, as consecutive planning
+        calls do); every step sits between its own pair of CUDA events, the L2 flush between the steps outside of them."""
+        evs = []
+        barrier()
+        for i in range(k):
+            flush.fill_(i & 0xFF)                               # evict weights + candidates from L2 (outside the events)
+            if cem:
+                mean.zero_(); std.fill_(1.0)                    # mean = 0, std = 1 at the start of a call (:79-80)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            plan_resident(i, exchange="nccl")
+            plan_resident(i, exchange)
             e.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts.append(s.elapsed_time(e))
-        nccl_ms = max_over_ranks(float(np.mean(ts)))
-    launches = eng.launch_count - launches0
+            evs.append((s, e))
+        barrier()
+        return [s.elapsed_time(e) for s, e in evs]
+
+    wall0 = time.perf_counter()
+    step_ms = timed_steps(args.steps, "peer")
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count - launches0                     # kernels of this library inside the timed region
+    nccl_ms = None
+    if distributed:                                             # the same step with the NCCL all-gather as the exchange
+        nccl_ms = max_over_ranks(float(np.mean(timed_steps(3 + min(args.steps, 10), "nccl")[3:])))
     ms_step = max_over_ranks(float(np.mean(step_ms)))
     rollouts_per_call = world * n * m * iters if args.scaling == "weak" else n_glob * m * iters
     value = rollouts_per_call / (ms_step * 1e-3)
@@ -485,9 +479,7 @@ def run_cuda(args):
         total = 0.0
         for i in range(steps):
             flush.fill_(i & 0xFF)
-            torch.cuda.synchronize()
-            if distributed:
-                dist.barrier()
+            torch.cuda.synchronize()                            # (no per-step barrier: the previous call's exchange left the ranks aligned)
             t0 = time.perf_counter()
             step()                                              # H2D obs, [adapt], sample, K1, [exchange], D2H actions
             total += time.perf_counter() - t0
