@@ -91,6 +91,10 @@ const char* l2a_last_error(void);
 int l2a_version(void);
 
 /* ---- context (replaces tf.Session creation, trainers/mb_trainer.py:46-48) ------------------------------ */
+/* Threading / streams: a context is NOT re-entrant and serves ONE stream at a time -- its per-env reduction workspace, the
+ * ensemble exchange scratch and the adapt workspace are shared by every launch made through it, so two l2a_rollout / l2a_adapt
+ * calls in flight on different streams of the same context would race.  Use one context per (process, device, stream); the
+ * host-buffer plans (l2a_plan_*) run on their own private stream and synchronise before returning. */
 int l2a_ctx_create(int device, l2a_ctx** out);
 int l2a_ctx_destroy(l2a_ctx* ctx);
 /* number of this library's kernels launched on the ctx since creation (bench.py's gpu_launches) */
@@ -289,7 +293,8 @@ int l2a_plan_attach_window(l2a_ctx* ctx, l2a_plan* plan, l2a_window* w, float in
  * l2a_cem_sample: a = mean + z*std (:86) -> samples [n, m, H*A] fp32 (rolled out UNclipped, :88-89) and
  *   clipped copy (:87).  mean/std are float64 [m, H*A]; z fp32 [n, m, H*A]; clip_low/high fp32 [H*A].
  * l2a_cem_refit: elite selection + mean/std update (:101-104) from returns [m, n].
- *   compat != 0 reproduces the reference's rank-mask defect (:101); compat == 0 takes the true top-k.
+ *   compat != 0 reproduces the reference's rank-mask defect (:101); compat == 0 takes the true top-k (m == 1 only:
+ *   L2A_ERR_UNSUPPORTED for m > 1, where the reference's sample -> env layout is itself inconsistent).
  *   rank_scratch: int32 [m, n]. */
 int l2a_cem_sample(l2a_ctx* ctx, const float* z, const double* mean, const double* std, const float* clip_low,
                    const float* clip_high, int n, int m, int ha, float* samples, float* clipped, void* stream);

@@ -2,7 +2,7 @@
 
 The planner is embarrassingly parallel over candidates: rank g rolls its own slice of every env's N candidates
 through the fused kernel (weights, statistics and observations replicated), producing per env the triple
-(best return, global candidate index, first action).  The only exchange is ONE all-gather of ``m x (2 + A)`` floats
+(best return, global candidate index, first action).  The only exchange is ONE all-gather of ``m x (3 + A)`` floats
 per planning call, followed by a local argmax with lowest-global-index tie-break -- identical to ``np.argmax`` over
 the concatenated returns (policies/mpc_controller.py:128-129), so G ranks return exactly what G = 1 returns for the
 same candidate tensor.  The reference has no multi-device path at all; this is new.
@@ -21,8 +21,8 @@ def shard_bounds(n_candidates, rank, world_size):
 
 
 def pack_best(best_ret, best_idx_global, best_act):
-    """[m, 2 + A] float32: (return, global index as float-exact int, action...).  Indices < 2**24 are exact in fp32;
-    larger candidate counts are carried in two 16-bit halves."""
+    """[m, 3 + A] float32: (return, global index >> 16, global index & 0xFFFF, action...): the index travels as two halves that
+    are exact in fp32."""
     m = best_ret.shape[0]
     idx = best_idx_global.to(torch.int64)
     hi = (idx >> 16).to(torch.float32)

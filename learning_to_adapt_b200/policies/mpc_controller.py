@@ -169,6 +169,9 @@ class MPCController(Policy, Serializable):
         ha = h * act_dim
         set_mode, first_set, n_sets = self.dynamics_model.planning_sets(m)
         num_elites = max(int(self.n_candidates * self.percent_elites), 1)                 # :78
+        if not self.cem_compat and m > 1:
+            raise NotImplementedError("cem_compat=False is defined for one env per call: for m > 1 the reference's own sample -> env "
+                                      "layout is inconsistent (mpc_controller.py:85-102) and only the bug-compatible mode reproduces it")
         self.pushed_window = False
         if self.sampler in ("numpy", "device") and self.parallel is None:
             # all iterations in ONE host-buffer C call (l2a_plan_run_ex, CEM planner), replayed as a CUDA graph
