@@ -726,6 +726,8 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
     if (world > 1) return fail(L2A_ERR_UNSUPPORTED, "the CEM planner is not sharded across GPUs");
     if (opts->cem_iters < 1 || opts->cem_num_elites < 1 || opts->cem_num_elites > p->n_candidates)
       return fail(L2A_ERR_INVALID, "cem_iters %d / cem_num_elites %d", opts->cem_iters, opts->cem_num_elites);
+    if (!opts->cem_compat && p->n_envs > 1)
+      return fail(L2A_ERR_UNSUPPORTED, "corrected CEM (cem_compat = 0) is defined for one env per call (see l2a_cem_refit)");
   }
   const int n_total = opts->n_candidates_total > 0 ? opts->n_candidates_total : p->n_candidates;
   if (opts->shard_offset < 0 || opts->shard_offset + p->n_candidates > n_total)
@@ -1578,6 +1580,9 @@ extern "C" int l2a_cem_refit(l2a_ctx* c, const float* returns, const float* clip
                              double alpha, int compat, int32_t* rank_scratch, double* mean, double* std_, void* stream) {
   if (!c || !returns || !clipped || !rank_scratch || !mean || !std_) return fail(L2A_ERR_INVALID, "NULL argument");
   if (n < 1 || m < 1 || ha < 1 || num_elites < 1 || num_elites > n) return fail(L2A_ERR_INVALID, "bad n/m/ha/num_elites");
+  if (!compat && m > 1)
+    return fail(L2A_ERR_UNSUPPORTED, "corrected CEM (compat = 0) is defined for one env per call: with m > 1 the reference's sample -> env "
+                                     "layout is itself inconsistent (mpc_controller.py:85-102), only the bug-compatible mode reproduces it");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((n + 255) / 256, m, kRankSplit);
