@@ -55,7 +55,8 @@ typedef enum {
 typedef enum {
   L2A_KERNEL_AUTO = 0,            /* tcgen05 when every hidden width is a multiple of 128, else SIMT */
   L2A_KERNEL_SIMT = 1,            /* fp32 FFMA kernel, any shape */
-  L2A_KERNEL_TCGEN05 = 2          /* split-bf16 (3-pass) tcgen05.mma kernel, fp32 accumulate in TMEM */
+  L2A_KERNEL_TCGEN05 = 2,         /* split-bf16 (3-pass) tcgen05.mma kernel, fp32 accumulate in TMEM */
+  L2A_KERNEL_TCGEN05_PAIR = 3     /* the same on CTA pairs (tcgen05.mma.cta_group::2, M = 256): hidden widths multiples of 256 */
 } l2a_kernel_choice;
 
 typedef struct l2a_ctx l2a_ctx;

@@ -9,7 +9,7 @@ L2A_MAX_LAYERS = 8
 
 REWARD_HALF_CHEETAH, REWARD_ANT, REWARD_ARM = 0, 1, 2
 SETS_SHARED, SETS_PER_ENV, SETS_ENSEMBLE_MEAN = 0, 1, 2
-KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05 = 0, 1, 2
+KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05, KERNEL_TCGEN05_PAIR = 0, 1, 2, 3
 
 EXPORTS = [
     "l2a_last_error", "l2a_version", "l2a_ctx_create", "l2a_ctx_destroy", "l2a_ctx_launch_count",

@@ -1,5 +1,6 @@
 // libl2a_b200.so -- C ABI of the B200-native MPC planning engine (see include/l2a_b200.h).
 // Host side: argument validation, workspace management, kernel selection and launches.  sm_100a only.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -21,11 +22,17 @@
 #include "rollout_rnn_simt.cuh"
 #include "rollout_rnn_tc.cuh"
 #include "rollout_tc.cuh"
+#include "rollout_tc2.cuh"
 #include "sample.cuh"
 #include "shard.cuh"
 #include "window.cuh"
 
 using namespace l2a;
+
+// AUTO kernel choice: 1 = prefer the CTA-pair tcgen05 rollout where the shape allows it (L2A_TC_PAIR=0/1 overrides at run time)
+#ifndef L2A_TC_PAIR_DEFAULT
+#define L2A_TC_PAIR_DEFAULT 0
+#endif
 
 static thread_local char g_err[512] = "";
 
@@ -47,6 +54,8 @@ static int fail(int code, const char* fmt, ...) {
 struct l2a_ctx {
   float* xch = nullptr;            // ensemble exchange scratch (global / L2), grown on demand
   size_t xch_cap = 0;
+  unsigned int* xflags = nullptr;  // CTA-pair rollout: per (tile, rank, member) step counters of the member exchange
+  size_t xflags_cap = 0;
   long long* timeline = nullptr;   // optional diagnostics buffer (l2a_debug_set_timeline)
   int device = 0;
   int num_sms = 0;
@@ -71,6 +80,10 @@ struct l2a_model {
   bool tc_ok = false;
   float* params = nullptr;     // [n_sets][set_stride]
   uint8_t* blobs = nullptr;    // [n_sets][plan.set_bytes]
+  Tc2Plan plan2;               // CTA-pair (cta_group::2) rollout: its own stage order and blob
+  bool tc2_ok = false;
+  uint8_t* blobs2 = nullptr;   // [n_sets][plan2.set_bytes]
+  CUtensorMap wmap2;           // blobs2 as a 2-D tensor of 128-byte rows, box = one 16 KB tile
   float* norm = nullptr;       // obs_mean[D] obs_den[D] act_mean[A] act_den[A] delta_mean[D] delta_scale[D]
   bool norm_set = false;
   NormDev norm_dev() const {
@@ -120,6 +133,7 @@ extern "C" int l2a_ctx_destroy(l2a_ctx* c) {
   cudaFree(c->adapt_acts);
   cudaFree(c->adapt_grads);
   cudaFree(c->xch);
+  cudaFree(c->xflags);
   delete c;
   return L2A_OK;
 }
@@ -171,6 +185,31 @@ extern "C" int l2a_tc_plan_query(const l2a_mlp_desc* d, int32_t* out8) {
   return L2A_OK;
 }
 
+// The pair blob as a 2-D tensor map: rows of 128 bytes (one swizzled K-major row of a tile), box = 128 rows = one 16 KB tile;
+// no swizzle in the map itself (the tiles are stored pre-swizzled).  cuTensorMapEncodeTiled comes from the driver through the
+// runtime's entry-point query, so the library does not link libcuda.
+typedef CUresult (*l2a_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool encode_weight_map(CUtensorMap* map, void* base, size_t bytes) {
+  static l2a_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+      cudaGetLastError();
+      return false;
+    }
+    fn = (l2a_encode_tiled_fn)p;
+  }
+  const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {128, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // --------------------------------------------------------------------------------------------- model
 extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** out) {
   if (!c || !d || !out) return fail(L2A_ERR_INVALID, "NULL argument");
@@ -193,8 +232,19 @@ extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** o
     if (cudaMalloc(&m->blobs, bbytes) != cudaSuccess) { cudaFree(m->params); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(blobs, %zu)", bbytes); }
     cudaMemset(m->blobs, 0, bbytes);
   }
+  m->tc2_ok = tc2_make_plan(md, &m->plan2);
+  if (m->tc2_ok) {
+    const size_t bbytes = (size_t)d->n_sets * (size_t)m->plan2.set_bytes;
+    if (cudaMalloc(&m->blobs2, bbytes) != cudaSuccess) { cudaFree(m->params); cudaFree(m->blobs); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(blobs2, %zu)", bbytes); }
+    cudaMemset(m->blobs2, 0, bbytes);
+    if (!encode_weight_map(&m->wmap2, m->blobs2, bbytes)) {          // no driver entry point: the pair kernel is simply not offered
+      cudaFree(m->blobs2);
+      m->blobs2 = nullptr;
+      m->tc2_ok = false;
+    }
+  }
   const size_t nbytes = sizeof(float) * (size_t)(4 * d->obs_dim + 2 * d->act_dim);
-  if (cudaMalloc(&m->norm, nbytes) != cudaSuccess) { cudaFree(m->params); cudaFree(m->blobs); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(norm)"); }
+  if (cudaMalloc(&m->norm, nbytes) != cudaSuccess) { cudaFree(m->params); cudaFree(m->blobs); cudaFree(m->blobs2); delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(norm)"); }
   *out = m;
   return L2A_OK;
 }
@@ -204,12 +254,25 @@ extern "C" int l2a_model_destroy(l2a_ctx* c, l2a_model* m) {
   if (c) cudaSetDevice(c->device);
   cudaFree(m->params);
   cudaFree(m->blobs);
+  cudaFree(m->blobs2);
   cudaFree(m->norm);
   delete m;
   return L2A_OK;
 }
 
 static int launch_prep(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, cudaStream_t st) {
+  if (m->tc2_ok) {
+    Prep2Args pa;
+    pa.dims = m->dims;
+    pa.plan = m->plan2;
+    pa.params = m->params;
+    pa.blobs = m->blobs2;
+    pa.first_set = first_set;
+    dim3 grid(m->plan2.hidden_stages + m->plan2.nkc[m->plan2.n_layers - 1], n_sets, 2);
+    tc2_prep_kernel<<<grid, 256, 0, st>>>(pa);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   if (!m->tc_ok) return L2A_OK;
   PrepArgs pa;
   pa.dims = m->dims;
@@ -345,6 +408,49 @@ static int launch_tc(l2a_ctx* c, const TcArgs& ta, int csize, cudaStream_t st) {
   return L2A_OK;
 }
 
+template <int NC, int DMAX>
+static int launch_tc2(l2a_ctx* c, const l2a_model* m, const Tc2Args& ta, int csize, cudaStream_t st) {
+  const size_t smem = Tc2Smem<NC>::total;
+  if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "CTA-pair rollout needs %zu B shared memory (> %d)", smem, c->max_smem_optin);
+  CUDA_TRY(cudaFuncSetAttribute(rollout_tc2_kernel<NC, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(ta.n_envs * ta.groups_per_env * csize * 2));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, rollout_tc2_kernel<NC, DMAX>, ta, m->wmap2));
+  c->launches++;
+  return L2A_OK;
+}
+
+// candidates per CTA of the pair kernel (a tile is 2 * nc candidates): fewest waves of CTA pairs, then the smaller tile
+static int pick_nc2(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
+  static const int opts[3] = {72, 48, 32};
+  if (const char* ov = getenv("L2A_TC2_NC")) {                  // tuning / experiments only
+    const int v = atoi(ov);
+    if (v == 72 || v == 48 || v == 32) return v;
+  }
+  int best = 72;
+  double best_cost = 1e300;
+  const int slots = std::max(1, c->num_sms / 2);                // CTA pairs resident at once (1 CTA / SM)
+  for (int i = 0; i < 3; ++i) {
+    const int nc = opts[i];
+    const long long pairs = (long long)n_envs * ((n_cand + 2 * nc - 1) / (2 * nc)) * csize;
+    const long long waves = (pairs + slots - 1) / slots;
+    const double cost = (double)waves * (48.0 + nc);
+    if (cost < best_cost) { best_cost = cost; best = nc; }
+  }
+  return best;
+}
+
 static int pick_nc(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
   static const int opts[4] = {80, 64, 48, 32};
   if (const char* ov = getenv("L2A_TC_NC")) {                   // tuning / experiments only
@@ -387,7 +493,14 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   int kernel = p->kernel;
   const int csize = (p->set_mode == L2A_SETS_ENSEMBLE_MEAN) ? p->n_sets : 1;
   const bool tc_possible = m->tc_ok && csize <= 8;
-  if (kernel == L2A_KERNEL_AUTO) kernel = tc_possible ? L2A_KERNEL_TCGEN05 : L2A_KERNEL_SIMT;
+  const bool tc2_possible = m->tc2_ok && csize <= 8;
+  if (kernel == L2A_KERNEL_AUTO) {
+    static const int prefer_pair = [] { const char* e = getenv("L2A_TC_PAIR"); return e ? atoi(e) : L2A_TC_PAIR_DEFAULT; }();
+    kernel = (tc2_possible && prefer_pair) ? L2A_KERNEL_TCGEN05_PAIR : tc_possible ? L2A_KERNEL_TCGEN05 : L2A_KERNEL_SIMT;
+  }
+  if (kernel == L2A_KERNEL_TCGEN05_PAIR && !tc2_possible)
+    return fail(L2A_ERR_UNSUPPORTED, "the CTA-pair tcgen05 rollout needs hidden widths that are multiples of 256 (<= 512), obs_dim <= 48, "
+                                     "act_dim <= 16 and <= 8 ensemble members");
   if (kernel == L2A_KERNEL_TCGEN05 && !tc_possible)
     return fail(L2A_ERR_UNSUPPORTED, "tcgen05 rollout needs hidden widths that are multiples of 128 (<= 512), obs_dim <= 128, "
                                      "act_dim <= 16 and <= 8 ensemble members");
@@ -438,6 +551,77 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return L2A_OK;
+  }
+
+  if (kernel == L2A_KERNEL_TCGEN05_PAIR) {
+    const int nc = pick_nc2(c, p->n_candidates, p->n_envs, csize);
+    const int groups = (p->n_candidates + 2 * nc - 1) / (2 * nc);
+    int rc = ensure_reduce_ws(c, (size_t)groups * 2 * p->n_envs, p->n_envs, st);
+    if (rc) return rc;
+    ra.part_ret = c->part_ret;
+    ra.part_idx = c->part_idx;
+    ra.counters = c->counters;
+    ra.tiles_per_env = groups * 2;
+    Tc2Args ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.dims = m->dims;
+    ta.plan = m->plan2;
+    ta.norm = m->norm_dev();
+    ta.params = m->params;
+    ta.obs0 = obs0;
+    ta.actions = actions;
+    ta.act_stride_t = p->act_stride_t;
+    ta.act_stride_row = p->act_stride_row;
+    ta.discount_pow = discount_pow;
+    ta.n_candidates = p->n_candidates;
+    ta.n_envs = p->n_envs;
+    ta.horizon = p->horizon;
+    ta.set_mode = p->set_mode;
+    ta.first_set = p->first_set;
+    ta.n_sets = p->n_sets;
+    ta.reward_kind = p->reward_kind;
+    ta.dt = p->dt;
+    ta.groups_per_env = groups;
+    ta.returns = returns;
+    ta.red = ra;
+    ta.timeline = c->timeline;
+    const bool small = m->dims.obs_dim <= 24 && m->dims.act_dim <= 8;
+    if (csize > 1) {
+      const size_t tiles = (size_t)p->n_envs * groups;
+      const size_t need = tiles * 2 * csize * 2 * (size_t)nc * (small ? 24 : 48);      // floats: [tile][parity][E][rank][NC][DMAX]
+      if (need > c->xch_cap) {
+        cudaFree(c->xch);
+        c->xch = nullptr;
+        c->xch_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->xch, need * sizeof(float)));
+        c->xch_cap = need;
+        c->ws_epoch++;
+      }
+      const size_t nflags = tiles * 2 * csize;
+      if (nflags > c->xflags_cap) {
+        cudaFree(c->xflags);
+        c->xflags = nullptr;
+        c->xflags_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->xflags, nflags * 2 * sizeof(unsigned int)));
+        c->xflags_cap = nflags * 2;
+        c->ws_epoch++;
+      }
+      CUDA_TRY(cudaMemsetAsync(c->xflags, 0, nflags * sizeof(unsigned int), st));        // step counters start at 0 every launch
+      ta.xch = c->xch;
+      ta.flags = c->xflags;
+    }
+    if (small) {
+      switch (nc) {
+        case 72: return launch_tc2<72, 24>(c, m, ta, csize, st);
+        case 48: return launch_tc2<48, 24>(c, m, ta, csize, st);
+        default: return launch_tc2<32, 24>(c, m, ta, csize, st);
+      }
+    }
+    switch (nc) {
+      case 72: return launch_tc2<72, 48>(c, m, ta, csize, st);
+      case 48: return launch_tc2<48, 48>(c, m, ta, csize, st);
+      default: return launch_tc2<32, 48>(c, m, ta, csize, st);
+    }
   }
 
   const int nc = pick_nc(c, p->n_candidates, p->n_envs, csize);

@@ -102,6 +102,11 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
   return v;
 }
+__device__ __forceinline__ uint32_t ld_dsmem_u32(uint32_t cluster_addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -281,6 +286,81 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t dst_tmem, uint32_t src
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- CTA pair (cta_group::2): M = 256 across two CTAs of a cluster
+// Both CTAs of the pair run the alloc / dealloc (same warp index, same smem slot offset); only the leader (cluster rank 0)
+// issues MMAs and commits.  Every tcgen05 instruction of a kernel uses the same cta_group.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot) {  // whole warp, in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {     // whole warp, in BOTH CTAs
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256: each CTA's shared memory supplies its 128 rows of A and its N/2 rows of B
+// (the descriptors are CTA-local offsets, identical in both CTAs); CTA r's TMEM receives rows [128 r, 128 r + 128) x N.
+template <int HINT>
+__device__ __forceinline__ void mma2_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (HINT == kAKeep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
+        : "memory");
+  } else if (HINT == kAReuse) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi32)
+        : "memory");
+  }
+}
+// all MMAs issued so far by this thread arrive, when complete, on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// 2-D tiled TMA load into THIS CTA's shared memory whose byte count completes on `mbar_cluster` (a shared::cluster address:
+// the leader CTA's barrier for both CTAs of the pair)
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const void* tmap, int32_t c0, int32_t c1, uint32_t mbar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(mbar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t smem_addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
+// generic-proxy writes (to shared memory of this CTA or of a cluster peer) -> visible to the async proxy (tensor core reads)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// global-memory flags of the member exchange between CTA pairs
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // ---------------------------------------------------------------- split-bf16 helpers

@@ -1,6 +1,7 @@
 """Development probe: A/B of libl2a_b200 build variants on ONE box (box-to-box variation is +-2 %).
 
-    python scripts/k1_ab.py [cfg,cfg,...] lib1.so lib2.so ...      (run under gpurun; `default` = the in-tree library)
+    python scripts/k1_ab.py [cfg,cfg,...] lib1.so lib2.so ...      (run under gpurun; `default` = the in-tree library;
+                                                                    lib@3 times the CTA-pair kernel, lib@2 the single-CTA one)
 
 Per variant (child process with L2A_B200_LIB set): device-resident time of the tcgen05 rollout at the named configs, CUDA
 events, L2 flushed between calls, median of 15, plus the max per-element relative error against the oracle on a strided
@@ -40,7 +41,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         acts_np = O.sample_rs_actions(3, prob["low"], prob["high"], h, n * m)
         acts = eng._f32(acts_np)
         fn = lambda wr=False: eng.rollout(obs, acts, n, h, prob["reward_kind"], prob["dt"], set_mode=mode, first_set=0, n_sets=nsets,
-                                          want_returns=wr, kernel=2)
+                                          want_returns=wr, kernel=int(os.environ.get('L2A_AB_KERNEL', '2')))
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -50,7 +51,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(); fn(); e.record(); torch.cuda.synchronize()
             ts.append(s.elapsed_time(e))
-        row = dict(cfg=name, lib=os.path.basename(os.environ.get("L2A_B200_LIB", "default")), ms=float(np.median(ts)), ms_min=float(np.min(ts)))
+        row = dict(cfg=name, lib=os.path.basename(os.environ.get("L2A_B200_LIB", "default")), kernel=int(os.environ.get("L2A_AB_KERNEL", "2")), ms=float(np.median(ts)), ms_min=float(np.min(ts)))
         if name == "headline":
             res = fn(True)
             torch.cuda.synchronize()
@@ -64,6 +65,8 @@ else:
     cfgs = sys.argv[1]
     for lib in sys.argv[2:]:
         env = dict(os.environ)
+        if "@" in lib:                                   # lib@kernel: 2 = single-CTA tcgen05, 3 = CTA pair
+            lib, env["L2A_AB_KERNEL"] = lib.split("@")
         if lib != "default":
             env["L2A_B200_LIB"] = os.path.abspath(lib)
         else:
