@@ -10,11 +10,12 @@
 // the tensor pipe's own rate), operand reads drop to ~81 B/clk per SM, and the ring handshakes are amortised over twice the
 // MMA time.
 // The price is an all-to-all in the hidden-layer epilogue: CTA r produces features of ALL 2*NC candidates, but the next
-// layer's B operand of the peer's candidates lives in the peer's shared memory.  Each epilogue warp transposes a 16-candidate
-// x 16-feature block through a 1 KB bounce buffer (stmatrix.trans, then every lane reads back one 16-byte row = 8 features
-// of one candidate) and stores the row either into its own CTA's activation chunk or, for the peer's candidates, into the
-// peer's chunk with st.shared::cluster (DSMEM).  Readiness is counted on the LEADER's mbarriers (remote arrives with
-// release.cluster from the peer), because only the leader CTA issues MMAs.
+// layer's B operand of the peer's candidates lives in the peer's shared memory.  The hidden activations are therefore kept
+// MN-MAJOR (candidates contiguous, unswizzled 8x8 core matrices): an epilogue thread owns one output feature (its TMEM lane),
+// holds 8 consecutive candidates per 32x32b TMEM load and writes them as ONE 16-byte store, into its own CTA's buffer or, for
+// the peer's candidates, into the peer's with st.shared::cluster (DSMEM) -- no transposition, no staging.  Readiness is counted
+// on the LEADER's mbarriers (remote arrives with release.cluster from the peer), because only the leader CTA issues MMAs.
+// (First version: K-major activations transposed through a per-warp stmatrix bounce buffer: 5.5 k cycles per M-block epilogue.)
 // The output layer keeps the swapped roles of rollout_tc.cuh (M = candidates: each CTA's own 128 activation rows are its half
 // of A; the [out_n x 64] weight tiles are B, split by N between the CTAs: x_hi * [W_hi ; W_lo] has W_hi in the leader and
 // W_lo in the peer), so every candidate's deltas land in the TMEM lanes of its own CTA's env-step thread.
@@ -33,6 +34,11 @@
 
 namespace l2a {
 
+// timing experiments only: 1 = every epilogue store goes to the CTA's own shared memory (garbage results); 2 = CTA-scope proxy
+// fence in the hidden epilogue (the cluster-scope release of the arrival stays)
+#ifndef L2A_TC2_EXPERIMENT
+#define L2A_TC2_EXPERIMENT 0
+#endif
 constexpr int kTc2StageBytes = 32768;     // per CTA and ring stage: W_hi tile + W_lo tile of this CTA's 128 rows (or output-layer tiles)
 constexpr int kTc2MaxStages = 4;
 constexpr int kTc2XChunk = kTcMaxChunks - 1;   // activation chunk that holds the layer-0 input (not written by the M-block-0 epilogue)
@@ -193,13 +199,11 @@ struct Tc2Smem {
   static constexpr int kChunkBytes = NC * 128;
   static constexpr size_t act_bytes = (size_t)2 * kTcMaxChunks * kChunkBytes;
   static constexpr size_t stage_off = act_bytes;
-  static constexpr size_t kBounce = 8 * 1024;           // 1 KB per epilogue / helper warp (hi 512 B + lo 512 B)
   static constexpr size_t kMisc = 2048;
-  static constexpr int kFit = (int)((232448 - (long long)act_bytes - (long long)kBounce - (long long)kMisc) / kTc2StageBytes);
+  static constexpr int kFit = (int)((232448 - (long long)act_bytes - (long long)kMisc) / kTc2StageBytes);
   static constexpr int kStages = kFit > kTc2MaxStages ? kTc2MaxStages : kFit;
   static_assert(kStages >= 2, "no room for the weight ring");
-  static constexpr size_t bounce_off = stage_off + (size_t)kStages * kTc2StageBytes;
-  static constexpr size_t misc_off = bounce_off + kBounce;
+  static constexpr size_t misc_off = stage_off + (size_t)kStages * kTc2StageBytes;
   static constexpr size_t total = misc_off + kMisc;
   static_assert(kChunkBytes % 1024 == 0, "activation chunks must stay 1024-byte aligned (SWIZZLE_128B atoms): NC % 8 == 0");
 };
@@ -223,7 +227,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
   uint8_t* act_hi = smem;
   uint8_t* act_lo = smem + (size_t)kTcMaxChunks * kChunkBytes;
   uint8_t* stages = smem + S::stage_off;
-  uint8_t* bounce = smem + S::bounce_off;
   float* n_obs_mean = reinterpret_cast<float*>(smem + S::misc_off);
   float* n_obs_den = n_obs_mean + DMAX;
   float* n_dmean = n_obs_den + DMAX;
@@ -269,9 +272,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     }
     umma::mbar_init(layer_full, 1);
     umma::mbar_init(early, 1);
-    umma::mbar_init(&act_ready[0], 512);
-    umma::mbar_init(&act_ready[1], 512);
-    umma::mbar_init(x_ready, 256);
+    umma::mbar_init(&act_ready[0], 16);          // one arrival per epilogue / helper warp of both CTAs
+    umma::mbar_init(&act_ready[1], 16);
+    umma::mbar_init(x_ready, 8);                 // one arrival per env-step warp of both CTAs
     umma::fence_barrier_init();
   }
   for (int i = tid; i < DMAX; i += kTcThreads) {
@@ -299,67 +302,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
   const uint32_t act_ready_leader = umma::map_to_cta(umma::smem_u32(&act_ready[0]), 0);
   const uint32_t x_ready_leader = umma::map_to_cta(umma::smem_u32(x_ready), 0);
 
-  // Hidden-layer epilogue of this warp's TMEM lane quadrant wq for the candidate blocks [CB0, CB1) (16 columns each) of every
-  // M-block: accumulator fragments -> bias + ReLU -> bf16 hi / lo -> transposed through the warp's bounce buffer -> 16-byte rows
-  // into the owning CTA's activation chunk.
-  constexpr int kCbAll = N2 / 16, kCbMain = (kCbAll + 1) / 2;
-  auto hidden_epilogue = [&](auto cb0_tag, auto cb1_tag, int l, int slot_a, int wq, int bw, uint32_t& lf_phase, uint32_t& early_phase) {
-    constexpr int CB0 = decltype(cb0_tag)::value, CB1 = decltype(cb1_tag)::value;
+  // Hidden-layer epilogue of this warp's TMEM lane quadrant wq.  The hidden activations are stored MN-MAJOR (candidates
+  // contiguous, no swizzle): element (candidate n, feature f) at (f/8) * kSlabBytes + (n/8) * 128 + (f%8) * 16 + (n%8) * 2, i.e.
+  // 8x8 core matrices of 128 contiguous bytes, SBO = 128 B between candidate groups, LBO = kSlabBytes between feature groups.
+  // With 32x32b TMEM loads a thread IS one output feature (TMEM lane) and holds 8 consecutive candidates per load: bias + ReLU
+  // -> bf16 hi / lo -> ONE 16-byte store per part, straight from registers into the owning CTA's buffer (st.shared for its own
+  // candidate groups, st.shared::cluster for the peer's) -- no transposition, no staging.  A warp's 32 lanes cover 4 feature
+  // groups x 8 rows: every quarter-warp stores 128 contiguous bytes.
+  // The epilogue warps take candidate groups [0, kGa) u [kGr, kGr + kGb), the helper warps the rest: both halves mix own and peer groups.
+  constexpr int kSlabBytes = NC * 16;                       // 8 features x NC candidates x 2 B
+  constexpr int kGr = NC / 8;                               // 8-candidate groups per CTA
+  constexpr int kGa = (kGr + 1) / 2, kGb = kGr / 2;
+  auto hidden_epilogue = [&](auto main_tag, int t, int l, int slot_a, int wq, bool stamps, uint32_t& lf_phase, uint32_t& early_phase) {
+    constexpr bool MAIN = decltype(main_tag)::value != 0;
     const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
     const uint32_t peer_hi = umma::map_to_cta(act_hi_addr, rank ^ 1u), peer_lo = umma::map_to_cta(act_lo_addr, rank ^ 1u);
-    const uint32_t my_unit = umma::smem_u32(bounce) + (uint32_t)bw * 1024u + (uint32_t)lane * 16u;   // stmatrix row address == the row read back
-    const int cand_l = (lane & 7) + ((lane >> 4) & 1) * 8;
-    const int fsel = ((lane >> 3) & 1) * 8;
     for (int mb = 0; mb < plan.nmb[l]; ++mb) {
       if (mb == 0) umma::mbar_wait(early, early_phase);
       else umma::mbar_wait(layer_full, lf_phase);
       umma::tc_fence_after();
+      if (stamps) L2A_STAMP(32 + 4 * l + (mb == 0 ? 0 : 3));
       const int slot = (mb == 0) ? slot_a : (slot_a + 1) % 3;
+      const int gfeat = mb * 256 + (int)rank * 128 + wq * 32 + lane;           // layer output feature of this thread's TMEM lane
+      const float bias = __ldg(P + md.b_off[l] + gfeat);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * N2);
+      const uint32_t row_off = (uint32_t)(gfeat >> 3) * (uint32_t)kSlabBytes + (uint32_t)(gfeat & 7) * 16u;
+      auto drain = [&](auto g0_tag, auto g1_tag) {
+        constexpr int G0 = decltype(g0_tag)::value, G1 = decltype(g1_tag)::value, CNT = G1 - G0;
+        if constexpr (CNT > 0) {
+          uint32_t r[CNT][8];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int lane_feat = wq * 32 + half * 16;                       // TMEM lanes of this (warp, half)
-        const int gfeat = mb * 256 + (int)rank * 128 + lane_feat;        // layer output feature of lane_feat
-        const float bias_a = __ldg(P + md.b_off[l] + gfeat + (lane >> 2));
-        const float bias_b = __ldg(P + md.b_off[l] + gfeat + (lane >> 2) + 8);
-        const uint32_t t_addr = tmem_base + ((uint32_t)lane_feat << 16) + (uint32_t)(slot * N2);
-        const uint32_t chunk_off = (uint32_t)(gfeat >> 6) * kChunkBytes;
-        const uint32_t fcol = (uint32_t)((gfeat & 63) + fsel) >> 3;
-        uint32_t r[CB1 - CB0][8];
+          for (int i = 0; i < CNT; ++i) umma::tmem_ld_32x32b_x8(t_addr + (uint32_t)((G0 + i) * 8), r[i]);
+          umma::tmem_ld_wait();
 #pragma unroll
-        for (int cb = CB0; cb < CB1; ++cb) umma::tmem_ld_16x256b_x2(t_addr + (uint32_t)(cb * 16), r[cb - CB0]);
-        umma::tmem_ld_wait();
+          for (int i = 0; i < CNT; ++i) {
+            const int g = G0 + i;
+            uint4 uh, ul;
+            {
+              uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int cb = CB0; cb < CB1; ++cb) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float b = (q & 1) ? bias_b : bias_a;
-            const float v0 = fmaxf(__uint_as_float(r[cb - CB0][2 * q]) + b, 0.f);          // core/utils.py:119-126 (ReLU dense)
-            const float v1 = fmaxf(__uint_as_float(r[cb - CB0][2 * q + 1]) + b, 0.f);
-            umma::split_bf16x2(v0, v1, hi[q], lo[q]);
-          }
-          umma::stmatrix_x4_trans(my_unit, hi[0], hi[1], hi[2], hi[3]);
-          umma::stmatrix_x4_trans(my_unit + 512u, lo[0], lo[1], lo[2], lo[3]);
-          __syncwarp();
-          const uint4 uh = umma::ld_shared_v4(my_unit), ul = umma::ld_shared_v4(my_unit + 512u);
-          __syncwarp();
-          const int cg = cb * 16 + cand_l;                                // accumulator column = candidate of the pair
-          const uint32_t to_peer_rank = (cg >= NC) ? 1u : 0u;             // rank that owns the candidate
-          const uint32_t row = (uint32_t)(cg - (int)to_peer_rank * NC);
-          const uint32_t off = chunk_off + row * 128u + (((fcol ^ row) & 7u) << 4);
-          if (to_peer_rank == rank) {
-            umma::st_shared_v4(act_hi_addr + off, uh);
-            umma::st_shared_v4(act_lo_addr + off, ul);
-          } else {
-            umma::st_cluster_v4(peer_hi + off, uh);
-            umma::st_cluster_v4(peer_lo + off, ul);
+              for (int q = 0; q < 4; ++q) {
+                const float v0 = fmaxf(__uint_as_float(r[i][2 * q]) + bias, 0.f);          // core/utils.py:119-126 (ReLU dense)
+                const float v1 = fmaxf(__uint_as_float(r[i][2 * q + 1]) + bias, 0.f);
+                umma::split_bf16x2(v0, v1, hi[q], lo[q]);
+              }
+              uh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              ul = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            const uint32_t owner = (g >= kGr) ? 1u : 0u;
+            const uint32_t off = row_off + (uint32_t)(g - (g >= kGr ? kGr : 0)) * 128u;
+            if (owner == rank || L2A_TC2_EXPERIMENT == 1) {
+              umma::st_shared_v4(act_hi_addr + off, uh);
+              umma::st_shared_v4(act_lo_addr + off, ul);
+            } else {
+              umma::st_cluster_v4(peer_hi + off, uh);
+              umma::st_cluster_v4(peer_lo + off, ul);
+            }
           }
         }
+      };
+      if (MAIN) {
+        drain(IntTag<0>{}, IntTag<kGa>{});
+        drain(IntTag<kGr>{}, IntTag<kGr + kGb>{});
+      } else {
+        drain(IntTag<kGa>{}, IntTag<kGr>{});
+        drain(IntTag<kGr + kGb>{}, IntTag<2 * kGr>{});
       }
-      umma::fence_proxy_async_all();
+      // every lane: its rows -> async proxy; then ONE cluster-scope release per warp (cumulative over the warp through
+      // __syncwarp) orders the rows stored into the peer's shared memory before the arrival on the leader's barrier
+      if (L2A_TC2_EXPERIMENT == 2) umma::fence_proxy_async_smem(); else umma::fence_proxy_async_cluster();
       umma::tc_fence_before();
-      if (rank == 0) umma::mbar_arrive(&act_ready[mb]);
-      else umma::mbar_arrive_remote(act_ready_leader + (uint32_t)mb * 8u);
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) umma::mbar_arrive_release_cluster(&act_ready[mb]);
+        else umma::mbar_arrive_remote(act_ready_leader + (uint32_t)mb * 8u);
+      }
+      if (stamps) L2A_STAMP(32 + 4 * l + (mb == 0 ? 1 : 2));
     }
     if (plan.nmb[l] == 1) umma::mbar_wait(layer_full, lf_phase);        // keeps the layer_full phase in step
     early_phase ^= 1u;
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
       int slot_a = 0;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l + 1 < L; ++l) {
-          hidden_epilogue(IntTag<kCbMain>{}, IntTag<kCbAll>{}, l, slot_a, wq, 4 + (warp - 6), lf_phase, early_phase);
+          hidden_epilogue(IntTag<0>{}, t, l, slot_a, wq, false, lf_phase, early_phase);
           slot_a = (slot_a + 2) % 3;
         }
         umma::mbar_wait(layer_full, lf_phase);                           // the output layer's completion
@@ -425,9 +443,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
       const uint32_t st_lo32 = umma::desc_lo32(umma::smem_u32(stages));
       constexpr uint32_t kChunkStep = (uint32_t)kChunkBytes >> 4, kStageStep = (uint32_t)kTc2StageBytes >> 4, kLoStep = (uint32_t)kTcTileBytes >> 4;
       auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1u; } };
-      // one stage = the three split-bf16 passes of one [256 x 64] weight block against activation chunk `ch` of all 2*NC candidates
-      auto tile_pair = [&](uint32_t d_tmem, int ch, bool first, int nks) {
-        const uint32_t bh = hi_lo32 + (uint32_t)ch * kChunkStep, bl = lo_lo32 + (uint32_t)ch * kChunkStep;
+      // hidden activations as MN-major B operand (see the epilogue): LBO = one 8-feature slab, a 16-wide k-step = two slabs
+      const uint32_t hi_mn32 = umma::desc_lo32_mn(umma::smem_u32(act_hi), (uint32_t)(NC * 16)), lo_mn32 = umma::desc_lo32_mn(umma::smem_u32(act_lo), (uint32_t)(NC * 16));
+      constexpr uint32_t kKsMn = (uint32_t)(2 * NC * 16) >> 4;         // k-step advance of an MN-major activation descriptor
+      constexpr uint32_t kIdescMn = kIdesc | umma::kIdescBMn;
+      // one stage = the three split-bf16 passes of one [256 x 64] weight block against activation chunk `ch` of all 2*NC candidates;
+      // MN = the chunk is a hidden activation (MN-major), else the K-major SWIZZLE_128B layer-0 input
+      auto tile_pair = [&](auto mn_tag, uint32_t d_tmem, int ch, bool first, int nks) {
+        constexpr bool MN = decltype(mn_tag)::value != 0;
+        constexpr uint32_t kb = MN ? kKsMn : 2u, b_hi32 = MN ? umma::kDescHi32Mn : umma::kDescHi32, idesc = MN ? kIdescMn : kIdesc;
+        const uint32_t bh = (MN ? hi_mn32 : hi_lo32) + (uint32_t)ch * kChunkStep, bl = (MN ? lo_mn32 : lo_lo32) + (uint32_t)ch * kChunkStep;
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         umma::mbar_wait(&full_hi[stage], phase);
         umma::tc_fence_after();
@@ -435,13 +460,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           if (nks == 4) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              umma::mma2_bf16_ss_lo<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
-              umma::mma2_bf16_ss_lo<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              umma::mma2_bf16_ss_ab<umma::kAKeep>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, (first && ks == 0) ? 0u : 1u);
+              umma::mma2_bf16_ss_ab<umma::kAReuse>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bl + kb * ks, b_hi32, idesc, 1u);
             }
           } else {
             for (int ks = 0; ks < nks; ++ks) {
-              umma::mma2_bf16_ss_lo<umma::kAKeep>(d_tmem, a_hi + 2 * ks, bh + 2 * ks, kIdesc, (first && ks == 0) ? 0u : 1u);
-              umma::mma2_bf16_ss_lo<umma::kAReuse>(d_tmem, a_hi + 2 * ks, bl + 2 * ks, kIdesc, 1u);
+              umma::mma2_bf16_ss_ab<umma::kAKeep>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, (first && ks == 0) ? 0u : 1u);
+              umma::mma2_bf16_ss_ab<umma::kAReuse>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bl + kb * ks, b_hi32, idesc, 1u);
             }
           }
           umma::mma2_commit_both(&empty_hi[stage]);          // the W_hi halves of both CTAs may be refilled
@@ -452,9 +477,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
         if (umma::elect_one()) {
           if (nks == 4) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma::mma2_bf16_ss_lo<umma::kANone>(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) umma::mma2_bf16_ss_ab<umma::kANone>(d_tmem, a_lo + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, 1u);
           } else {
-            for (int ks = 0; ks < nks; ++ks) umma::mma2_bf16_ss_lo<umma::kANone>(d_tmem, a_lo + 2 * ks, bh + 2 * ks, kIdesc, 1u);
+            for (int ks = 0; ks < nks; ++ks) umma::mma2_bf16_ss_ab<umma::kANone>(d_tmem, a_lo + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, 1u);
           }
           umma::mma2_commit_both(&empty_lo[stage]);
         }
@@ -493,24 +518,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
       // (mod 3): the slot layer i does not touch, so M-block 0 of layer i+1 starts while layer i's epilogue drains, and its
       // M-block 1 reuses a_i, drained before layer i+1's inputs were complete.
       int slot_a = 0;
-      const uint32_t idesc_out = umma::make_idesc_bf16(256, (uint32_t)plan.out_n);
-      const uint32_t idesc_out2 = umma::make_idesc_bf16(256, (uint32_t)(2 * plan.out_n));
+      const uint32_t idesc_out = umma::make_idesc_bf16(256, (uint32_t)plan.out_n) | umma::kIdescAMn;        // A = MN-major activations
+      const uint32_t idesc_out2 = umma::make_idesc_bf16(256, (uint32_t)(2 * plan.out_n)) | umma::kIdescAMn;
       const uint32_t out_kc_step = (uint32_t)plan.out_kc_bytes >> 4, out_x_step = (uint32_t)(plan.out_n * 128) >> 4;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l + 1 < L; ++l) {
           const int nmb = plan.nmb[l], nkc = plan.nkc[l], nks_last = plan.nks_last[l];
           const uint32_t dA = tmem_base + (uint32_t)(slot_a * N2), dB = tmem_base + (uint32_t)(((slot_a + 1) % 3) * N2);
+          L2A_STAMP(4 * l + 0);
+          L2A_TIMELINE(if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64());
           if (l == 0) {
             umma::mbar_wait_cluster(x_ready, xr_phase);
             xr_phase ^= 1u;
             umma::tc_fence_after();
+            L2A_STAMP(4 * l + 3);
             if (plan.l0_packed) {
               packed_stage(dA, dB, nks_last);
               commit(early);
             } else {
-              tile_pair(dA, kTc2XChunk, true, nks_last);
+              tile_pair(IntTag<0>{}, dA, kTc2XChunk, true, nks_last);
               commit(early);                                  // M-block 0's epilogue writes chunks 0-3, the input sits in kTc2XChunk
-              if (nmb > 1) tile_pair(dB, kTc2XChunk, true, nks_last);
+              if (nmb > 1) tile_pair(IntTag<0>{}, dB, kTc2XChunk, true, nks_last);
             }
           } else {
             const int nsrc = plan.nmb[l - 1];
@@ -518,19 +546,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
               umma::mbar_wait_cluster(&act_ready[ev], (act_phase >> ev) & 1u);
               act_phase ^= (1u << ev);
               umma::tc_fence_after();
+              if (ev == 0) L2A_STAMP(4 * l + 3);
               const int kc_end = min(nkc, 4 * ev + 4);
-              for (int kc = 4 * ev; kc < kc_end; ++kc) tile_pair(dA, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
+              for (int kc = 4 * ev; kc < kc_end; ++kc) tile_pair(IntTag<1>{}, dA, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
             }
+            L2A_STAMP(4 * l + 1);
             if (nmb == 1) commit(early);
             else {
               // M-block 1; M-block 0's epilogue overwrites chunks 0-3 in place: it may start once M-block 1 is past them
               for (int kc = 0; kc < nkc; ++kc) {
-                tile_pair(dB, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
+                tile_pair(IntTag<1>{}, dB, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
                 if (kc == min(nkc - 1, 3)) commit(early);
               }
             }
           }
           commit(layer_full);
+          L2A_STAMP(4 * l + 2);
           slot_a = (slot_a + 2) % 3;
         }
         // ---- output layer, roles swapped: D[cand, feat] (+)= X[cand, 64-chunk] * W[64-chunk, feat]; A = each CTA's own
@@ -540,10 +571,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           const int nkc = plan.nkc[l], nsrc = plan.nmb[l - 1];
           const uint32_t d_out = tmem_base + (uint32_t)(slot_a * N2);
           int j = 0;
+          L2A_STAMP(4 * l + 0);
           for (int ev = 0; ev < nsrc; ++ev) {
             umma::mbar_wait_cluster(&act_ready[ev], (act_phase >> ev) & 1u);
             act_phase ^= (1u << ev);
             umma::tc_fence_after();
+            if (ev == 0) L2A_STAMP(4 * l + 3);
             const int kc_end = min(nkc, 4 * ev + 4);
             for (int kc = 4 * ev; kc < kc_end; ++kc) {
               if (j == 0) {
@@ -551,14 +584,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
                 umma::mbar_wait(&full_lo[stage], phase);
                 umma::tc_fence_after();
               }
-              const uint32_t xh = hi_lo32 + (uint32_t)kc * kChunkStep, xl = lo_lo32 + (uint32_t)kc * kChunkStep;
+              const uint32_t xh = hi_mn32 + (uint32_t)kc * kChunkStep, xl = lo_mn32 + (uint32_t)kc * kChunkStep;
               const uint32_t wy = st_lo32 + (uint32_t)stage * kStageStep + (uint32_t)j * out_kc_step, wx = wy + out_x_step;
               const bool last_in_stage = (j + 1 == plan.out_kcs) || (kc == nkc - 1);
               if (umma::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                  umma::mma2_bf16_ss_lo<umma::kANone>(d_out, xh + 2 * ks, wy + 2 * ks, idesc_out2, (kc == 0 && ks == 0) ? 0u : 1u);   // x_hi * [W_hi ; W_lo]
-                  umma::mma2_bf16_ss_lo<umma::kANone>(d_out, xl + 2 * ks, wx + 2 * ks, idesc_out, 1u);                                 // x_lo * W_hi
+                  umma::mma2_bf16_ss_ab<umma::kANone>(d_out, xh + kKsMn * ks, umma::kDescHi32Mn, wy + 2 * ks, umma::kDescHi32, idesc_out2,
+                                                      (kc == 0 && ks == 0) ? 0u : 1u);                                               // x_hi * [W_hi ; W_lo]
+                  umma::mma2_bf16_ss_ab<umma::kANone>(d_out, xl + kKsMn * ks, umma::kDescHi32Mn, wx + 2 * ks, umma::kDescHi32, idesc_out, 1u);   // x_lo * W_hi
                 }
                 if (last_in_stage) {
                   umma::mma2_commit_both(&empty_hi[stage]);
@@ -570,6 +604,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
             }
           }
           commit(layer_full);
+          L2A_STAMP(4 * l + 2);
           slot_a = (slot_a + 2) % 3;
         }
       }
@@ -649,10 +684,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           for (int g = used; g < need; ++g) store_group(g, z);
         }
       }
-      umma::fence_proxy_async_all();
+      umma::fence_proxy_async_smem();              // (this CTA's own shared memory only)
       umma::tc_fence_before();
-      if (rank == 0) umma::mbar_arrive(x_ready);
-      else umma::mbar_arrive_remote(x_ready_leader);
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) umma::mbar_arrive(x_ready);
+        else umma::mbar_arrive_remote(x_ready_leader);
+      }
     };
 
     load_actions(0);
@@ -661,13 +699,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     for (int t = 0; t < H; ++t) {
       const float disc_t = __ldg(a.discount_pow + t);
       for (int l = 0; l + 1 < L; ++l) {
-        hidden_epilogue(IntTag<0>{}, IntTag<kCbMain>{}, l, slot_a, warp, warp, lf_phase, early_phase);
+        hidden_epilogue(IntTag<1>{}, t, l, slot_a, warp, warp == 0, lf_phase, early_phase);
         slot_a = (slot_a + 2) % 3;
       }
       if (t + 1 < H) load_actions(t + 1);
       umma::mbar_wait(layer_full, lf_phase);
       lf_phase ^= 1u;
       umma::tc_fence_after();
+      if (warp == 0) L2A_STAMP(60);
       float dl[DMAX];
       {
         uint32_t r[DMAX], r2[DMAX];
@@ -694,6 +733,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
       }
       slot_a = (slot_a + 2) % 3;
       umma::tc_fence_before();
+      if (warp == 0) L2A_STAMP(61);
       if (ensemble) {
         // Member exchange through L2 (see the header): rows stored -> gpu-scope fence -> CTA barrier -> one release flag per
         // (member, rank) -> the E-1 other flags acquired -> CTA barrier -> the other members' rows read with ld.global.cg and
@@ -708,10 +748,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           for (int q = 0; q < DQ; ++q)
             if (q < dq) mine[q * NC] = make_float4(dl[4 * q], dl[4 * q + 1], dl[4 * q + 2], dl[4 * q + 3]);
         }
-        __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0) L2A_STAMP(65);
         unsigned int* const flags = a.flags + ((size_t)tile_id * 2 + rank) * csize;
-        if (tid == 0) umma::st_release_gpu(flags + member, (unsigned int)(t + 1));
+        if (tid == 0) {                              // one gpu-scope release for the CTA's rows (cumulative through the barrier)
+          umma::fence_acq_rel_gpu();
+          umma::st_relaxed_gpu(flags + member, (unsigned int)(t + 1));
+        }
+        if (warp == 0) L2A_STAMP(66);
+        L2A_TIMELINE(if (a.timeline && (blockIdx.x & 1) == 0 && blockIdx.x < 10 && t == 1 && tid == 0) a.timeline[86 + blockIdx.x] = (long long)umma::globaltimer_ns());
         if (tid < csize && tid != member) {
           const long long w0 = clock64();
           while (umma::ld_acquire_gpu(flags + tid) < (unsigned int)(t + 1)) {
@@ -719,6 +764,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0) L2A_STAMP(67);
+        L2A_TIMELINE(if (a.timeline && (blockIdx.x & 1) == 0 && blockIdx.x < 10 && t == 1 && tid == 0) a.timeline[87 + blockIdx.x] = (long long)umma::globaltimer_ns());
         if (has_cand) {
           const float inv_e = 1.0f / (float)csize;
           const float4* rows = blk0 + (size_t)rank * kBlk + n;                     // member e: + e * 2 * kBlk
@@ -756,6 +803,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           else mean_rows(IntTag<8>{}, IntTag<1>{});
         }
       }
+      if (warp == 0) L2A_STAMP(62);
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {
         float dx = 0.f, nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
@@ -772,7 +820,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
         const float rew = reward_value(a.reward_kind, 0.f, a.dt, asq, dx, nx0, nx1, nx2);
         ret = fmaf(disc_t, rew, ret);                        // mpc_controller.py:126
       }
+      if (warp == 0) L2A_STAMP(63);
       if (t + 1 < H) write_x();
+      if (warp == 0) L2A_STAMP(64);
     }
 
     float v = -__int_as_float(0x7f800000);

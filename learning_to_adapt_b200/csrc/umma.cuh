@@ -325,6 +325,36 @@ __device__ __forceinline__ void mma2_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, 
         : "memory");
   }
 }
+// Same with the high descriptor words of A and B given separately (operands in different canonical layouts, e.g. K-major
+// SWIZZLE_128B weights against MN-major unswizzled activations).
+template <int HINT>
+__device__ __forceinline__ void mma2_bf16_ss_ab(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if (HINT == kAKeep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi)
+        : "memory");
+  } else if (HINT == kAReuse) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi)
+        : "memory");
+  }
+}
+// MN-major (M / N contiguous) unswizzled operand of 8x8 core matrices (128 contiguous bytes each): SBO = 128 B between 8-row groups
+// along M / N, LBO = `lbo_bytes` between 8-column groups along K.  High word: SBO, descriptor version 1, layout type 0.
+constexpr uint32_t kDescHi32Mn = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo32_mn(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+constexpr uint32_t kIdescAMn = 1u << 15, kIdescBMn = 1u << 16;     // instruction-descriptor bits: A / B operand is MN-major
 // all MMAs issued so far by this thread arrive, when complete, on the barrier at this shared-memory offset in BOTH CTAs
 __device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -351,8 +381,23 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t smem_addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
   return v;
 }
-// generic-proxy writes (to shared memory of this CTA or of a cluster peer) -> visible to the async proxy (tensor core reads)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to shared memory of this CTA or of a cluster peer -> visible to the async proxy (tensor core reads).
+// (The unqualified fence.proxy.async also covers global memory and compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC.)
+__device__ __forceinline__ void fence_proxy_async_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
+// arrive with cluster-scope release on a barrier of THIS CTA (orders this thread's -- and, through a preceding __syncwarp /
+// bar.sync, its warp's / CTA's -- stores into the peer's shared memory before the arrival)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // global-memory flags of the member exchange between CTA pairs
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
