@@ -66,7 +66,7 @@ def load(debug=False):
     if debug in _libs:
         return _libs[debug]
     default = DEBUG_LIB_PATH if debug else LIB_PATH
-    path = os.environ.get("L2A_B200_LIB", default) if not debug else default      # development: A/B two builds on the same box
+    path = os.environ.get("L2A_B200_DEBUG_LIB" if debug else "L2A_B200_LIB", default)      # development: A/B two builds on the same box
     if not os.path.exists(path):
         raise ImportError(
             "learning_to_adapt_b200: %s is missing. Build it with `python -m learning_to_adapt_b200.build%s` "

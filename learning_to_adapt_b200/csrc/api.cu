@@ -31,7 +31,7 @@ using namespace l2a;
 
 // AUTO kernel choice: 1 = prefer the CTA-pair tcgen05 rollout where the shape allows it (L2A_TC_PAIR=0/1 overrides at run time)
 #ifndef L2A_TC_PAIR_DEFAULT
-#define L2A_TC_PAIR_DEFAULT 0
+#define L2A_TC_PAIR_DEFAULT 1
 #endif
 
 static thread_local char g_err[512] = "";
@@ -416,7 +416,7 @@ static int launch_tc2(l2a_ctx* c, const l2a_model* m, const Tc2Args& ta, int csi
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(ta.n_envs * ta.groups_per_env * csize * 2));
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(kTc2Threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -433,18 +433,20 @@ static int launch_tc2(l2a_ctx* c, const l2a_model* m, const Tc2Args& ta, int csi
 
 // candidates per CTA of the pair kernel (a tile is 2 * nc candidates): fewest waves of CTA pairs, then the smaller tile
 static int pick_nc2(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
-  static const int opts[3] = {72, 48, 32};
+  static const int opts[4] = {80, 72, 48, 32};
   if (const char* ov = getenv("L2A_TC2_NC")) {                  // tuning / experiments only
     const int v = atoi(ov);
-    if (v == 72 || v == 48 || v == 32) return v;
+    if (v == 80 || v == 72 || v == 48 || v == 32) return v;
   }
   int best = 72;
   double best_cost = 1e300;
-  const int slots = std::max(1, c->num_sms / 2);                // CTA pairs resident at once (1 CTA / SM)
-  for (int i = 0; i < 3; ++i) {
+  // candidate tiles resident at once: 1 CTA / SM, and the csize member pairs of a tile only make progress together (they
+  // meet every horizon step), so a wave holds whole tiles
+  const int slots = std::max(1, (c->num_sms / 2) / csize);
+  for (int i = 0; i < 4; ++i) {
     const int nc = opts[i];
-    const long long pairs = (long long)n_envs * ((n_cand + 2 * nc - 1) / (2 * nc)) * csize;
-    const long long waves = (pairs + slots - 1) / slots;
+    const long long tiles = (long long)n_envs * ((n_cand + 2 * nc - 1) / (2 * nc));
+    const long long waves = (tiles + slots - 1) / slots;
     const double cost = (double)waves * (48.0 + nc);
     if (cost < best_cost) { best_cost = cost; best = nc; }
   }
@@ -612,12 +614,14 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
     }
     if (small) {
       switch (nc) {
+        case 80: return launch_tc2<80, 24>(c, m, ta, csize, st);
         case 72: return launch_tc2<72, 24>(c, m, ta, csize, st);
         case 48: return launch_tc2<48, 24>(c, m, ta, csize, st);
         default: return launch_tc2<32, 24>(c, m, ta, csize, st);
       }
     }
     switch (nc) {
+      case 80: return launch_tc2<80, 48>(c, m, ta, csize, st);
       case 72: return launch_tc2<72, 48>(c, m, ta, csize, st);
       case 48: return launch_tc2<48, 48>(c, m, ta, csize, st);
       default: return launch_tc2<32, 48>(c, m, ta, csize, st);

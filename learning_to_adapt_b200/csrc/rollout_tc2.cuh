@@ -34,11 +34,19 @@
 
 namespace l2a {
 
-// timing experiments only: 1 = every epilogue store goes to the CTA's own shared memory (garbage results); 2 = CTA-scope proxy
-// fence in the hidden epilogue (the cluster-scope release of the arrival stays)
+// timing experiments only: 1 = every epilogue store goes to the CTA's own shared memory (garbage results); 3 = cluster-scope
+// proxy fence by every lane in the hidden epilogue (see there)
 #ifndef L2A_TC2_EXPERIMENT
 #define L2A_TC2_EXPERIMENT 0
 #endif
+// warpgroups per CTA: 3 = epilogue/env + (producer, issuer, helpers) + (helpers, 2nd producer); 4 adds a second helper group
+// (warps 12-15), every non-env warp then runs at 88 registers
+#ifndef L2A_TC2_WGS
+#define L2A_TC2_WGS 3
+#endif
+constexpr int kTc2Threads = 128 * L2A_TC2_WGS;
+constexpr int kTc2Parts = L2A_TC2_WGS - 1;          // warps that share a TMEM lane quadrant in the hidden epilogue
+#define L2A_TC2_DEC_REGS() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(L2A_TC2_WGS == 4 ? 88 : 128))
 constexpr int kTc2StageBytes = 32768;     // per CTA and ring stage: W_hi tile + W_lo tile of this CTA's 128 rows (or output-layer tiles)
 constexpr int kTc2MaxStages = 4;
 constexpr int kTc2XChunk = kTcMaxChunks - 1;   // activation chunk that holds the layer-0 input (not written by the M-block-0 epilogue)
@@ -209,7 +217,7 @@ struct Tc2Smem {
 };
 
 template <int NC, int DMAX>
-__global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Args a, const __grid_constant__ CUtensorMap wmap) {
+__global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Args a, const __grid_constant__ CUtensorMap wmap) {
   using S = Tc2Smem<NC>;
   constexpr int kChunkBytes = S::kChunkBytes;
   constexpr int kStages = S::kStages;
@@ -272,12 +280,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     }
     umma::mbar_init(layer_full, 1);
     umma::mbar_init(early, 1);
-    umma::mbar_init(&act_ready[0], 16);          // one arrival per epilogue / helper warp of both CTAs
-    umma::mbar_init(&act_ready[1], 16);
+    umma::mbar_init(&act_ready[0], 8 * kTc2Parts);   // one arrival per epilogue / helper warp of both CTAs
+    umma::mbar_init(&act_ready[1], 8 * kTc2Parts);
     umma::mbar_init(x_ready, 8);                 // one arrival per env-step warp of both CTAs
     umma::fence_barrier_init();
   }
-  for (int i = tid; i < DMAX; i += kTcThreads) {
+  for (int i = tid; i < DMAX; i += kTc2Threads) {
     const bool in = i < D;
     n_obs_mean[i] = in ? a.norm.obs_mean[i] : 0.f;
     n_obs_den[i] = in ? 1.0f / a.norm.obs_den[i] : 0.f;
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     n_dscale[i] = in ? a.norm.delta_scale[i] : 0.f;
     n_bias_out[i] = in ? P[md.b_off[L - 1] + i] : 0.f;
   }
-  for (int i = tid; i < kTcMaxAct; i += kTcThreads) {
+  for (int i = tid; i < kTcMaxAct; i += kTc2Threads) {
     n_act_mean[i] = (i < A) ? a.norm.act_mean[i] : 0.f;
     n_act_den[i] = (i < A) ? 1.0f / a.norm.act_den[i] : 0.f;
   }
@@ -309,12 +317,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
   // -> bf16 hi / lo -> ONE 16-byte store per part, straight from registers into the owning CTA's buffer (st.shared for its own
   // candidate groups, st.shared::cluster for the peer's) -- no transposition, no staging.  A warp's 32 lanes cover 4 feature
   // groups x 8 rows: every quarter-warp stores 128 contiguous bytes.
-  // The epilogue warps take candidate groups [0, kGa) u [kGr, kGr + kGb), the helper warps the rest: both halves mix own and peer groups.
+  // The kTc2Parts warps of a quadrant (epilogue warp + helpers) split the candidate groups: part p takes the p-th share of the
+  // CTA's own groups and the (kTc2Parts-1-p)-th share of the peer's, so every warp mixes local and DSMEM stores.
   constexpr int kSlabBytes = NC * 16;                       // 8 features x NC candidates x 2 B
   constexpr int kGr = NC / 8;                               // 8-candidate groups per CTA
-  constexpr int kGa = (kGr + 1) / 2, kGb = kGr / 2;
-  auto hidden_epilogue = [&](auto main_tag, int t, int l, int slot_a, int wq, bool stamps, uint32_t& lf_phase, uint32_t& early_phase) {
-    constexpr bool MAIN = decltype(main_tag)::value != 0;
+  auto hidden_epilogue = [&](auto part_tag, int t, int l, int slot_a, int wq, bool stamps, uint32_t& lf_phase, uint32_t& early_phase) {
+    constexpr int PART = decltype(part_tag)::value, RPART = kTc2Parts - 1 - PART;
     const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
     const uint32_t peer_hi = umma::map_to_cta(act_hi_addr, rank ^ 1u), peer_lo = umma::map_to_cta(act_lo_addr, rank ^ 1u);
     for (int mb = 0; mb < plan.nmb[l]; ++mb) {
@@ -361,16 +369,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
           }
         }
       };
-      if (MAIN) {
-        drain(IntTag<0>{}, IntTag<kGa>{});
-        drain(IntTag<kGr>{}, IntTag<kGr + kGb>{});
-      } else {
-        drain(IntTag<kGa>{}, IntTag<kGr>{});
-        drain(IntTag<kGr + kGb>{}, IntTag<2 * kGr>{});
-      }
-      // every lane: its rows -> async proxy; then ONE cluster-scope release per warp (cumulative over the warp through
-      // __syncwarp) orders the rows stored into the peer's shared memory before the arrival on the leader's barrier
-      if (L2A_TC2_EXPERIMENT == 2) umma::fence_proxy_async_smem(); else umma::fence_proxy_async_cluster();
+      drain(IntTag<(PART * kGr) / kTc2Parts>{}, IntTag<((PART + 1) * kGr) / kTc2Parts>{});
+      drain(IntTag<kGr + (RPART * kGr) / kTc2Parts>{}, IntTag<kGr + ((RPART + 1) * kGr) / kTc2Parts>{});
+      // every lane: its rows in this CTA's shared memory -> async proxy (CTA-scope proxy fence); then ONE cluster-scope release per
+      // warp (cumulative over the warp through __syncwarp; SASS: MEMBAR.ALL.GPU, i.e. the rows stored into the peer's shared memory
+      // have been performed there) before the arrival on the leader's barrier.  fence.proxy.async.shared::cluster by every lane
+      // instead (a second MEMBAR.ALL.GPU per lane in front of the same SM-local FENCE.VIEW.ASYNC.S) costs 2 k cycles per horizon
+      // step (0.655 vs 0.610 ms at the headline shape) and changes no result.
+      if (L2A_TC2_EXPERIMENT == 3) umma::fence_proxy_async_cluster(); else umma::fence_proxy_async_smem();
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -385,15 +391,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
   };
 
   if (warp >= 6) {
-    // ================================================================ epilogue helpers (warps 6-9), second producer (warp 10)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
-    if (warp < 10) {
+    // ================================================================ epilogue helpers (warps 6-9 [, 12-15]), second producer (warp 10)
+    L2A_TC2_DEC_REGS();
+    if (warp < 10 || warp >= 12) {
       const int wq = warp & 3;
       uint32_t lf_phase = 0, early_phase = 0;
       int slot_a = 0;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l + 1 < L; ++l) {
-          hidden_epilogue(IntTag<0>{}, t, l, slot_a, wq, false, lf_phase, early_phase);
+          if (kTc2Parts == 3 && warp >= 12) hidden_epilogue(IntTag<kTc2Parts - 1>{}, t, l, slot_a, wq, false, lf_phase, early_phase);
+          else hidden_epilogue(IntTag<1>{}, t, l, slot_a, wq, false, lf_phase, early_phase);
           slot_a = (slot_a + 2) % 3;
         }
         umma::mbar_wait(layer_full, lf_phase);                           // the output layer's completion
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     }
   } else if (warp == 4) {
     // ================================================================ TMA producer: W_hi halves
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    L2A_TC2_DEC_REGS();
     if (lane == 0) {
       const uint32_t full_leader = umma::map_to_cta(umma::smem_u32(&full_hi[0]), 0);
       int stage = 0;
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     }
     __syncwarp();
   } else if (warp == 5) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    L2A_TC2_DEC_REGS();
     // ================================================================ MMA issuer (leader CTA only; the whole warp walks the loops)
     if (rank == 0) {
       int stage = 0;
@@ -699,7 +706,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc2_kernel(const Tc2Arg
     for (int t = 0; t < H; ++t) {
       const float disc_t = __ldg(a.discount_pow + t);
       for (int l = 0; l + 1 < L; ++l) {
-        hidden_epilogue(IntTag<1>{}, t, l, slot_a, warp, warp == 0, lf_phase, early_phase);
+        hidden_epilogue(IntTag<0>{}, t, l, slot_a, warp, warp == 0, lf_phase, early_phase);
         slot_a = (slot_a + 2) % 3;
       }
       if (t + 1 < H) load_actions(t + 1);

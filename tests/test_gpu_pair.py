@@ -113,3 +113,96 @@ def test_pair_kernel_repeatable_and_unsupported_shape():
     actions = O.sample_rs_actions(2, prob["low"], prob["high"], 3, 40)
     with pytest.raises(Exception, match="256"):
         _run(eng, prob, actions, 40, 3, "shared", 1, PAIR)
+
+
+# ------------------------------------------------------------------------------------------------ the host-buffer planning calls
+@pytest.mark.parametrize("graph", [True, False])
+def test_pair_kernel_inside_the_host_buffer_plan_call(graph, monkeypatch):
+    """l2a_plan_run_ex with a pair-eligible model (AUTO -> CTA-pair kernel, including the flag reset of the member exchange inside
+    the captured graph): every call's choice equals the oracle's argmax over the candidates that call drew."""
+    if not graph:
+        monkeypatch.setenv("L2A_NO_GRAPH", "1")
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=5, m=2, seed=21)
+    eng = make_engine(prob)
+    n, h = 200, 6
+    for call in range(4):
+        obs = prob["obs0"] + 0.01 * call
+        acts, ret, idx = eng.plan_rs_host(obs, n, h, prob["reward_kind"], prob["dt"], prob["low"], prob["high"],
+                                          discount=0.95, set_mode=2, first_set=0, n_sets=5, seed=7)
+        cand = eng.last_plan_candidates()
+        np.testing.assert_array_equal(cand, O.sample_rs_actions_device(7, call, prob["low"], prob["high"], h, 2 * n))
+        want = O.rollout_returns(obs.astype(np.float32).astype(np.float64), cand.astype(np.float64), prob["param_sets"],
+                                 prob["norm"], prob["reward_kind"], prob["dt"], 0.95, "ensemble")
+        assert_argmax_consistent(idx, want)
+        assert_returns_close(ret, want[range(2), idx])
+        np.testing.assert_array_equal(acts, cand[0].reshape(2, n, -1)[range(2), idx].astype(np.float64))
+        assert eng.last_plan_uses_graph() == (graph and call >= 1)
+
+
+def test_pair_kernel_behind_the_drop_in_controller_numpy_stream():
+    """MPCController.get_actions with the package's default sampler (numpy's MT19937 stream regenerated on the device) on a
+    512-wide model = the CTA-pair kernel: the chosen actions are the oracle's choice on numpy's own draw, bit for bit."""
+    from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=3, seed=31)
+    env = SyntheticEnv("half_cheetah")
+    model = MLPDynamicsModel("dyn", env, hidden_sizes=(512, 512))
+    model.set_params(prob["param_sets"][0])
+    model.set_normalization(prob["norm"])
+    ctrl = MPCController("policy", env, model, n_candidates=250, horizon=7)
+    np.random.seed(12)
+    for call in range(2):
+        acts, _ = ctrl.get_actions(prob["obs0"])
+    np.random.seed(12)
+    for call in range(2):
+        cand = np.random.uniform(prob["low"], prob["high"], size=(7 * 250 * 3, prob["act_dim"])).reshape(7, 750, -1)
+        want_act, best, _ = O.rs_plan(prob["obs0"], cand, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"])
+    np.testing.assert_array_equal(acts, want_act)
+
+
+def test_pair_kernel_grbal_loop_device_window_equals_host_lists():
+    """The whole GrBAL sampling loop (window gather -> K2 adapt -> re-tile of BOTH blobs -> K1 per-env sets -> window push in one
+    call) on a 256-wide model, i.e. through the pair kernel: same actions and bit-identical adapted weights as the host lists."""
+    from tests.test_gpu_window import _grbal
+    paths_d, adapted_d, prob = _grbal("device", hidden=(256, 256))
+    paths_l, adapted_l, _ = _grbal("lists", hidden=(256, 256))
+    for pd, pl in zip(paths_d, paths_l):
+        np.testing.assert_array_equal(pd["actions"], pl["actions"])
+    for ad, al in zip(adapted_d, adapted_l):
+        for k in ad:
+            np.testing.assert_array_equal(ad[k], al[k])
+
+
+def test_pair_kernel_cem_one_call_teacher_forced():
+    """CEM in one host-buffer call on a 512-wide model, ONE iteration, bug-compatible mode, numpy's normal stream: the call's
+    per-candidate returns agree with the oracle on the same samples, and its refit (mean, std) is exactly the reference's rule
+    (mpc_controller.py:101-104) applied to the call's own returns."""
+    from learning_to_adapt_b200.dynamics.mlp_dynamics import MLPDynamicsModel
+    from learning_to_adapt_b200.envs.synthetic import SyntheticEnv
+    from learning_to_adapt_b200.policies.mpc_controller import MPCController
+    n, h, pct, alpha = 1200, 12, 0.1, 0.1
+    prob = O.make_problem("half_cheetah", hidden_sizes=(512, 512), n_sets=1, m=1, seed=16)
+    A = prob["act_dim"]
+    env = SyntheticEnv("half_cheetah")
+    model = MLPDynamicsModel("dyn", env, hidden_sizes=(512, 512))
+    model.set_params(prob["param_sets"][0])
+    model.set_normalization(prob["norm"])
+    ctrl = MPCController("policy", env, model, use_cem=True, n_candidates=n, horizon=h, num_cem_iters=1, percent_elites=pct, alpha=alpha)
+    ctrl.keep_returns = True
+    np.random.seed(28)
+    acts, _ = ctrl.get_actions(prob["obs0"])
+    got = ctrl.last_plan["returns"]
+    z = np.random.RandomState(28).normal(size=(n, 1, h * A))                              # mean 0, std 1: the samples are z itself
+    a_roll = np.transpose(z.astype(np.float32).astype(np.float64).reshape(n, h, A), (1, 0, 2))
+    want = O.rollout_returns(prob["obs0"], a_roll, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "shared")
+    assert_returns_close(got, want)
+    k = max(int(n * pct), 1)
+    order = np.argsort(-np.asarray(got, np.float64), axis=-1, kind="stable")
+    mask = (order < k).T
+    clipped = np.clip(z, np.concatenate([prob["low"]] * h), np.concatenate([prob["high"]] * h))
+    elites = clipped[mask]
+    np.testing.assert_allclose(ctrl.last_cem_state[0][0], (1 - alpha) * elites.mean(axis=0), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ctrl.last_cem_state[1][0], elites.std(axis=0), rtol=1e-9, atol=1e-12)
+    best = int(np.argmax(got[0]))
+    np.testing.assert_array_equal(acts[0], z[best, 0, :A])                              # :106: first action of the best (unclipped) sample
