@@ -163,7 +163,17 @@ __global__ void __launch_bounds__(256) tc2_prep_kernel(const Prep2Args a) {
   uint8_t* tile_hi = set_base + ((size_t)blockIdx.x * 2 + rank) * kTc2StageBytes;
   uint8_t* tile_lo = tile_hi + kTcTileBytes;
   const bool packed = (l == 0 && p.l0_packed);
-  const int mb = packed ? 0 : rem / p.nkc[l], kc = packed ? 0 : rem % p.nkc[l];
+  int mb = 0, kc = 0;
+  if (!packed) {
+    if (l == 0) { mb = rem / p.nkc[l]; kc = rem % p.nkc[l]; }
+    else {
+      // hidden layers behind layer 0: K halves outermost -- chunks [0,4) for every M-block, then chunks [4, nkc) for every M-block
+      // (the first half needs only M-block 0 of the previous layer's epilogue)
+      const int h0 = p.nkc[l] < 4 ? p.nkc[l] : 4, h1 = p.nkc[l] - h0;
+      if (rem < p.nmb[l] * h0) { mb = rem / h0; kc = rem % h0; }
+      else { rem -= p.nmb[l] * h0; mb = rem / h1; kc = h0 + rem % h1; }
+    }
+  }
   for (int item = threadIdx.x; item < 128 * 8; item += blockDim.x) {
     const int r = item & 127, ch = item >> 7;
     const int f = (packed ? (ch >> 2) : mb) * 256 + rank * 128 + r;
@@ -342,6 +352,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
 #pragma unroll
           for (int i = 0; i < CNT; ++i) umma::tmem_ld_32x32b_x8(t_addr + (uint32_t)((G0 + i) * 8), r[i]);
           umma::tmem_ld_wait();
+          L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[100 + (G0 >= kGr ? 3 : 0)] = clock64());
 #pragma unroll
           for (int i = 0; i < CNT; ++i) {
             const int g = G0 + i;
@@ -369,8 +380,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
           }
         }
       };
-      drain(IntTag<(PART * kGr) / kTc2Parts>{}, IntTag<((PART + 1) * kGr) / kTc2Parts>{});
+      // the peer's groups first: their DSMEM stores are in flight while the own groups are converted
       drain(IntTag<kGr + (RPART * kGr) / kTc2Parts>{}, IntTag<kGr + ((RPART + 1) * kGr) / kTc2Parts>{});
+      L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[104] = clock64());
+      drain(IntTag<(PART * kGr) / kTc2Parts>{}, IntTag<((PART + 1) * kGr) / kTc2Parts>{});
+      L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[101] = clock64());
       // every lane: its rows in this CTA's shared memory -> async proxy (CTA-scope proxy fence); then ONE cluster-scope release per
       // warp (cumulative over the warp through __syncwarp; SASS: MEMBAR.ALL.GPU, i.e. the rows stored into the peer's shared memory
       // have been performed there) before the arrival on the leader's barrier.  fence.proxy.async.shared::cluster by every lane
@@ -379,6 +393,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
       if (L2A_TC2_EXPERIMENT == 3) umma::fence_proxy_async_cluster(); else umma::fence_proxy_async_smem();
       umma::tc_fence_before();
       __syncwarp();
+      L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[105] = clock64());
       if (lane == 0) {
         if (rank == 0) umma::mbar_arrive_release_cluster(&act_ready[mb]);
         else umma::mbar_arrive_remote(act_ready_leader + (uint32_t)mb * 8u);
@@ -549,23 +564,23 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
             }
           } else {
             const int nsrc = plan.nmb[l - 1];
-            for (int ev = 0; ev < nsrc; ++ev) {               // M-block 0, K-outer over the chunks as the previous epilogue publishes them
+            // K halves outermost: event ev = M-block ev of the previous layer's epilogue published chunks [4 ev, 4 ev + 4); both
+            // M-blocks of this layer consume them before the next event is needed, so the second half of the stages has the whole
+            // epilogue of the previous layer's M-block 1 (and the first half that of M-block 0) to hide behind.
+            // M-block 0 may be drained once its own accumulation is complete AND nothing reads chunks 0-3 any more (its epilogue
+            // overwrites them in place): after its part of the last event when there are two events, else with the whole layer.
+            for (int ev = 0; ev < nsrc; ++ev) {
               umma::mbar_wait_cluster(&act_ready[ev], (act_phase >> ev) & 1u);
               act_phase ^= (1u << ev);
               umma::tc_fence_after();
               if (ev == 0) L2A_STAMP(4 * l + 3);
               const int kc_end = min(nkc, 4 * ev + 4);
-              for (int kc = 4 * ev; kc < kc_end; ++kc) tile_pair(IntTag<1>{}, dA, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
-            }
-            L2A_STAMP(4 * l + 1);
-            if (nmb == 1) commit(early);
-            else {
-              // M-block 1; M-block 0's epilogue overwrites chunks 0-3 in place: it may start once M-block 1 is past them
-              for (int kc = 0; kc < nkc; ++kc) {
-                tile_pair(IntTag<1>{}, dB, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
-                if (kc == min(nkc - 1, 3)) commit(early);
+              for (int mb = 0; mb < nmb; ++mb) {
+                for (int kc = 4 * ev; kc < kc_end; ++kc) tile_pair(IntTag<1>{}, mb ? dB : dA, kc, kc == 0, (kc == nkc - 1) ? nks_last : 4);
+                if (mb == 0 && ev == nsrc - 1 && nsrc > 1) { commit(early); L2A_STAMP(4 * l + 1); }
               }
             }
+            if (nsrc == 1) commit(early);
           }
           commit(layer_full);
           L2A_STAMP(4 * l + 2);

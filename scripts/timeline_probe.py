@@ -49,3 +49,8 @@ for e in range(min(nsets, 5)):
         print("  member %d (globaltimer, ns rel. to member 0's flag): flag released %7d   all flags seen %7d" % (e, int(t[86 + 2 * e] - t[86]), int(t[87 + 2 * e] - t[86])))
     else:
         print("  member %d: deltas ready -> member mean done: %7d cycles" % (e, int(t[87 + 2 * e] - t[86 + 2 * e])))
+
+if KERNEL == 3:
+    e0 = t[32 + 4 * 1]
+    print("pair epilogue of layer 1, M-block 0, warp 0 (cycles after `early` seen): own groups loaded %d, stored %d | peer groups loaded %d, stored (issued) %d | proxy fence + syncwarp %d | arrived %d"
+          % tuple(int(t[i] - e0) for i in (100, 101, 103, 104, 105, 32 + 4 * 1 + 1)))
