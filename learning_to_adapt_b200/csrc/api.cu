@@ -590,7 +590,8 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
     const bool small = m->dims.obs_dim <= 24 && m->dims.act_dim <= 8;
     if (csize > 1) {
       const size_t tiles = (size_t)p->n_envs * groups;
-      const size_t need = tiles * 2 * csize * 2 * (size_t)nc * (small ? 24 : 48);      // floats: [tile][parity][E][rank][NC][DMAX]
+      // floats: [tile][parity][E][rank][NC][DMAX]; the flag-in-data exchange stores a step word beside every value (2x)
+      const size_t need = tiles * 2 * csize * 2 * (size_t)nc * (small ? 24 : 48) * (L2A_TC2_LL ? 2 : 1);
       if (need > c->xch_cap) {
         cudaFree(c->xch);
         c->xch = nullptr;
@@ -609,6 +610,7 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
         c->ws_epoch++;
       }
       CUDA_TRY(cudaMemsetAsync(c->xflags, 0, nflags * sizeof(unsigned int), st));        // step counters start at 0 every launch
+      if (L2A_TC2_LL) CUDA_TRY(cudaMemsetAsync(c->xch, 0, need * sizeof(float), st));      // ... and so do the step words in the rows
       ta.xch = c->xch;
       ta.flags = c->xflags;
     }

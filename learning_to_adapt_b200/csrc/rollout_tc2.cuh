@@ -41,6 +41,13 @@ namespace l2a {
 #endif
 // warpgroups per CTA: 3 = epilogue/env + (producer, issuer, helpers) + (helpers, 2nd producer); 4 adds a second helper group
 // (warps 12-15), every non-env warp then runs at 88 registers
+// member exchange of the ensemble mode: 0 (default) = rows + one release flag per (member, rank); 1 = flag-in-data ("LL": every
+// 16-byte unit carries two {value, step} words, readers poll the data itself: no fence, no flag round trip, no CTA barrier).
+// Measured (B200, headline): LL 0.819 ms vs 0.602 ms -- 128 threads x 40 polled 16-byte gpu-scope loads per CTA make the
+// exchange 27 k cycles per step instead of 7 k (profiles/r02_negative_results.md); kept for the record, parity-green.
+#ifndef L2A_TC2_LL
+#define L2A_TC2_LL 0
+#endif
 #ifndef L2A_TC2_WGS
 #define L2A_TC2_WGS 3
 #endif
@@ -756,6 +763,74 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
       slot_a = (slot_a + 2) % 3;
       umma::tc_fence_before();
       if (warp == 0) L2A_STAMP(61);
+#if L2A_TC2_LL
+      if (ensemble) {
+        // Member exchange through L2, flag in data: a row is DMAX/2 16-byte units {d[2q], step+1, d[2q+1], step+1}, laid out
+        // [member][rank][unit][candidate] (a warp's store of one unit is 512 contiguous bytes).  Every thread publishes its own row with
+        // relaxed gpu-scope 16-byte stores and polls the same row of the other members until both step words of every unit match
+        // (each 8-byte {value, step} half is single-copy atomic, so a matching word carries its value): one L2 round trip after
+        // the slowest member's stores, no fence, no barrier.  Members are averaged in member order 0..E-1 (bit-identical on every
+        // member).  Double-buffered by step parity; the host zeroes the scratch before every launch.
+        constexpr int DU = DMAX / 2;
+        const int du = (D + 1) >> 1;
+        constexpr size_t kBlkU = (size_t)NC * DU;
+        uint4* const blk0 = reinterpret_cast<uint4*>(a.xch) + ((size_t)(tile_id * 2 + (t & 1)) * csize) * 2 * kBlkU;
+        const uint32_t flag = (uint32_t)(t + 1);
+        if (has_cand) {
+          uint4* mine = blk0 + (size_t)(member * 2 + (int)rank) * kBlkU + n;
+#pragma unroll
+          for (int q = 0; q < DU; ++q)
+            if (q < du) umma::st_relaxed_gpu_v4(mine + q * NC, make_uint4(__float_as_uint(dl[2 * q]), flag, __float_as_uint(dl[2 * q + 1]), flag));
+        }
+        if (warp == 0) L2A_STAMP(65);
+        L2A_TIMELINE(if (a.timeline && (blockIdx.x & 1) == 0 && blockIdx.x < 10 && t == 1 && tid == 0) a.timeline[86 + blockIdx.x] = (long long)umma::globaltimer_ns());
+        if (has_cand) {
+          constexpr int EB = 2, QB = (DMAX <= 24) ? DU : 6;               // members x units polled together (register budget)
+          float acc[DMAX];
+#pragma unroll
+          for (int k = 0; k < DMAX; ++k) acc[k] = 0.f;
+          const uint4* rows = blk0 + (size_t)rank * kBlkU + n;              // member e: + e * 2 * kBlkU
+#pragma unroll
+          for (int qb = 0; qb < DU; qb += QB) {
+            if (qb < du) {
+              for (int e0 = 0; e0 < csize; e0 += EB) {
+                uint4 u[EB][QB];
+                const long long w0 = clock64();
+                bool ok;
+                do {
+                  ok = true;
+#pragma unroll
+                  for (int j = 0; j < EB; ++j)
+#pragma unroll
+                    for (int q = 0; q < QB; ++q)
+                      if (qb + q < DU && e0 + j < csize && e0 + j != member && qb + q < du) {
+                        u[j][q] = umma::ld_relaxed_gpu_v4(rows + (size_t)(e0 + j) * 2 * kBlkU + (qb + q) * NC);
+                        ok = ok && (u[j][q].y == flag) && (u[j][q].w == flag);
+                      }
+                  if (!ok && clock64() - w0 > L2A_WATCHDOG_CYCLES) __trap();
+                } while (!ok);
+#pragma unroll
+                for (int j = 0; j < EB; ++j)
+                  if (e0 + j < csize) {
+                    const bool own = (e0 + j == member);
+#pragma unroll
+                    for (int q = 0; q < QB; ++q)
+                      if (qb + q < DU) {
+                        const int k = 2 * (qb + q);
+                        acc[k] += own ? dl[k] : __uint_as_float(u[j][q].x);
+                        acc[k + 1] += own ? dl[k + 1] : __uint_as_float(u[j][q].z);
+                      }
+                  }
+              }
+            }
+          }
+          const float inv_e = 1.0f / (float)csize;
+#pragma unroll
+          for (int k = 0; k < DMAX; ++k) dl[k] = (k < 2 * du) ? acc[k] * inv_e : dl[k];
+        }
+        if (warp == 0) L2A_STAMP(67);
+      }
+#else
       if (ensemble) {
         // Member exchange through L2 (see the header): rows stored -> gpu-scope fence -> CTA barrier -> one release flag per
         // (member, rank) -> the E-1 other flags acquired -> CTA barrier -> the other members' rows read with ld.global.cg and
@@ -825,6 +900,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
           else mean_rows(IntTag<8>{}, IntTag<1>{});
         }
       }
+#endif
       if (warp == 0) L2A_STAMP(62);
       // ---------------- env step: (mean) delta -> reward -> state update -> next normalised input
       if (has_cand) {

@@ -393,6 +393,15 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 __device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// 16-byte relaxed gpu-scope store / load (each 8-byte half is single-copy atomic: the {value, flag} words of the member exchange)
+__device__ __forceinline__ void st_relaxed_gpu_v4(uint4* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
