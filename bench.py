@@ -25,8 +25,9 @@ e2e    : the same metric through the public API call MPCController.get_actions(o
          the ranks' winners over NVLink), device->host copy of the chosen actions -- all inside the timed region.  Sampler =
          device Philox; `default_sampler_value` = the same with the package's DEFAULT sampler (the reference's numpy stream
          regenerated on the device), which is what unchanged run scripts get.
-roofline: dominant kernel rollout_tc_kernel, tensor-pipe bound; achieved = algorithmic FLOPs per launch (rows*H*E*F, counted once
-         although split-bf16 issues 3 MMA passes) / mean launch duration measured here with CUDA events.
+roofline: dominant kernel rollout_tc2_kernel (the CTA-pair tcgen05 rollout; rollout_tc_kernel with L2A_TC_PAIR=0), tensor-pipe bound;
+         achieved = algorithmic FLOPs per launch (rows*H*E*F, counted once although split-bf16 issues 3 MMA passes) / mean launch
+         duration measured here with CUDA events.
 cpu_baseline / --impl reference: the reference's planner on the host cores: the VERBATIM upstream MPCController (oracle/_ref, made
          by oracle/make_ref.py) when present -- kind "reference" -- else its oracle restatement (kind "port"); the dynamics model
          behind it is the oracle's float32 BLAS port in both cases (TF 1.13.1 cannot be installed; "ensemble" has no upstream code).
@@ -510,9 +511,10 @@ def run_cuda(args):
     flops_per_launch = n * m * h * e_eff * F
     achieved = flops_per_launch / (ms_kernel * 1e-3) / 1e12
     traffic = None
+    kernel_name = "rollout_tc_kernel" if os.environ.get("L2A_TC_PAIR") == "0" else "rollout_tc2_kernel"
     tpath = os.path.join(REPO, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("rollout_tc_kernel:" + args.config)
+        traffic = json.load(open(tpath)).get(kernel_name + ":" + args.config)
     line = dict(metric=METRIC, value=value, unit="rollouts/s", n_gpus=world, steps=args.steps, warmup=W,
                 ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="bf16x3-split (fp32 accumulate)",
                 data="synthetic", config=config_dict(args.config, cfg, world, args.scaling,
@@ -526,7 +528,7 @@ def run_cuda(args):
                 exchange=(dict(value_uses="peer-memory exchange kernel (l2a_plan_exchange_resident)", ms_per_step_peer=ms_step,
                                ms_per_step_nccl_allgather=nccl_ms) if distributed else None),
                 roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"],
-                              traffic=traffic, kernel="rollout_tc_kernel", kernel_ms=ms_kernel,
+                              traffic=traffic, kernel=kernel_name, kernel_ms=ms_kernel,
                               flops_per_launch=flops_per_launch, peak_source=peaks["source"],
                               note="algorithmic FLOPs counted once; the kernel issues 3 bf16 MMA passes per product (split-bf16), so the "
                                    "attainable fraction of the bf16 peak is 1/3; traffic = ncu dram bytes per launch (profiles/)"),

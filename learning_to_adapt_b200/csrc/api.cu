@@ -84,6 +84,7 @@ struct l2a_model {
   bool tc2_ok = false;
   uint8_t* blobs2 = nullptr;   // [n_sets][plan2.set_bytes]
   CUtensorMap wmap2;           // blobs2 as a 2-D tensor of 128-byte rows, box = one 16 KB tile
+  std::vector<uint8_t> stale1; // per set: the single-CTA blob is behind the fp32 parameters (re-tiled on demand, see launch_prep)
   float* norm = nullptr;       // obs_mean[D] obs_den[D] act_mean[A] act_den[A] delta_mean[D] delta_scale[D]
   bool norm_set = false;
   NormDev norm_dev() const {
@@ -224,6 +225,7 @@ extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** o
   MlpDims& md = m->dims;
   fill_dims(d, &md);
   m->tc_ok = tc_make_plan(md, &m->plan);
+  m->stale1.assign((size_t)d->n_sets, 0);
   const size_t pbytes = (size_t)d->n_sets * md.set_stride * sizeof(float);
   if (cudaMalloc(&m->params, pbytes) != cudaSuccess) { delete m; return fail(L2A_ERR_CUDA, "cudaMalloc(params, %zu)", pbytes); }
   cudaMemset(m->params, 0, pbytes);
@@ -260,6 +262,29 @@ extern "C" int l2a_model_destroy(l2a_ctx* c, l2a_model* m) {
   return L2A_OK;
 }
 
+static bool prefer_pair() {
+  static const int v = [] { const char* e = getenv("L2A_TC_PAIR"); return e ? atoi(e) : L2A_TC_PAIR_DEFAULT; }();
+  return v != 0;
+}
+
+static int launch_prep1(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, cudaStream_t st) {
+  PrepArgs pa;
+  pa.dims = m->dims;
+  pa.plan = m->plan;
+  pa.params = m->params;
+  pa.blobs = m->blobs;
+  pa.first_set = first_set;
+  dim3 grid(m->plan.hidden_pairs + m->plan.nkc[m->plan.n_layers - 1], n_sets);
+  tc_prep_kernel<<<grid, 256, 0, st>>>(pa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  for (int s = first_set; s < first_set + n_sets; ++s) m->stale1[s] = 0;
+  return L2A_OK;
+}
+
+// Re-tile weight sets after their fp32 parameters changed (set_params, adapt, fit).  The blob of the kernel AUTO would choose
+// is rebuilt here, on the caller's stream; when that is the CTA-pair blob the single-CTA blob is only marked stale and rebuilt
+// by the first rollout that explicitly asks for that kernel (GrBAL adapts every env step: one re-tiling pass, not two).
 static int launch_prep(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, cudaStream_t st) {
   if (m->tc2_ok) {
     Prep2Args pa;
@@ -274,17 +299,11 @@ static int launch_prep(l2a_ctx* c, l2a_model* m, int first_set, int n_sets, cuda
     CUDA_TRY(cudaGetLastError());
   }
   if (!m->tc_ok) return L2A_OK;
-  PrepArgs pa;
-  pa.dims = m->dims;
-  pa.plan = m->plan;
-  pa.params = m->params;
-  pa.blobs = m->blobs;
-  pa.first_set = first_set;
-  dim3 grid(m->plan.hidden_pairs + m->plan.nkc[m->plan.n_layers - 1], n_sets);
-  tc_prep_kernel<<<grid, 256, 0, st>>>(pa);
-  c->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return L2A_OK;
+  if (m->tc2_ok && prefer_pair()) {
+    for (int s = first_set; s < first_set + n_sets; ++s) m->stale1[s] = 1;
+    return L2A_OK;
+  }
+  return launch_prep1(c, m, first_set, n_sets, st);
 }
 
 extern "C" int l2a_model_set_params(l2a_ctx* c, l2a_model* m, int set, const float* const* W, const float* const* b, void* stream) {
@@ -497,8 +516,7 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   const bool tc_possible = m->tc_ok && csize <= 8;
   const bool tc2_possible = m->tc2_ok && csize <= 8;
   if (kernel == L2A_KERNEL_AUTO) {
-    static const int prefer_pair = [] { const char* e = getenv("L2A_TC_PAIR"); return e ? atoi(e) : L2A_TC_PAIR_DEFAULT; }();
-    kernel = (tc2_possible && prefer_pair) ? L2A_KERNEL_TCGEN05_PAIR : tc_possible ? L2A_KERNEL_TCGEN05 : L2A_KERNEL_SIMT;
+    kernel = (tc2_possible && prefer_pair()) ? L2A_KERNEL_TCGEN05_PAIR : tc_possible ? L2A_KERNEL_TCGEN05 : L2A_KERNEL_SIMT;
   }
   if (kernel == L2A_KERNEL_TCGEN05_PAIR && !tc2_possible)
     return fail(L2A_ERR_UNSUPPORTED, "the CTA-pair tcgen05 rollout needs hidden widths that are multiples of 256 (<= 512), obs_dim <= 48, "
@@ -630,6 +648,14 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
     }
   }
 
+  for (int s = p->first_set; s <= last_set; ++s)
+    if (m->stale1[s]) {                                  // (see launch_prep) contiguous runs of stale sets, re-tiled on this stream
+      int e = s;
+      while (e + 1 <= last_set && m->stale1[e + 1]) ++e;
+      int rc1 = launch_prep1(c, m, s, e - s + 1, st);
+      if (rc1) return rc1;
+      s = e;
+    }
   const int nc = pick_nc(c, p->n_candidates, p->n_envs, csize);
   const int groups = (p->n_candidates + nc - 1) / nc;
   int rc = ensure_reduce_ws(c, (size_t)groups * p->n_envs, p->n_envs, st);
@@ -965,6 +991,9 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
   pl->out_meta = off;  off += cem ? sizeof(int32_t) * 2 * (size_t)std::max(1, opts->cem_iters) : 0;
   pl->out_bytes = align_up(off, 16);
   pl->use_graph = getenv("L2A_NO_GRAPH") == nullptr;
+  // a plan that forces the single-CTA tcgen05 kernel while AUTO prefers the CTA pair re-tiles stale sets on demand inside
+  // l2a_rollout (launch_prep): that decision is taken per call on the host, so such a plan issues its launches directly
+  if (p->kernel == L2A_KERNEL_TCGEN05 && m->tc2_ok && prefer_pair()) pl->use_graph = false;
   std::vector<float> consts((size_t)2 * A + H + (cem ? 2 * (size_t)ha : 0));
   std::vector<double> consts64((size_t)2 * A);
   if (cem)

@@ -33,8 +33,8 @@ if [[ "$WHAT" == *ncu* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
       --log-file gpurun_out/r02_launches_all_paths.csv python scripts/ncu_targets.py all > gpurun_out/r02_ncu_targets.log 2>&1
   # full capture of the dominant kernel (one launch, after the warm-up ones)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout_tc_kernel -s 3 -c 1 \
-      -o gpurun_out/r02_rollout_tc_full -f python scripts/ncu_targets.py headline > gpurun_out/r02_ncu_full.log 2>&1
-  ncu -i gpurun_out/r02_rollout_tc_full.ncu-rep --page raw --csv > gpurun_out/r02_rollout_tc_full_raw.csv 2>/dev/null
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout_tc2_kernel -s 3 -c 1 \
+      -o gpurun_out/r02_rollout_tc2_full -f python scripts/ncu_targets.py headline > gpurun_out/r02_ncu_full.log 2>&1
+  ncu -i gpurun_out/r02_rollout_tc2_full.ncu-rep --page raw --csv > gpurun_out/r02_rollout_tc2_full_raw.csv 2>/dev/null
   ls -la gpurun_out | tail -20
 fi
