@@ -1881,7 +1881,7 @@ extern "C" int l2a_shard_select(l2a_ctx* c, const float* gathered, int G, int m,
 #ifdef L2A_DEBUG_KERNELS
 extern "C" int l2a_debug_pair(l2a_ctx* c, int mode, int iters, int copy_bytes, long long* cycles_out, void* stream) {
   if (!c || !cycles_out) return fail(L2A_ERR_INVALID, "NULL argument");
-  if (mode < 0 || mode > 1 || iters < 1 || copy_bytes < 16 || copy_bytes > 16384 || copy_bytes % 16 != 0)
+  if (mode < 0 || mode > 3 || iters < 1 || copy_bytes < 16 || copy_bytes > 16384 || copy_bytes % 16 != 0)
     return fail(L2A_ERR_INVALID, "bad mode/iters/copy_bytes");
   if ((long long)iters * copy_bytes >= (1 << 20)) return fail(L2A_ERR_INVALID, "iters * copy_bytes must stay below the mbarrier tx-count range (1 MiB)");
   CUDA_TRY(cudaSetDevice(c->device));

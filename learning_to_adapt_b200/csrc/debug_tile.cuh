@@ -437,6 +437,28 @@ __global__ void __launch_bounds__(128, 1) debug_pair_kernel(int mode, int iters,
       umma::mbar_wait(&bar[0], 0);
       if ((tid & 31) == 0) { cycles_out[0] = clock64() - t0; cycles_out[1] = t_issued - t0; }
     }
+  } else if (mode == 2 || mode == 3) {
+    // DSMEM generic stores from registers (the pair kernel's epilogue): `copy_bytes` / 16 warps-wide 16-byte-per-lane
+    // st.shared::cluster instructions per warp, 4 warps, into the peer's 32 KB xfer region (b-tile area reused), then one
+    // cluster-scope release fence.  mode 2: a warp instruction covers 512 contiguous bytes; mode 3: four 128-byte pieces 1152
+    // bytes apart (what the MN-major epilogue issues).  cycles_out[2 + rank] = cycles until the fence has completed.
+    const uint32_t peer = rank ^ 1u;
+    const uint32_t base = umma::map_to_cta(umma::smem_u32(pair_smem), peer);        // the peer's 64 KB weight-ring area
+    const int lane = tid & 31;
+    const uint4 v = make_uint4(tid, 1, 2, 3);
+    umma::cluster_sync_all();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t slot = (uint32_t)((it * 4 + warp) & 31);                          // 32 slots of 2 KB
+      uint32_t off;
+      if (mode == 2) off = slot * 2048u + (uint32_t)lane * 16u;
+      else off = (slot & 7u) * 128u + (uint32_t)(lane >> 3) * 1152u + (uint32_t)(lane & 7) * 16u + (slot >> 3) * 4608u;
+      umma::st_cluster_v4(base + off, v);
+    }
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    const long long t1 = clock64();
+    if (tid == 0) cycles_out[2 + rank] = t1 - t0;
+    umma::cluster_sync_all();
   } else {
     // each CTA pushes `iters` copies into the peer's xfer_dst; the receiver waits on its own barrier
     if (warp == 1 && (tid & 31) == 0) {

@@ -28,3 +28,13 @@ for nbytes in (1024, 4096, 10240, 16384):
         torch.cuda.synchronize()
     o = out.cpu().numpy()
     print("DSMEM bulk copy %5d B x %2d, both directions: %.1f / %.1f B/clk per receiver" % (nbytes, iters, nbytes * iters / o[2], nbytes * iters / o[3]))
+
+for mode, what in ((2, "512 contiguous bytes per warp instruction"), (3, "four 128-byte pieces 1152 B apart per warp instruction (MN-major epilogue)")):
+    for iters in (16, 64, 256):
+        for _ in range(2):
+            N.check(lib.l2a_debug_pair(ctx, mode, iters, 16, C.c_void_p(out.data_ptr()), None))
+            torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        nbytes = iters * 4 * 512                     # 4 warps x 512 B per instruction
+        print("DSMEM st.shared::cluster.v4, %s: %4d instr / warp, %6d B per CTA: %.1f / %.1f B/clk (both directions at once)"
+              % (what, iters, nbytes, nbytes / o[2], nbytes / o[3]))

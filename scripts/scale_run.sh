@@ -10,3 +10,7 @@ for c in headline cfg5; do
   python -c "
 import json; d=json.load(open('gpurun_out/r02_bench_${c}_n$N.json')); print('$c N=$N value %.4g e2e %.4g ms/step %.4f e2e ms %.4f' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['e2e']['ms_per_call']))"
 done
+c=headline
+L2A_BENCH_SKIP_CPU=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 296$N bench.py --gpus $N --steps 20 --warmup 3 --config $c --scaling strong > gpurun_out/r02_bench_${c}_strong_n$N.json 2> gpurun_out/r02_bench_${c}_strong_n$N.err
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_${c}_strong_n$N.json')); print('$c strong N=$N value %.4g e2e %.4g ms/step %.4f e2e ms %.4f' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['e2e']['ms_per_call']))"
