@@ -1,7 +1,7 @@
 // K2: GrBAL one-step inner adaptation (dynamics/meta_mlp_dynamics.py:321-345, _adapt_sym 409-421, graph 96-120).
 //   theta'_k = theta - lr * d/dtheta mean_{M x D}((target_k - f_theta(x_k))^2)        for each task k < K.
 // Two kernels:
-//   adapt_fwd_bwd_kernel : a thread-block CLUSTER of kAdaptCluster CTAs per task walks the 2L-1 dependent stages (forward
+//   adapt_fwd_bwd_kernel : a thread-block CLUSTER of 16 (K <= 8 tasks) or 8 CTAs per task walks the 2L-1 dependent stages (forward
 //                          layers, loss gradient, backward chain).  Every stage is a skinny product over the M <= 32 context
 //                          rows: each CTA computes a slice of the stage's output features from the full input (32 KB, re-read
 //                          from L2 into shared memory), publishes it to the global workspace and the cluster barrier
@@ -18,7 +18,8 @@ namespace l2a {
 
 constexpr int kAdaptMaxM = 32;
 constexpr int kAdaptThreads = 256;
-constexpr int kAdaptCluster = 8;
+constexpr int kAdaptCluster = 8;          // CTAs per task: 16 (the non-portable maximum, one cluster per GPC) while all tasks' clusters are
+constexpr int kAdaptClusterMax = 16;      // resident at once (K <= 8 on B200's 8 GPCs), else 8
 
 struct AdaptArgs {
   MlpDims dims;
@@ -33,6 +34,7 @@ struct AdaptArgs {
   int act_off[kMaxLayers + 1];    // float offset of h_l inside a task's block (act_off[n_layers] = block size)
   int grad_off[kMaxLayers + 1];   // float offset of g_l inside a task's block
   float* params_out;        // == params (sets dst_first_set + k)
+  int csize;                // cluster size of adapt_fwd_bwd_kernel (CTAs per task)
 };
 
 template <int MR>
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(kAdaptThreads, 1) adapt_fwd_bwd_kernel(const A
   float* s_part = s_in + (size_t)W * MR;          // k-split partial sums [4 * kAdaptThreads][MR]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int crank = (int)umma::cluster_ctarank();
-  const int k = blockIdx.x / kAdaptCluster;       // task
+  const int k = blockIdx.x / a.csize;             // task
   const float* P = a.params + (size_t)a.src_set * md.set_stride;
   float* A0 = a.acts + (size_t)k * (size_t)a.act_off[md.n_layers];
   float* G0 = a.grads + (size_t)k * (size_t)a.grad_off[md.n_layers];
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(kAdaptThreads, 1) adapt_fwd_bwd_kernel(const A
       }
     }
     __syncthreads();
-    const int fs = (dout + kAdaptCluster - 1) / kAdaptCluster;          // output features per CTA
+    const int fs = (dout + a.csize - 1) / a.csize;                      // output features per CTA
     const int j0 = crank * fs, nf = max(0, min(fs, dout - j0));
     // thread = (group of 4 adjacent output features, k-slice): one 16-byte weight load feeds 4 x MR FMAs, 8 loads in flight
     const bool vec4 = (dout % 4 == 0) && (fs % 4 == 0);
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kAdaptThreads, 1) adapt_fwd_bwd_kernel(const A
       }
     }
     __syncthreads();
-    const int is = (din + kAdaptCluster - 1) / kAdaptCluster;
+    const int is = (din + a.csize - 1) / a.csize;
     const int i0 = crank * is, ni = max(0, min(is, din - i0));
     for (int ii = warp; ii < ni; ii += kAdaptThreads / 32) {
       const int i = i0 + ii;
@@ -199,27 +201,76 @@ __global__ void __launch_bounds__(kAdaptThreads, 1) adapt_fwd_bwd_kernel(const A
   }
 }
 
-// grid.x = tiles over the flattened [in_l * out_l] (+ out_l bias) of one layer, grid.y = layer, grid.z = task
+// theta'[i][j] = theta[i][j] - lr * sum_r h[i][r] g[r][j]   (+ the bias row: b'[j] = b[j] - lr * sum_r g[r][j])      _adapt_sym :416-417
+// grid.x = tiles of kUpdTI input rows x kUpdTJ output columns (row tiles fastest; one extra row tile carries the bias), grid.y = layer,
+// grid.z = task.  A CTA stages its h rows ([r][i], transposed) and g columns in shared memory once; a thread owns 4 rows x 4
+// adjacent columns: per context row r one 16-byte g load + one 16-byte h load feed 16 FMAs, theta is read and theta' written as
+// 16-byte vectors (HBM / L2 streaming: 4 B in + 4 B out per parameter).  Sum over r in ascending order, as the first version did.
+constexpr int kUpdTI = 32, kUpdTJ = 128;
 __global__ void __launch_bounds__(256) adapt_update_kernel(const AdaptArgs a) {
+  __shared__ __align__(16) float h_s[kAdaptMaxM][kUpdTI];
+  __shared__ __align__(16) float g_s[kAdaptMaxM][kUpdTJ];
   const MlpDims& md = a.dims;
   const int l = blockIdx.y, k = blockIdx.z, M = a.M;
   const int din = md.dims[l], dout = md.dims[l + 1];
+  const int tiles_j = (dout + kUpdTJ - 1) / kUpdTJ, tiles_i = (din + kUpdTI - 1) / kUpdTI;
+  if ((int)blockIdx.x >= tiles_j * (tiles_i + 1)) return;
+  const int tj = blockIdx.x / (tiles_i + 1), ti = blockIdx.x % (tiles_i + 1);
+  const int i0 = ti * kUpdTI, j0 = tj * kUpdTJ;
   const float* P = a.params + (size_t)a.src_set * md.set_stride;
   float* Q = a.params_out + (size_t)(a.dst_first_set + k) * md.set_stride;
   const float* h = a.acts + (size_t)k * (size_t)a.act_off[md.n_layers] + a.act_off[l];       // [din][M]
   const float* g = a.grads + (size_t)k * (size_t)a.grad_off[md.n_layers] + a.grad_off[l];    // [M][dout]
-  const int total = din * dout + dout;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    if (idx < din * dout) {
-      const int i = idx / dout, j = idx % dout;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < M * kUpdTJ; idx += 256) {
+    const int r = idx / kUpdTJ, j = idx % kUpdTJ;
+    g_s[r][j] = (j0 + j < dout) ? __ldcg(&g[(size_t)r * dout + j0 + j]) : 0.f;
+  }
+  if (ti < tiles_i)
+    for (int idx = tid; idx < kUpdTI * M; idx += 256) {
+      const int i = idx / M, r = idx % M;
+      h_s[r][i] = (i0 + i < din) ? __ldcg(&h[(size_t)(i0 + i) * M + r]) : 0.f;
+    }
+  __syncthreads();
+  const int jq = (tid & 31) * 4, iq = (tid >> 5) * 4;          // 32 column groups x 8 row groups
+  if (ti == tiles_i) {                                         // the bias row of this column tile
+    if (tid < kUpdTJ && j0 + tid < dout) {
       float s = 0.f;
-      for (int r = 0; r < M; ++r) s = fmaf(h[(size_t)i * M + r], g[(size_t)r * dout + j], s);
-      Q[md.w_off[l] + idx] = P[md.w_off[l] + idx] - a.lr * s;                 // _adapt_sym :416-417
+      for (int r = 0; r < M; ++r) s += g_s[r][tid];
+      Q[md.b_off[l] + j0 + tid] = P[md.b_off[l] + j0 + tid] - a.lr * s;
+    }
+    return;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+  for (int r = 0; r < M; ++r) {
+    const float4 gv = *reinterpret_cast<const float4*>(&g_s[r][jq]);
+    const float4 hv = *reinterpret_cast<const float4*>(&h_s[r][iq]);
+    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[u][0] = fmaf(hh[u], gv.x, acc[u][0]);
+      acc[u][1] = fmaf(hh[u], gv.y, acc[u][1]);
+      acc[u][2] = fmaf(hh[u], gv.z, acc[u][2]);
+      acc[u][3] = fmaf(hh[u], gv.w, acc[u][3]);
+    }
+  }
+  const bool vec = (dout % 4 == 0) && (j0 + jq + 3 < dout) && (md.w_off[l] % 4 == 0);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + iq + u;
+    if (i >= din) continue;
+    const size_t off = (size_t)md.w_off[l] + (size_t)i * dout + j0 + jq;
+    if (vec) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(P + off));
+      *reinterpret_cast<float4*>(Q + off) = make_float4(p.x - a.lr * acc[u][0], p.y - a.lr * acc[u][1], p.z - a.lr * acc[u][2], p.w - a.lr * acc[u][3]);
     } else {
-      const int j = idx - din * dout;
-      float s = 0.f;
-      for (int r = 0; r < M; ++r) s += g[(size_t)r * dout + j];
-      Q[md.b_off[l] + j] = P[md.b_off[l] + j] - a.lr * s;
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (j0 + jq + v < dout) Q[off + v] = P[off + v] - a.lr * acc[u][v];
     }
   }
 }

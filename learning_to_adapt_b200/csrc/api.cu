@@ -71,6 +71,7 @@ struct l2a_ctx {
   float* adapt_acts = nullptr;
   float* adapt_grads = nullptr;
   size_t adapt_acts_cap = 0, adapt_grads_cap = 0;
+  int adapt_max_clusters16[2] = {-1, -1};   // cudaOccupancyMaxActiveClusters of adapt_fwd_bwd_kernel<16 / 32> at cluster size 16
 };
 
 struct l2a_model {
@@ -1583,17 +1584,52 @@ static int adapt_impl(l2a_ctx* c, l2a_model* m, const float* x, const float* tar
     if ((int)smem > c->max_smem_optin) return fail(L2A_ERR_UNSUPPORTED, "adapt needs %zu B shared memory (layer width %d)", smem, md.max_width);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(K * kAdaptCluster));
+    // 16 CTAs per task (non-portable cluster size: one cluster per GPC) while every task's cluster is resident at once; measured
+    // at K = 5, M = 16, 512^3: 134 -> 111 us for the three adapt kernels; K = 10 needs two waves of 16 and is faster with 8
+    aa.csize = kAdaptCluster;
+    if (K <= 8) {
+      // ... if the device can hold K clusters of 16 at once (asked once per context and context-row variant)
+      int& cached = c->adapt_max_clusters16[mr == 16 ? 0 : 1];
+      if (cached < 0) {
+        cudaLaunchConfig_t q;
+        memset(&q, 0, sizeof(q));
+        q.gridDim = dim3(8 * kAdaptClusterMax);
+        q.blockDim = dim3(kAdaptThreads);
+        q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = kAdaptClusterMax;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        q.attrs = qa;
+        q.numAttrs = 1;
+        int n = 0;
+        cudaError_t e1 = (mr == 16) ? cudaFuncSetAttribute(adapt_fwd_bwd_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                                    : cudaFuncSetAttribute(adapt_fwd_bwd_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e2 = (mr == 16) ? cudaFuncSetAttribute(adapt_fwd_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                    : cudaFuncSetAttribute(adapt_fwd_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e3 = (mr == 16) ? cudaOccupancyMaxActiveClusters(&n, adapt_fwd_bwd_kernel<16>, &q)
+                                    : cudaOccupancyMaxActiveClusters(&n, adapt_fwd_bwd_kernel<32>, &q);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cudaGetLastError(); n = 0; }
+        cached = n;
+      }
+      if (cached >= K) aa.csize = kAdaptClusterMax;
+    }
+    cfg.gridDim = dim3((unsigned)(K * aa.csize));
     cfg.blockDim = dim3(kAdaptThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kAdaptCluster;
+    attr[0].val.clusterDim.x = (unsigned)aa.csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (aa.csize > 8) {
+      CUDA_TRY(cudaFuncSetAttribute(adapt_fwd_bwd_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      CUDA_TRY(cudaFuncSetAttribute(adapt_fwd_bwd_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     if (mr == 16) {
       CUDA_TRY(cudaFuncSetAttribute(adapt_fwd_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CUDA_TRY(cudaLaunchKernelEx(&cfg, adapt_fwd_bwd_kernel<16>, aa));
@@ -1603,9 +1639,10 @@ static int adapt_impl(l2a_ctx* c, l2a_model* m, const float* x, const float* tar
     }
     c->launches++;
   }
-  int max_elems = 0;
-  for (int l = 0; l < md.n_layers; ++l) max_elems = std::max(max_elems, md.dims[l] * md.dims[l + 1] + md.dims[l + 1]);
-  dim3 grid((max_elems + 256 * 4 - 1) / (256 * 4), md.n_layers, K);
+  int max_tiles = 0;
+  for (int l = 0; l < md.n_layers; ++l)
+    max_tiles = std::max(max_tiles, ((md.dims[l + 1] + kUpdTJ - 1) / kUpdTJ) * ((md.dims[l] + kUpdTI - 1) / kUpdTI + 1));
+  dim3 grid((unsigned)max_tiles, md.n_layers, K);
   adapt_update_kernel<<<grid, 256, 0, st>>>(aa);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
