@@ -30,6 +30,35 @@ def param_keys(n_hidden):
     return keys + ["output/kernel", "output/bias"]
 
 
+_NUMPY_MT = None
+
+
+def numpy_mt19937_state():
+    """Direct access to numpy's GLOBAL legacy generator state (the stream np.random.uniform / normal draw from): returns
+    (bit_generator, address of its `mt19937_state` struct {uint32 key[624]; int pos;}) or None when the layout cannot be confirmed.
+
+    np.random.get_state() + set_state() cost ~150 us per planning call (tuple building, validation, a 624-word copy each way) --
+    more than the device spends regenerating the stream.  The bit generator's ctypes interface exposes the struct's address
+    (numpy/random/src/mt19937/mt19937.h); the host-buffer planning call reads the key / position from there and writes the advanced
+    state back in place, under the generator's own lock.  The layout is checked once against get_state()."""
+    global _NUMPY_MT
+    if _NUMPY_MT is None:
+        _NUMPY_MT = False
+        try:
+            bg = np.random.mtrand._rand._bit_generator
+            addr = bg.ctypes.state_address
+            addr = int(addr.value if hasattr(addr, "value") else addr)
+            with bg.lock:
+                key = np.ctypeslib.as_array((C.c_uint32 * 624).from_address(addr))
+                pos = C.c_int32.from_address(addr + 624 * 4)
+                st = np.random.get_state()
+                if st[0] == "MT19937" and np.array_equal(key, st[1]) and int(pos.value) == int(st[2]):
+                    _NUMPY_MT = (bg, addr)
+        except Exception:
+            _NUMPY_MT = False
+    return _NUMPY_MT or None
+
+
 class PlanningEngine(object):
     """One (process, device) planning context + one dynamics model with `n_sets` resident weight sets."""
 
@@ -248,14 +277,24 @@ class PlanningEngine(object):
                 plan["window"] = window                    # keeps it alive
             self._plans[key] = plan
         plan["io"].flags = int(flags) if window is not None else 0
-        if sampler == "mt19937":
-            st = np.random.get_state()
-            assert st[0] == "MT19937"
-            plan["key"][:] = st[1]
-            plan["pos"].value = int(st[2])
-        N.check(self.lib.l2a_plan_run_ex(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p), C.byref(plan["io"]), _stream()))
-        if sampler == "mt19937":
-            np.random.set_state(("MT19937", plan["key"], int(plan["pos"].value), st[3], st[4]))
+        io = plan["io"]
+        fast = numpy_mt19937_state() if sampler == "mt19937" else None
+        if fast is not None:
+            # uniform draws touch only (key, pos): the call reads and advances numpy's own state struct in place
+            bg, addr = fast
+            io.mt_key, io.mt_pos = addr, addr + 624 * 4
+            with bg.lock:
+                N.check(self.lib.l2a_plan_run_ex(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p), C.byref(io), _stream()))
+        else:
+            if sampler == "mt19937":
+                st = np.random.get_state()
+                assert st[0] == "MT19937"
+                plan["key"][:] = st[1]
+                plan["pos"].value = int(st[2])
+                io.mt_key, io.mt_pos = plan["key"].ctypes.data, C.addressof(plan["pos"])
+            N.check(self.lib.l2a_plan_run_ex(self._ctx, plan["handle"], obs.ctypes.data_as(C.c_void_p), C.byref(io), _stream()))
+            if sampler == "mt19937":
+                np.random.set_state(("MT19937", plan["key"], int(plan["pos"].value), st[3], st[4]))
         self._last_plan = plan
         return plan["act"].copy(), plan["ret"].copy(), plan["idx"].copy()
 

@@ -75,3 +75,30 @@ def test_executor_auto_reset():
             assert all(np.abs(o).max() < 1.0 for o in obs) and (ex.ts == 0).all()
     with pytest.raises(AssertionError):
         ex.step([np.zeros(6)] * 2)
+
+
+def test_numpy_global_mt19937_state_is_reachable_in_place():
+    """The default sampler hands numpy's OWN generator state struct to the planning call (engine.numpy_mt19937_state): the address
+    must be the {uint32 key[624]; int pos;} that np.random.get_state() reports, stay the same object across seeding / drawing,
+    and a state written through it must be what np.random draws from next (that is how the advanced state comes back)."""
+    import ctypes as C
+    import numpy as np
+    from learning_to_adapt_b200.engine import numpy_mt19937_state
+    fast = numpy_mt19937_state()
+    assert fast is not None, "numpy's bit generator no longer exposes the mt19937 state layout this relies on"
+    bg, addr = fast
+    key = np.ctypeslib.as_array((C.c_uint32 * 624).from_address(addr))
+    pos = C.c_int32.from_address(addr + 624 * 4)
+    for seed, burn in ((0, 0), (5, 3), (123, 1000)):
+        np.random.seed(seed)
+        np.random.uniform(size=burn)
+        st = np.random.get_state()
+        assert np.array_equal(key, st[1]) and pos.value == st[2]
+    other = np.random.RandomState(77)
+    other.uniform(size=555)
+    s2 = other.get_state()
+    with bg.lock:
+        key[:] = s2[1]
+        pos.value = int(s2[2])
+    np.testing.assert_array_equal(np.random.uniform(-1, 1, size=(40, 6)), other.uniform(-1, 1, size=(40, 6)))
+    assert np.random.get_state()[2] == other.get_state()[2]
