@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
   using S = Tc2Smem<NC>;
   constexpr int kChunkBytes = S::kChunkBytes;
   constexpr int kStages = S::kStages;
+  // W_hi / W_lo halves of a stage with their own barriers and producer threads only where the ring is 2 deep (NC >= 72): a deeper
+  // ring already covers the refill latency, and one handshake per stage instead of two is worth ~100 cycles per stage there
+  constexpr bool kSplit = (kStages == 2);
   constexpr int N2 = 2 * NC;                               // MMA N = candidates of the pair
   constexpr uint32_t kIdesc = umma::make_idesc_bf16(256, N2);
   static_assert(N2 % 16 == 0 && N2 <= 256 && 3 * N2 <= 512, "UMMA N constraint (M = 256) / three accumulator slots in 512 TMEM columns");
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
         lf_phase ^= 1u;
         slot_a = (slot_a + 2) % 3;
       }
-    } else if (warp == 10 && lane == 0) {
+    } else if (kSplit && warp == 10 && lane == 0) {
       // W_lo halves of every stage (both CTAs stream their own rows; the bytes complete on the leader's barrier)
       const uint32_t full_leader = umma::map_to_cta(umma::smem_u32(&full_lo[0]), 0);
       int stage = 0;
@@ -454,9 +457,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
       for (int t = 0; t < H; ++t) {
         for (int st = 0; st < plan.stages_per_set; ++st) {
           umma::mbar_wait(&empty_hi[stage], phase ^ 1u);
-          if (rank == 0) umma::mbar_arrive_expect_tx(&full_hi[stage], 2u * kTcTileBytes);
+          if (rank == 0) umma::mbar_arrive_expect_tx(&full_hi[stage], (kSplit ? 2u : 4u) * kTcTileBytes);
           const int row = ((set * plan.stages_per_set + st) * 2 + (int)rank) * 256;
           umma::tma2_load_2d(stages + (size_t)stage * kTc2StageBytes, &wmap, 0, row, full_leader + (uint32_t)stage * 8u);
+          if (!kSplit)
+            umma::tma2_load_2d(stages + (size_t)stage * kTc2StageBytes + kTcTileBytes, &wmap, 0, row + 128, full_leader + (uint32_t)stage * 8u);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -485,6 +490,29 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         umma::mbar_wait(&full_hi[stage], phase);
         umma::tc_fence_after();
+        if constexpr (!kSplit) {
+          // whole stage behind one barrier: per k-step W_hi * x_hi (keep), W_hi * x_lo (reuse), W_lo * x_hi; one release
+          if (umma::elect_one()) {
+            if (nks == 4) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma::mma2_bf16_ss_ab<umma::kAKeep>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, (first && ks == 0) ? 0u : 1u);
+                umma::mma2_bf16_ss_ab<umma::kAReuse>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bl + kb * ks, b_hi32, idesc, 1u);
+                umma::mma2_bf16_ss_ab<umma::kANone>(d_tmem, a_lo + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, 1u);
+              }
+            } else {
+              for (int ks = 0; ks < nks; ++ks) {
+                umma::mma2_bf16_ss_ab<umma::kAKeep>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, (first && ks == 0) ? 0u : 1u);
+                umma::mma2_bf16_ss_ab<umma::kAReuse>(d_tmem, a_hi + 2 * ks, umma::kDescHi32, bl + kb * ks, b_hi32, idesc, 1u);
+                umma::mma2_bf16_ss_ab<umma::kANone>(d_tmem, a_lo + 2 * ks, umma::kDescHi32, bh + kb * ks, b_hi32, idesc, 1u);
+              }
+            }
+            umma::mma2_commit_both(&empty_hi[stage]);
+          }
+          __syncwarp();
+          advance();
+          return;
+        }
         if (umma::elect_one()) {
           if (nks == 4) {
 #pragma unroll
@@ -520,7 +548,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
         const uint32_t a_hi = st_lo32 + (uint32_t)stage * kStageStep, a_lo = a_hi + kLoStep;
         const uint32_t xh = hi_lo32 + (uint32_t)kTc2XChunk * kChunkStep, xl = lo_lo32 + (uint32_t)kTc2XChunk * kChunkStep;
         umma::mbar_wait(&full_hi[stage], phase);
-        umma::mbar_wait(&full_lo[stage], phase);
+        if (kSplit) umma::mbar_wait(&full_lo[stage], phase);
         umma::tc_fence_after();
         if (umma::elect_one()) {
 #pragma unroll
@@ -534,7 +562,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
             }
           }
           umma::mma2_commit_both(&empty_hi[stage]);
-          umma::mma2_commit_both(&empty_lo[stage]);
+          if (kSplit) umma::mma2_commit_both(&empty_lo[stage]);
         }
         __syncwarp();
         advance();
@@ -610,7 +638,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
             for (int kc = 4 * ev; kc < kc_end; ++kc) {
               if (j == 0) {
                 umma::mbar_wait(&full_hi[stage], phase);
-                umma::mbar_wait(&full_lo[stage], phase);
+                if (kSplit) umma::mbar_wait(&full_lo[stage], phase);
                 umma::tc_fence_after();
               }
               const uint32_t xh = hi_mn32 + (uint32_t)kc * kChunkStep, xl = lo_mn32 + (uint32_t)kc * kChunkStep;
@@ -625,7 +653,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
                 }
                 if (last_in_stage) {
                   umma::mma2_commit_both(&empty_hi[stage]);
-                  umma::mma2_commit_both(&empty_lo[stage]);
+                  if (kSplit) umma::mma2_commit_both(&empty_lo[stage]);
                 }
               }
               __syncwarp();
