@@ -13,8 +13,10 @@
 // layer's B operand of the peer's candidates lives in the peer's shared memory.  The hidden activations are therefore kept
 // MN-MAJOR (candidates contiguous, unswizzled 8x8 core matrices): an epilogue thread owns one output feature (its TMEM lane),
 // holds 8 consecutive candidates per 32x32b TMEM load and writes them as ONE 16-byte store, into its own CTA's buffer or, for
-// the peer's candidates, into the peer's with st.shared::cluster (DSMEM) -- no transposition, no staging.  Readiness is counted
-// on the LEADER's mbarriers (remote arrives with release.cluster from the peer), because only the leader CTA issues MMAs.
+// the peer's candidates, into the peer's with st.async (DSMEM, the bytes counted on the peer's `in_ready` mbarrier) -- no
+// transposition, no staging, no fence on the sending side.  A warp reports to the LEADER's mbarriers (only the leader CTA issues
+// MMAs) once its own rows are in place and its CTA's incoming bytes have landed; the peer's arrivals are relaxed remote arrives:
+// no cluster-scope release (MEMBAR.ALL.GPU, 1.2-1.8 k cycles on B200) anywhere on the layer-to-layer path.
 // (First version: K-major activations transposed through a per-warp stmatrix bounce buffer: 5.5 k cycles per M-block epilogue.)
 // The output layer keeps the swapped roles of rollout_tc.cuh (M = candidates: each CTA's own 128 activation rows are its half
 // of A; the [out_n x 64] weight tiles are B, split by N between the CTAs: x_hi * [W_hi ; W_lo] has W_hi in the leader and
@@ -47,6 +49,12 @@ namespace l2a {
 // exchange 27 k cycles per step instead of 7 k (profiles/r02_negative_results.md); kept for the record, parity-green.
 #ifndef L2A_TC2_LL
 #define L2A_TC2_LL 0
+#endif
+// epilogue all-to-all: 1 (default) = st.async into the peer with the bytes counted on the peer's `in_ready` mbarrier (no fence on the
+// sending side; every warp waits for its own CTA's incoming bytes, then arrives on the leader WITHOUT a cluster-scope release);
+// 0 = plain st.shared::cluster + one mbarrier.arrive.release.cluster per warp (MEMBAR.ALL.GPU: 1.2-1.8 k cycles per M-block)
+#ifndef L2A_TC2_STASYNC
+#define L2A_TC2_STASYNC 1
 #endif
 #ifndef L2A_TC2_WGS
 #define L2A_TC2_WGS 3
@@ -270,8 +278,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
   uint64_t* layer_full = bars + 4 * kTc2MaxStages; // both CTAs
   uint64_t* early = layer_full + 1;                // both CTAs: M-block 0 of a hidden layer may be drained
   uint64_t* act_ready = layer_full + 2;            // [2] leader only: 512 arrivals (256 epilogue / helper threads of each CTA)
-  uint64_t* x_ready = layer_full + 4;              // leader only: 256 arrivals (the env-step threads of both CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 5);
+  uint64_t* x_ready = layer_full + 4;              // leader only: one arrival per env-step warp of both CTAs
+  uint64_t* in_ready = layer_full + 5;             // [2] both CTAs: the peer's st.async bytes of M-block mb have landed here (tx count)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_full + 7);
   float* red_v = reinterpret_cast<float*>(tmem_slot + 2);
   int* red_i = reinterpret_cast<int*>(red_v + 4);
   int* s_flag = red_i + 4;
@@ -303,6 +312,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
     umma::mbar_init(&act_ready[0], 8 * kTc2Parts);   // one arrival per epilogue / helper warp of both CTAs
     umma::mbar_init(&act_ready[1], 8 * kTc2Parts);
     umma::mbar_init(x_ready, 8);                 // one arrival per env-step warp of both CTAs
+    umma::mbar_init(&in_ready[0], 1);            // one expect_tx arrival per use + the peer's bytes
+    umma::mbar_init(&in_ready[1], 1);
     umma::fence_barrier_init();
   }
   for (int i = tid; i < DMAX; i += kTc2Threads) {
@@ -341,7 +352,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
   // CTA's own groups and the (kTc2Parts-1-p)-th share of the peer's, so every warp mixes local and DSMEM stores.
   constexpr int kSlabBytes = NC * 16;                       // 8 features x NC candidates x 2 B
   constexpr int kGr = NC / 8;                               // 8-candidate groups per CTA
-  auto hidden_epilogue = [&](auto part_tag, int t, int l, int slot_a, int wq, bool stamps, uint32_t& lf_phase, uint32_t& early_phase) {
+  auto hidden_epilogue = [&](auto part_tag, int t, int l, int slot_a, int wq, bool stamps, uint32_t& lf_phase, uint32_t& early_phase, uint32_t& in_phase) {
     constexpr int PART = decltype(part_tag)::value, RPART = kTc2Parts - 1 - PART;
     const uint32_t act_hi_addr = umma::smem_u32(act_hi), act_lo_addr = umma::smem_u32(act_lo);
     const uint32_t peer_hi = umma::map_to_cta(act_hi_addr, rank ^ 1u), peer_lo = umma::map_to_cta(act_lo_addr, rank ^ 1u);
@@ -355,6 +366,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
       const float bias = __ldg(P + md.b_off[l] + gfeat);
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * N2);
       const uint32_t row_off = (uint32_t)(gfeat >> 3) * (uint32_t)kSlabBytes + (uint32_t)(gfeat & 7) * 16u;
+      const uint32_t peer_in = umma::map_to_cta(umma::smem_u32(&in_ready[mb]), rank ^ 1u);
+      if (L2A_TC2_STASYNC && PART == 0 && wq == 0 && lane == 0)       // this CTA expects the peer's half of the M-block: 128 features x NC candidates x (hi, lo)
+        umma::mbar_arrive_expect_tx(&in_ready[mb], (uint32_t)(NC * 512));
       auto drain = [&](auto g0_tag, auto g1_tag) {
         constexpr int G0 = decltype(g0_tag)::value, G1 = decltype(g1_tag)::value, CNT = G1 - G0;
         if constexpr (CNT > 0) {
@@ -383,6 +397,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
             if (owner == rank || L2A_TC2_EXPERIMENT == 1) {
               umma::st_shared_v4(act_hi_addr + off, uh);
               umma::st_shared_v4(act_lo_addr + off, ul);
+            } else if (L2A_TC2_STASYNC) {
+              umma::st_async_cluster_v4(peer_hi + off, uh, peer_in);
+              umma::st_async_cluster_v4(peer_lo + off, ul, peer_in);
             } else {
               umma::st_cluster_v4(peer_hi + off, uh);
               umma::st_cluster_v4(peer_lo + off, ul);
@@ -395,24 +412,34 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
       L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[104] = clock64());
       drain(IntTag<(PART * kGr) / kTc2Parts>{}, IntTag<((PART + 1) * kGr) / kTc2Parts>{});
       L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[101] = clock64());
-      // every lane: its rows in this CTA's shared memory -> async proxy (CTA-scope proxy fence); then ONE cluster-scope release per
-      // warp (cumulative over the warp through __syncwarp; SASS: MEMBAR.ALL.GPU, i.e. the rows stored into the peer's shared memory
-      // have been performed there) before the arrival on the leader's barrier.  fence.proxy.async.shared::cluster by every lane
-      // instead (a second MEMBAR.ALL.GPU per lane in front of the same SM-local FENCE.VIEW.ASYNC.S) costs 2 k cycles per horizon
-      // step (0.655 vs 0.610 ms at the headline shape) and changes no result.
+      // every lane: its rows in this CTA's own shared memory -> async proxy (CTA-scope proxy fence).  The rows sent to the peer are
+      // st.async stores counted on the peer's in_ready barrier (L2A_TC2_STASYNC); the earlier version used plain st.shared::cluster
+      // and ONE cluster-scope release per warp in front of the arrival (SASS: MEMBAR.ALL.GPU, 1.2-1.8 k cycles per M-block on the
+      // critical path of the next layer: headline 0.596 vs 0.573 ms, cfg1 0.118 vs 0.110 ms).
       if (L2A_TC2_EXPERIMENT == 3) umma::fence_proxy_async_cluster(); else umma::fence_proxy_async_smem();
       umma::tc_fence_before();
       __syncwarp();
       L2A_TIMELINE(if (stamps && l == 1 && mb == 0 && a.timeline && blockIdx.x == 0 && t == 1 && lane == 0) a.timeline[105] = clock64());
+#if L2A_TC2_STASYNC
+      // this warp's rows are in place in its own CTA (proxy fence above) and on their way into the peer (counted there); once the
+      // peer's rows have landed HERE the warp reports to the leader -- no cluster-scope release anywhere on this path
+      umma::mbar_wait_cluster(&in_ready[mb], (in_phase >> mb) & 1u);
+      if (lane == 0) {
+        if (rank == 0) umma::mbar_arrive(&act_ready[mb]);
+        else umma::mbar_arrive_remote_relaxed(act_ready_leader + (uint32_t)mb * 8u);
+      }
+#else
       if (lane == 0) {
         if (rank == 0) umma::mbar_arrive_release_cluster(&act_ready[mb]);
         else umma::mbar_arrive_remote(act_ready_leader + (uint32_t)mb * 8u);
       }
+#endif
       if (stamps) L2A_STAMP(32 + 4 * l + (mb == 0 ? 1 : 2));
     }
     if (plan.nmb[l] == 1) umma::mbar_wait(layer_full, lf_phase);        // keeps the layer_full phase in step
     early_phase ^= 1u;
     lf_phase ^= 1u;
+    in_phase ^= (plan.nmb[l] == 1) ? 1u : 3u;
   };
 
   if (warp >= 6) {
@@ -420,12 +447,12 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
     L2A_TC2_DEC_REGS();
     if (warp < 10 || warp >= 12) {
       const int wq = warp & 3;
-      uint32_t lf_phase = 0, early_phase = 0;
+      uint32_t lf_phase = 0, early_phase = 0, in_phase = 0;
       int slot_a = 0;
       for (int t = 0; t < H; ++t) {
         for (int l = 0; l + 1 < L; ++l) {
-          if (kTc2Parts == 3 && warp >= 12) hidden_epilogue(IntTag<kTc2Parts - 1>{}, t, l, slot_a, wq, false, lf_phase, early_phase);
-          else hidden_epilogue(IntTag<1>{}, t, l, slot_a, wq, false, lf_phase, early_phase);
+          if (kTc2Parts == 3 && warp >= 12) hidden_epilogue(IntTag<kTc2Parts - 1>{}, t, l, slot_a, wq, false, lf_phase, early_phase, in_phase);
+          else hidden_epilogue(IntTag<1>{}, t, l, slot_a, wq, false, lf_phase, early_phase, in_phase);
           slot_a = (slot_a + 2) % 3;
         }
         umma::mbar_wait(layer_full, lf_phase);                           // the output layer's completion
@@ -674,7 +701,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
     const bool valid = n < nvalid;
     const long long row = (long long)env * a.n_candidates + c0 + (valid ? n : 0);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    uint32_t lf_phase = 0, early_phase = 0;
+    uint32_t lf_phase = 0, early_phase = 0, in_phase = 0;
     int slot_a = 0;
     float ret = 0.f, asq = 0.f;
     constexpr int AMAX = (DMAX <= 24) ? 8 : kTcMaxAct;
@@ -746,7 +773,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
       __syncwarp();
       if (lane == 0) {
         if (rank == 0) umma::mbar_arrive(x_ready);
-        else umma::mbar_arrive_remote(x_ready_leader);
+        else umma::mbar_arrive_remote_relaxed(x_ready_leader);     // own shared memory only, performed by the CTA-scope proxy fence above
       }
     };
 
@@ -756,7 +783,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
     for (int t = 0; t < H; ++t) {
       const float disc_t = __ldg(a.discount_pow + t);
       for (int l = 0; l + 1 < L; ++l) {
-        hidden_epilogue(IntTag<0>{}, t, l, slot_a, warp, warp == 0, lf_phase, early_phase);
+        hidden_epilogue(IntTag<0>{}, t, l, slot_a, warp, warp == 0, lf_phase, early_phase, in_phase);
         slot_a = (slot_a + 2) % 3;
       }
       if (t + 1 < H) load_actions(t + 1);

@@ -79,6 +79,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive WITHOUT a cluster-scope release (no MEMBAR.ALL.GPU, ~1.5 k cycles on B200): for arrivals that only certify
+// writes to the arriving CTA's OWN shared memory, which a preceding fence.proxy.async.shared::cta (MEMBAR.ALL.CTA +
+// FENCE.VIEW.ASYNC.S) has already performed -- shared memory has one copy, so CTA-scope performed is performed for the peer's
+// tensor-core reads too -- or data whose arrival is tracked by an mbarrier transaction count.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -372,6 +379,13 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const void* tmap, i
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// Asynchronous 16-byte store into a cluster peer's shared memory whose completion is counted (16 bytes of complete_tx) on an
+// mbarrier of the SAME peer CTA: the sender needs no fence, the receiver sees the data once the barrier's phase completes.
+__device__ __forceinline__ void st_async_cluster_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+               : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t smem_addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
