@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
   umma::tc_fence_after();
   const uint32_t tmem_base = umma::ld_dsmem_u32(umma::map_to_cta(umma::smem_u32(tmem_slot), 0));   // the pair's allocation (leader's slot)
 
+  // (Waits on barriers the peer arrives on use the plain CTA-scope try_wait: everything they order lives in shared memory;
+  // the .acquire.cluster form adds a CCTL.IVALL -- an L1 invalidation -- to every successful wait of the MMA issuer.)
   // leader-side addresses of the barriers the peer arrives on
   const uint32_t act_ready_leader = umma::map_to_cta(umma::smem_u32(&act_ready[0]), 0);
   const uint32_t x_ready_leader = umma::map_to_cta(umma::smem_u32(x_ready), 0);
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
 #if L2A_TC2_STASYNC
       // this warp's rows are in place in its own CTA (proxy fence above) and on their way into the peer (counted there); once the
       // peer's rows have landed HERE the warp reports to the leader -- no cluster-scope release anywhere on this path
-      umma::mbar_wait_cluster(&in_ready[mb], (in_phase >> mb) & 1u);
+      umma::mbar_wait(&in_ready[mb], (in_phase >> mb) & 1u);
       if (lane == 0) {
         if (rank == 0) umma::mbar_arrive(&act_ready[mb]);
         else umma::mbar_arrive_remote_relaxed(act_ready_leader + (uint32_t)mb * 8u);
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
           L2A_STAMP(4 * l + 0);
           L2A_TIMELINE(if (a.timeline && blockIdx.x == 0 && t == 2 && l == 0 && lane == 0) a.timeline[80] = clock64());
           if (l == 0) {
-            umma::mbar_wait_cluster(x_ready, xr_phase);
+            umma::mbar_wait(x_ready, xr_phase);
             xr_phase ^= 1u;
             umma::tc_fence_after();
             L2A_STAMP(4 * l + 3);
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
             // M-block 0 may be drained once its own accumulation is complete AND nothing reads chunks 0-3 any more (its epilogue
             // overwrites them in place): after its part of the last event when there are two events, else with the whole layer.
             for (int ev = 0; ev < nsrc; ++ev) {
-              umma::mbar_wait_cluster(&act_ready[ev], (act_phase >> ev) & 1u);
+              umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
               act_phase ^= (1u << ev);
               umma::tc_fence_after();
               if (ev == 0) L2A_STAMP(4 * l + 3);
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
           int j = 0;
           L2A_STAMP(4 * l + 0);
           for (int ev = 0; ev < nsrc; ++ev) {
-            umma::mbar_wait_cluster(&act_ready[ev], (act_phase >> ev) & 1u);
+            umma::mbar_wait(&act_ready[ev], (act_phase >> ev) & 1u);
             act_phase ^= (1u << ev);
             umma::tc_fence_after();
             if (ev == 0) L2A_STAMP(4 * l + 3);
