@@ -56,6 +56,10 @@ namespace l2a {
 #ifndef L2A_TC2_STASYNC
 #define L2A_TC2_STASYNC 1
 #endif
+// hidden epilogue arithmetic with the packed fp32x2 adder (1) or scalar adds (0); results are bit-identical
+#ifndef L2A_TC2_FADD2
+#define L2A_TC2_FADD2 1
+#endif
 #ifndef L2A_TC2_WGS
 #define L2A_TC2_WGS 3
 #endif
@@ -387,9 +391,13 @@ __global__ void __launch_bounds__(kTc2Threads, 1) rollout_tc2_kernel(const Tc2Ar
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
+#if L2A_TC2_FADD2
+                umma::bias_relu_split_bf16x2(r[i][2 * q], r[i][2 * q + 1], bias, hi[q], lo[q]);  // core/utils.py:119-126 (ReLU dense)
+#else
                 const float v0 = fmaxf(__uint_as_float(r[i][2 * q]) + bias, 0.f);          // core/utils.py:119-126 (ReLU dense)
                 const float v1 = fmaxf(__uint_as_float(r[i][2 * q + 1]) + bias, 0.f);
                 umma::split_bf16x2(v0, v1, hi[q], lo[q]);
+#endif
               }
               uh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               ul = make_uint4(lo[0], lo[1], lo[2], lo[3]);

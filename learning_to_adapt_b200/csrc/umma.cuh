@@ -197,6 +197,23 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, u
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h1), "f"(v0 - h0));
 }
+// Same split for the pair (a0 + b, a1 + b) after ReLU, with the packed fp32x2 adder (FADD2) for the bias add and the residual
+// subtraction: 8 instead of 10 instructions per two elements, bit-identical results (IEEE adds either way).
+__device__ __forceinline__ void bias_relu_split_bf16x2(uint32_t a0, uint32_t a1, float bias, uint32_t& hi, uint32_t& lo) {
+  uint64_t v, b2, h2, d;
+  uint32_t v0, v1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(bias));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(v), "l"(b2));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(v0), "=r"(v1) : "l"(v));
+  const float r0 = fmaxf(__uint_as_float(v0), 0.f), r1 = fmaxf(__uint_as_float(v1), 0.f);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(r1), "f"(r0));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(r0), "f"(r1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(h2) : "r"(hi << 16), "r"(hi & 0xffff0000u));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(v), "l"(h2));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(v0), "=r"(v1) : "l"(d));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(__uint_as_float(v1)), "f"(__uint_as_float(v0)));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
