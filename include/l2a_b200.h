@@ -340,6 +340,11 @@ int l2a_shard_select(l2a_ctx* ctx, const float* gathered, int G, int m, int A, f
  * hidden_pairs (32 KB ring stages of the hidden layers), out_n (MMA N of the output layer), out_kcs (K chunks per output
  * stage), out_stages, stages_per_set, set_bytes (low and high 32 bits).  Used by the CPU-side tests of the host logic. */
 int l2a_tc_plan_query(const l2a_mlp_desc* desc, int32_t* out8);
+/* Same for the CTA-pair kernel (tcgen05.mma.cta_group::2; hidden widths multiples of 256 and <= 512): out12[0] = 1 if supported, then
+ * hidden_stages (64 KB ring stages = 2 x 32 KB, one half per CTA), l0_packed, out_n, out_kcs, out_stages, stages_per_set, set_bytes
+ * (low, high 32 bits); and the launch geometry the tile choice gives `n_candidates` x `n_envs` with `n_members` ensemble members on
+ * a device with `num_sms` SMs: out12[9] = candidates per CTA, out12[10] = candidate tiles per env, out12[11] = CTAs. */
+int l2a_tc2_plan_query(const l2a_mlp_desc* desc, int32_t n_candidates, int32_t n_envs, int32_t n_members, int32_t num_sms, int32_t* out12);
 
 /* Diagnostics and microbenchmarks: only in the DEBUG build of the library (-DL2A_DEBUG_KERNELS -> lib/libl2a_b200_debug.so,
  * `python -m learning_to_adapt_b200.build --debug`); the product library does not contain them. */

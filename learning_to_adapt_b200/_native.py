@@ -20,7 +20,7 @@ EXPORTS = [
     "l2a_window_create", "l2a_window_destroy", "l2a_window_set_normalization", "l2a_window_push", "l2a_window_reset",
     "l2a_window_length", "l2a_window_gather", "l2a_adapt_from_window", "l2a_plan_attach_window",
     "l2a_plan_create", "l2a_plan_run", "l2a_plan_destroy", "l2a_plan_create_ex", "l2a_plan_run_ex", "l2a_plan_exchange_buffer",
-    "l2a_plan_attach_peers", "l2a_plan_exchange_resident", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_plan_copy_returns", "l2a_plan_io_bytes", "l2a_sample_uniform", "l2a_tc_plan_query",
+    "l2a_plan_attach_peers", "l2a_plan_exchange_resident", "l2a_ipc_get_handle", "l2a_ipc_open_handle", "l2a_ipc_close_handle", "l2a_plan_uses_graph", "l2a_plan_copy_candidates", "l2a_plan_copy_returns", "l2a_plan_io_bytes", "l2a_sample_uniform", "l2a_tc_plan_query", "l2a_tc2_plan_query",
 ]
 
 
@@ -105,6 +105,7 @@ def load(debug=False):
     lib.l2a_plan_copy_returns.argtypes = [vp, vp, vp]
     lib.l2a_plan_io_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.l2a_tc_plan_query.argtypes = [C.POINTER(MlpDesc), vp]
+    lib.l2a_tc2_plan_query.argtypes = [C.POINTER(MlpDesc), i32, i32, i32, i32, vp]
     lib.l2a_sample_uniform.argtypes = [vp, vp, vp, vp, i64, i32, C.c_uint64, C.c_uint64, vp]
     lib.l2a_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
     lib.l2a_adapt.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]

@@ -212,6 +212,30 @@ static bool encode_weight_map(CUtensorMap* map, void* base, size_t bytes) {
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int pick_nc2(int num_sms, int n_cand, int n_envs, int csize);
+
+extern "C" int l2a_tc2_plan_query(const l2a_mlp_desc* d, int32_t n_candidates, int32_t n_envs, int32_t n_members, int32_t num_sms, int32_t* out12) {
+  if (!d || !out12) return fail(L2A_ERR_INVALID, "NULL argument");
+  if (d->n_hidden < 1 || d->n_hidden > kMaxLayers - 1) return fail(L2A_ERR_INVALID, "n_hidden %d not in [1,%d]", d->n_hidden, kMaxLayers - 1);
+  for (int i = 0; i < d->n_hidden; ++i)
+    if (d->hidden[i] < 1) return fail(L2A_ERR_INVALID, "hidden[%d] = %d", i, d->hidden[i]);
+  if (d->obs_dim < 3 || d->act_dim < 1 || n_candidates < 1 || n_envs < 1 || n_members < 1 || num_sms < 2) return fail(L2A_ERR_INVALID, "bad argument");
+  MlpDims md;
+  fill_dims(d, &md);
+  Tc2Plan plan;
+  const bool ok = tc2_make_plan(md, &plan) && n_members <= 8;
+  memset(out12, 0, 12 * sizeof(int32_t));
+  out12[0] = ok ? 1 : 0;
+  if (ok) {
+    out12[1] = plan.hidden_stages; out12[2] = plan.l0_packed; out12[3] = plan.out_n; out12[4] = plan.out_kcs; out12[5] = plan.out_stages;
+    out12[6] = plan.stages_per_set; out12[7] = (int32_t)(plan.set_bytes & 0xFFFFFFFFll); out12[8] = (int32_t)(plan.set_bytes >> 32);
+    const int nc = pick_nc2(num_sms, n_candidates, n_envs, n_members);
+    const int groups = (n_candidates + 2 * nc - 1) / (2 * nc);
+    out12[9] = nc; out12[10] = groups; out12[11] = n_envs * groups * n_members * 2;
+  }
+  return L2A_OK;
+}
+
 // --------------------------------------------------------------------------------------------- model
 extern "C" int l2a_model_create(l2a_ctx* c, const l2a_mlp_desc* d, l2a_model** out) {
   if (!c || !d || !out) return fail(L2A_ERR_INVALID, "NULL argument");
@@ -452,7 +476,7 @@ static int launch_tc2(l2a_ctx* c, const l2a_model* m, const Tc2Args& ta, int csi
 }
 
 // candidates per CTA of the pair kernel (a tile is 2 * nc candidates): fewest waves of CTA pairs, then the smaller tile
-static int pick_nc2(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
+static int pick_nc2(int num_sms, int n_cand, int n_envs, int csize) {
   static const int opts[4] = {80, 72, 48, 32};
   if (const char* ov = getenv("L2A_TC2_NC")) {                  // tuning / experiments only
     const int v = atoi(ov);
@@ -462,7 +486,7 @@ static int pick_nc2(const l2a_ctx* c, int n_cand, int n_envs, int csize) {
   double best_cost = 1e300;
   // candidate tiles resident at once: 1 CTA / SM, and the csize member pairs of a tile only make progress together (they
   // meet every horizon step), so a wave holds whole tiles
-  const int slots = std::max(1, (c->num_sms / 2) / csize);
+  const int slots = std::max(1, (num_sms / 2) / csize);
   for (int i = 0; i < 4; ++i) {
     const int nc = opts[i];
     const long long tiles = (long long)n_envs * ((n_cand + 2 * nc - 1) / (2 * nc));
@@ -575,7 +599,7 @@ extern "C" int l2a_rollout(l2a_ctx* c, l2a_model* m, const l2a_rollout_params* p
   }
 
   if (kernel == L2A_KERNEL_TCGEN05_PAIR) {
-    const int nc = pick_nc2(c, p->n_candidates, p->n_envs, csize);
+    const int nc = pick_nc2(c->num_sms, p->n_candidates, p->n_envs, csize);
     const int groups = (p->n_candidates + 2 * nc - 1) / (2 * nc);
     int rc = ensure_reduce_ws(c, (size_t)groups * 2 * p->n_envs, p->n_envs, st);
     if (rc) return rc;

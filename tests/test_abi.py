@@ -108,3 +108,40 @@ def test_tensor_core_tiling_of_the_baseline_shapes():
         assert st == 0 and p[0] == 0, shape
     st, _ = _plan(20, 6, ())
     assert st == -1
+
+
+def _plan2(obs_dim, act_dim, hidden, n, m, members, sms=148):
+    from learning_to_adapt_b200 import _native
+    lib = _native.load()
+    d = _native.MlpDesc()
+    d.obs_dim, d.act_dim, d.n_hidden, d.n_sets = obs_dim, act_dim, len(hidden), max(1, members)
+    for i, h in enumerate(hidden):
+        d.hidden[i] = h
+    out = (ctypes.c_int32 * 12)()
+    status = lib.l2a_tc2_plan_query(ctypes.byref(d), n, m, members, sms, out)
+    return status, list(out)
+
+
+def test_cta_pair_plan_and_tile_choice_of_the_baseline_configs():
+    """Host logic of the CTA-pair kernel (no GPU): ring stages per weight set (64 KB = one 32 KB half per CTA) and the tile choice --
+    fewest waves of WHOLE tiles (the members of a tile only progress together), then the smaller tile -- on a 148-SM device."""
+    # headline: packed layer 0 (1 stage) + 2 x 16 + 2 output stages (5 K chunks of 6 KB per stage); 14 tiles of 144 x 5 members = 140 CTAs
+    st, p = _plan2(20, 6, (512, 512, 512), 2000, 1, 5)
+    assert st == 0 and p[:7] == [1, 33, 1, 32, 5, 2, 35] and p[7] == 35 * 65536 and p[9:] == [72, 14, 140]
+    # cfg3 (Ant): unpacked layer 0 (2 stages), output N = 48 -> 9 KB per K chunk -> 3 per stage -> 3 stages
+    st, p = _plan2(41, 8, (512, 512, 512), 2000, 1, 5)
+    assert st == 0 and p[:7] == [1, 34, 0, 48, 3, 3, 37] and p[9:] == [72, 14, 140]
+    # cfg5's per-GPU share: 29 tiles of 144 would need three waves of 14 whole tiles, 26 tiles of 160 need two
+    st, p = _plan2(41, 8, (512, 512, 512), 4096, 1, 5)
+    assert st == 0 and p[9:] == [80, 26, 260]
+    # cfg1 / cfg2 / cfg4: no ensemble -> 74 pair slots; the smallest tile that still fits one wave
+    assert _plan2(20, 6, (512, 512), 500, 1, 1)[1][9:] == [32, 8, 16]
+    assert _plan2(20, 6, (512, 512, 512), 1000, 5, 1)[1][9:] == [48, 11, 110]
+    assert _plan2(20, 6, (512, 512), 5000, 1, 1)[1][9:] == [48, 53, 106]
+    assert _plan2(20, 6, (512, 512), 2000, 10, 1)[1][9:] == [72, 14, 280]
+    # a 256-wide layer is one M-block; 128-wide layers, > 8 members: no pair variant (the single-CTA / SIMT kernels serve them)
+    st, p = _plan2(20, 6, (256, 256), 300, 1, 1)
+    assert st == 0 and p[:7] == [1, 1 + 4, 0, 32, 5, 1, 6]
+    assert _plan2(20, 6, (128, 128), 300, 1, 1)[1][0] == 0
+    assert _plan2(20, 6, (512, 512), 300, 1, 9)[1][0] == 0
+    assert _plan2(20, 6, (), 300, 1, 1)[0] == -1
