@@ -7,6 +7,8 @@ Every test prints the error figures (`tests.helpers.error_report`: max-scaled AN
 to gpurun_out/parity_configs.jsonl when that directory exists.
 
 Tolerance: 1e-4 relative per element on returns (north_star), floor = batch median |return|.
+The rollouts run with kernel = AUTO, i.e. the product's default (the CTA-pair tcgen05 kernel at these 512-wide shapes); cfg1 also runs
+the single-CTA tcgen05 and the SIMT kernel, tests/test_gpu_parity.py and tests/test_gpu_pair.py cross-check the kernels with each other.
 """
 import json
 import os
@@ -32,7 +34,8 @@ def _record(tag, rep, **extra):
             f.write(json.dumps(row) + "\n")
 
 
-def _rollout(eng, prob, actions, n, h, discount, set_mode, first_set, n_sets, kernel=2):
+def _rollout(eng, prob, actions, n, h, discount, set_mode, first_set, n_sets, kernel=0):
+    """kernel 0 = AUTO: the product's default choice (the CTA-pair tcgen05 kernel at these shapes); 2 = single-CTA tcgen05, 1 = SIMT."""
     res = eng.rollout(dev(prob["obs0"]), dev(actions), n, h, prob["reward_kind"], prob["dt"], discount=discount,
                       set_mode=set_mode, first_set=first_set, n_sets=n_sets, kernel=kernel)
     torch.cuda.synchronize()
@@ -53,7 +56,7 @@ def test_cfg1_half_cheetah_rs_full():
     n, h = 500, 10
     actions = O.sample_rs_actions(21, prob["low"], prob["high"], h, n)
     want = O.rollout_returns(prob["obs0"], actions, prob["param_sets"], prob["norm"], prob["reward_kind"], prob["dt"], 1.0, "shared")
-    for kernel in (2, 1):
+    for kernel in (0, 2, 1):
         res = _rollout(eng, prob, actions, n, h, 1.0, 0, 0, 1, kernel)
         rep = assert_returns_close(res["returns"], want)
         assert_argmax_consistent(res["best_idx"], want)
