@@ -42,6 +42,8 @@ def numpy_mt19937_state():
     (numpy/random/src/mt19937/mt19937.h); the host-buffer planning call reads the key / position from there and writes the advanced
     state back in place, under the generator's own lock.  The layout is checked once against get_state()."""
     global _NUMPY_MT
+    if _NUMPY_MT and np.random.mtrand._rand._bit_generator is not _NUMPY_MT[0]:
+        _NUMPY_MT = None                  # np.random.set_bit_generator() replaced the global generator: look again
     if _NUMPY_MT is None:
         _NUMPY_MT = False
         try:
