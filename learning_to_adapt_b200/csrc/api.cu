@@ -766,6 +766,10 @@ struct l2a_plan {
   uint64_t calls = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr;
+  // CEM with numpy's normal stream: the generator chain (raw words -> polar attempts -> compaction -> state) of iteration i+1 runs on
+  // a second stream beside K1 of iteration i (it needs the generator state after iteration i's draw, not its returns)
+  cudaStream_t stream_mt = nullptr;
+  std::vector<cudaEvent_t> ev_mt;    // fork, then per iteration: normals ready, normals consumed; last: chain done
   uint8_t* in_host = nullptr;    // pinned input block (layout: in_* offsets)
   uint8_t* in_dev = nullptr;
   uint8_t* out_host = nullptr;   // pinned output block (layout: out_* offsets)
@@ -928,6 +932,8 @@ extern "C" int l2a_plan_destroy(l2a_ctx* c, l2a_plan* pl) {
   for (int f = 0; f < 4; ++f)
     if (pl->exec_flags[f]) cudaGraphExecDestroy(pl->exec_flags[f]);
   if (pl->ev_in) cudaEventDestroy(pl->ev_in);
+  for (cudaEvent_t ev : pl->ev_mt) cudaEventDestroy(ev);
+  if (pl->stream_mt) cudaStreamDestroy(pl->stream_mt);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   cudaFreeHost(pl->in_host);
   cudaFreeHost(pl->out_host);
@@ -1036,6 +1042,14 @@ extern "C" int l2a_plan_create_ex(l2a_ctx* c, l2a_model* m, const l2a_rollout_pa
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
+  if (e == cudaSuccess && opts->planner == L2A_PLANNER_CEM && opts->sampler == L2A_SAMPLER_MT19937 && getenv("L2A_CEM_SERIAL") == nullptr) {
+    e = cudaStreamCreateWithFlags(&pl->stream_mt, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 * opts->cem_iters + 2 && e == cudaSuccess; ++i) {
+      cudaEvent_t ev = nullptr;
+      e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e == cudaSuccess) pl->ev_mt.push_back(ev);
+    }
+  }
   if (e == cudaSuccess) e = cudaMallocHost(&pl->in_host, pl->in_bytes);
   if (e == cudaSuccess) e = cudaMallocHost(&pl->out_host, pl->out_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&pl->in_dev, pl->in_bytes);
@@ -1195,23 +1209,43 @@ static int plan_enqueue_cem(l2a_ctx* c, l2a_plan* pl) {
   const MtStateBlock* state_in = reinterpret_cast<const MtStateBlock*>(pl->in_dev + pl->in_key);
   MtStateBlock* scratch = reinterpret_cast<MtStateBlock*>(pl->mt_scratch);
   int32_t* meta_out = reinterpret_cast<int32_t*>(pl->out_dev + pl->out_meta);
+  // numpy's stream: generator chain on its own stream (see l2a_plan), forked behind the H2D copy of the uploaded state
+  const bool fork = mt && pl->stream_mt != nullptr;
+  cudaStream_t smt = fork ? pl->stream_mt : st;
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(pl->ev_mt[0], st));
+    CUDA_TRY(cudaStreamWaitEvent(smt, pl->ev_mt[0], 0));
+  }
+  auto enqueue_normals = [&](int it) -> int {
+    const bool last_it = (it + 1 == pl->o.cem_iters);
+    // np.random.normal(size=(n, m, h*A)) (:85) continued from where the previous iteration left the generator
+    MtStateBlock* state_out = last_it ? reinterpret_cast<MtStateBlock*>(pl->out_dev + pl->out_key) : &scratch[it & 1];
+    mt19937_raw_kernel<<<1, kMtRawThreads, 0, smt>>>(state_in->key, &state_in->pos, pl->mt_words, pl->mt_raw);
+    mt19937_gauss_kernel<<<(unsigned)((pl->attempts + 255) / 256), 256, 0, smt>>>(pl->mt_raw, &state_in->pos, pl->attempts, pl->gflags, pl->gvals);
+    const int n_chunks = (int)((pl->attempts + kGaussChunk - 1) / kGaussChunk);
+    CUDA_TRY(cudaMemsetAsync(meta_out + 2 * it, 0xFF, 2 * sizeof(int32_t), smt));                 // attempts consumed = -1 until found
+    mt19937_gauss_count_kernel<<<n_chunks, 256, 0, smt>>>(pl->gflags, pl->attempts, pl->gcounts);
+    mt19937_gauss_scan_kernel<<<1, 1024, 0, smt>>>(pl->gcounts, n_chunks);
+    if (fork && it > 0) CUDA_TRY(cudaStreamWaitEvent(smt, pl->ev_mt[2 * (it - 1) + 2], 0));       // z64 of the previous iteration has been consumed
+    mt19937_gauss_scatter_kernel<<<n_chunks, 256, 0, smt>>>(pl->gflags, pl->gvals, pl->gcounts, pl->attempts, tot, &state_in->has_gauss,
+                                                           &state_in->cached, pl->z64, meta_out + 2 * it, &state_out->cached);
+    if (fork) CUDA_TRY(cudaEventRecord(pl->ev_mt[2 * it + 1], smt));                               // normals of iteration `it` ready
+    mt19937_state_out_kernel<<<1, 256, 0, smt>>>(pl->mt_raw, &state_in->pos, 0, meta_out + 2 * it, state_out->key, &state_out->pos);
+    CUDA_TRY(cudaMemcpyAsync(&state_out->has_gauss, meta_out + 2 * it + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, smt));
+    c->launches += 6;
+    state_in = state_out;
+    return L2A_OK;
+  };
+  if (fork) {                                        // iteration 0's draw; iteration i+1's is enqueued as soon as z64 of iteration i is consumed
+    int rc = enqueue_normals(0);
+    if (rc) return rc;
+    if (pl->o.cem_iters == 1) CUDA_TRY(cudaEventRecord(pl->ev_mt[2 * pl->o.cem_iters + 1], smt));
+  }
   for (int it = 0; it < pl->o.cem_iters; ++it) {
     const bool last = (it + 1 == pl->o.cem_iters);
     if (mt) {
-      // np.random.normal(size=(n, m, h*A)) (:85) continued from where the previous iteration left the generator
-      MtStateBlock* state_out = last ? reinterpret_cast<MtStateBlock*>(pl->out_dev + pl->out_key) : &scratch[it & 1];
-      mt19937_raw_kernel<<<1, kMtRawThreads, 0, st>>>(state_in->key, &state_in->pos, pl->mt_words, pl->mt_raw);
-      mt19937_gauss_kernel<<<(unsigned)((pl->attempts + 255) / 256), 256, 0, st>>>(pl->mt_raw, &state_in->pos, pl->attempts, pl->gflags, pl->gvals);
-      const int n_chunks = (int)((pl->attempts + kGaussChunk - 1) / kGaussChunk);
-      CUDA_TRY(cudaMemsetAsync(meta_out + 2 * it, 0xFF, 2 * sizeof(int32_t), st));                 // attempts consumed = -1 until found
-      mt19937_gauss_count_kernel<<<n_chunks, 256, 0, st>>>(pl->gflags, pl->attempts, pl->gcounts);
-      mt19937_gauss_scan_kernel<<<1, 1024, 0, st>>>(pl->gcounts, n_chunks);
-      mt19937_gauss_scatter_kernel<<<n_chunks, 256, 0, st>>>(pl->gflags, pl->gvals, pl->gcounts, pl->attempts, tot, &state_in->has_gauss,
-                                                             &state_in->cached, pl->z64, meta_out + 2 * it, &state_out->cached);
-      mt19937_state_out_kernel<<<1, 256, 0, st>>>(pl->mt_raw, &state_in->pos, 0, meta_out + 2 * it, state_out->key, &state_out->pos);
-      CUDA_TRY(cudaMemcpyAsync(&state_out->has_gauss, meta_out + 2 * it + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-      c->launches += 6;
-      state_in = state_out;
+      if (fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_mt[2 * it + 1], 0));
+      else { int rc = enqueue_normals(it); if (rc) return rc; }
     } else {
       sample_normal_kernel<<<(unsigned)((tot + 4 * 256 - 1) / (4 * 256)), 256, 0, st>>>(pl->z64, tot, pl->o.seed, call_dev, (uint32_t)it);
       c->launches++;
@@ -1220,6 +1254,14 @@ static int plan_enqueue_cem(l2a_ctx* c, l2a_plan* pl) {
     cem_sample64_kernel<<<blocks, 256, 0, st>>>(pl->z64, mean, std_, clip_low, clip_high, n, mm, ha, A, pl->actions, pl->clipped, pl->first64);   // :86-87
     c->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (fork) {
+      CUDA_TRY(cudaEventRecord(pl->ev_mt[2 * it + 2], st));                                          // z64 consumed
+      if (!last) {                                                                                   // next iteration's draw, beside this iteration's K1
+        int rc2 = enqueue_normals(it + 1);
+        if (rc2) return rc2;
+        if (it + 2 == pl->o.cem_iters) CUDA_TRY(cudaEventRecord(pl->ev_mt[2 * pl->o.cem_iters + 1], smt));
+      }
+    }
     int rc = l2a_rollout(c, pl->model, &pl->p, reinterpret_cast<const float*>(pl->in_dev), pl->actions, pl->consts + 2 * A, pl->returns,
                          best_ret, best_idx, best_act, st);                                          // :88-100
     if (rc) return rc;
@@ -1235,6 +1277,7 @@ static int plan_enqueue_cem(l2a_ctx* c, l2a_plan* pl) {
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
   }
+  if (fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_mt[2 * pl->o.cem_iters + 1], 0));                 // join: the generator chain is complete
   CUDA_TRY(cudaMemcpyAsync(pl->out_dev + pl->out_mean, mean, sizeof(double) * 2 * (size_t)mm * ha, cudaMemcpyDeviceToDevice, st));
   return L2A_OK;
 }
