@@ -145,3 +145,41 @@ def test_cta_pair_plan_and_tile_choice_of_the_baseline_configs():
     assert _plan2(20, 6, (128, 128), 300, 1, 1)[1][0] == 0
     assert _plan2(20, 6, (512, 512), 300, 1, 9)[1][0] == 0
     assert _plan2(20, 6, (), 300, 1, 1)[0] == -1
+
+
+def test_product_library_carries_the_blackwell_instructions():
+    """The built sm_100a library, disassembled: every tensor-core rollout kernel issues tcgen05.mma (UTCHMMA) with its commit
+    (UTCBAR) and tcgen05.ld (LDTM); the CTA-pair kernel fetches its weight tiles through tensor-map TMA (UTMALDG), the single-CTA
+    and the recurrent kernel through bulk TMA copies (UBLKCP)."""
+    import shutil
+    import subprocess
+    from learning_to_adapt_b200.build import LIB_PATH, build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    build()
+    sass = subprocess.run([cuobjdump, "-sass", LIB_PATH], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert "arch = sm_100a" in sass
+    census = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            census[name] = {}
+            continue
+        if name is None:
+            continue
+        m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m:
+            census[name][m.group(1)] = census[name].get(m.group(1), 0) + 1
+    def kernels(tag):
+        found = {k: v for k, v in census.items() if tag in k}
+        assert found, "no %s kernel in the library" % tag
+        return found
+    for tag, tma in (("rollout_tc2_kernel", "UTMALDG"), ("rollout_tc_kernel", "UBLKCP"), ("rollout_rnn_tc_kernel", "UBLKCP")):
+        for k, ops in kernels(tag).items():
+            assert ops.get("UTCHMMA", 0) >= 30, (k, ops.get("UTCHMMA"))
+            assert ops.get("UTCBAR", 0) >= 1 and ops.get("LDTM", 0) >= 1 and ops.get(tma, 0) >= 1, k
+            assert ops.get("SYNCS", 0) >= 10, k                      # mbarrier pipeline
+    assert len(kernels("rollout_tc2_kernel")) >= 8                    # NC in {32, 48, 72, 80} x two state-register instances
