@@ -26,6 +26,9 @@ Pinning status (see DESIGN.md "Oracle"):
     rule (mean of the E predicted deltas) is this build's definition.
   * device candidate sampler (Philox4x32-10, throughput mode only; the reference draws with numpy's MT19937,
     which the parity mode keeps)             -- PINNED to Random123's published known-answer vectors.
+  * numpy's legacy stream itself (MT19937 refill, ``uniform``, polar ``normal``; third-party: numpy, pinned 1.15.1 upstream)
+                                           -- ``oracle/mt19937_oracle.py``, PINNED against numpy bit for bit
+    (``tests/test_mt19937_oracle_cpu.py``); on the GPU the device generator is compared with numpy directly.
 """
 from collections import OrderedDict
 
